@@ -1,0 +1,152 @@
+/*
+ * dgs_b200.h -- C ABI of libdgs_b200.so: the B200-native (sm_100a) hot path of Open-DiffusionGS.
+ *
+ * Plain C: raw DEVICE pointers, sizes, a cudaStream_t passed as void*.  No torch types, no C++
+ * exceptions cross this boundary; every entry point returns a status code and
+ * dgs_last_error() gives the message.  Each entry point cites the reference interface it
+ * replaces (paths relative to the reference repo; DGR = submodules/diff-gaussian-rasterization).
+ *
+ * All kernels are enqueued on the caller's stream.  Only the rasterizer forward synchronises
+ * that stream once (to read the instance count R that sizes the binning arena), exactly like
+ * the reference's cudaMemcpy at DGR/cuda_rasterizer/rasterizer_impl.cu:281 -- but ONCE PER BATCH
+ * of (sample, view) pairs instead of once per view.
+ */
+#ifndef DGS_B200_H_INCLUDED
+#define DGS_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGS_VERSION 100
+
+typedef enum {
+  DGS_OK = 0,
+  DGS_ERR_INVALID_ARGUMENT = 1, /* replaces AT_ERROR / std::runtime_error, rasterize_points.cu:57-59 */
+  DGS_ERR_CUDA = 2,             /* replaces CHECK_CUDA's throw, auxiliary.h:166-173 */
+  DGS_ERR_ALLOC = 3,            /* allocator callback returned NULL */
+  DGS_ERR_OVERFLOW = 4          /* instance count does not fit 32 bits */
+} dgs_status;
+
+/* Arena allocator callback: must return DEVICE memory of at least `bytes` bytes (256-B aligned)
+ * that stays valid until the matching backward has run.  Replaces the reference's
+ * std::function<char*(size_t)> resize callbacks (DGR/cuda_rasterizer/rasterizer.h:31-34,
+ * DGR/rasterize_points.cu:27-33). */
+typedef void* (*dgs_alloc_fn)(size_t bytes, void* user);
+
+int dgs_version(void);
+const char* dgs_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * B1a. Single-view rasterizer: what `_C.rasterize_gaussians`, `_C.rasterize_gaussians_backward`
+ * and `_C.mark_visible` bind (DGR/ext.cpp:15-19; DGR/rasterize_points.h:18-66;
+ * CudaRasterizer::Rasterizer::{forward,backward,markVisible}, DGR/cuda_rasterizer/rasterizer.h:24-85).
+ * Inputs are the ACTIVATED tensors the reference binding receives (post-exp scales, normalised
+ * quaternions, post-sigmoid opacities).  NULL == "not provided" (the reference's empty tensor).
+ * viewmatrix / projmatrix are the 16 floats of the reference's transposed matrices
+ * (element [4*c + r] = row r, column c; DGR/cuda_rasterizer/auxiliary.h:58-77).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int P;            /* number of Gaussians                     */
+  int D;            /* active SH degree (0..3)                 */
+  int M;            /* SH coefficients per Gaussian in `shs`   */
+  int W, H;         /* image size                              */
+  const float* background;     /* [3]      */
+  const float* means3D;        /* [P,3]    */
+  const float* shs;            /* [P,M,3] or NULL */
+  const float* colors_precomp; /* [P,3]   or NULL */
+  const float* opacities;      /* [P]      */
+  const float* scales;         /* [P,3]   or NULL */
+  const float* rotations;      /* [P,4]   or NULL */
+  const float* cov3D_precomp;  /* [P,6]   or NULL */
+  const float* viewmatrix;     /* [16]     */
+  const float* projmatrix;     /* [16]     */
+  const float* campos;         /* [3]      */
+  float scale_modifier;
+  float tan_fovx, tan_fovy;
+  int prefiltered;  /* accepted for signature parity; culled points are skipped either way */
+  int debug;        /* non-zero: synchronise and check for CUDA errors after every stage */
+} dgs_raster_args;
+
+/* Sizes of the three opaque arenas (geometry: per Gaussian, binning: per instance, image: per pixel)
+ * -- the equivalents of required<GeometryState/BinningState/ImageState>() (rasterizer_impl.h:67-73). */
+size_t dgs_raster_geom_bytes(int n_views, int P);
+size_t dgs_raster_binning_bytes(long long R);
+size_t dgs_raster_image_bytes(int n_views, int W, int H);
+
+/* Forward (rasterizer_impl.cu:198-336).  out_color [3,H,W] and radii [P] are caller-allocated;
+ * the three arenas are obtained through the callbacks and must be handed back to the backward.
+ * *num_rendered receives R (the reference's return value). */
+int dgs_raster_forward(const dgs_raster_args* args, dgs_alloc_fn geom_alloc, void* geom_user,
+                       dgs_alloc_fn binning_alloc, void* binning_user, dgs_alloc_fn image_alloc,
+                       void* image_user, float* out_color, int* radii, int* num_rendered,
+                       void* stream);
+
+/* Backward (rasterizer_impl.cu:340-434).  The nine gradient buffers are caller-allocated and
+ * ZERO-initialised (rasterize_points.cu:151-159): dL_dmean2D [P,3], dL_dconic [P,2,2],
+ * dL_dopacity [P,1], dL_dcolor [P,3], dL_dmean3D [P,3], dL_dcov3D [P,6], dL_dsh [P,M,3],
+ * dL_dscale [P,3], dL_drot [P,4]. */
+int dgs_raster_backward(const dgs_raster_args* args, int R, const int* radii, const void* geom_buffer,
+                        const void* binning_buffer, const void* image_buffer, const float* dL_dpix,
+                        float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                        float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
+                        float* dL_drot, void* stream);
+
+/* markVisible (rasterizer_impl.cu:54-66,141-153): present[i] = view-space z > 0.2 */
+int dgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * B1b. Batched renderer: one call for ALL (sample, view) pairs of `Renderer.forward`
+ * (diffusionGS/models/gsrenderer/renderer.py:34-92) = DeferredGaussianRender.forward/backward
+ * (gs_core.py:949-1060) + render_opencv_cam (874-945) + Camera (277-316) + the GaussianModel
+ * activations (330-334,545-570), fused.  Inputs are the RAW per-sample parameter tensors
+ * (fp32, contiguous): xyz [B,P,3], features [B,P,M,3], scaling [B,P,3], rotation [B,P,4],
+ * opacity [B,P,1], C2W [B,V,4,4] row-major, fxfycxcy [B,V,4].  Output [B,V,3,H,W].
+ * The forward keeps its sorted tile lists in the arenas; the backward re-uses them (no re-render,
+ * unlike gs_core.py:1041-1056) and returns gradients w.r.t. the raw tensors, summed over views.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, V, P, M, D, W, H;
+  const float* xyz;
+  const float* features;
+  const float* scaling;
+  const float* rotation;
+  const float* opacity;
+  const float* c2w;
+  const float* fxfycxcy;
+  float scale_modifier; /* 1.0 when the reference passes scaling_modifier=None */
+  float bg[3];          /* (1,1,1) in render_opencv_cam, gs_core.py:880 */
+  int debug;
+} dgs_render_batch_args;
+
+int dgs_render_batch_forward(const dgs_render_batch_args* args, dgs_alloc_fn geom_alloc, void* geom_user,
+                             dgs_alloc_fn binning_alloc, void* binning_user, dgs_alloc_fn image_alloc,
+                             void* image_user, float* out_images, long long* num_rendered,
+                             void* stream);
+
+/* d_* are caller-allocated, same shapes as the inputs; they are fully overwritten.  scratch_alloc
+ * provides the per-(view, Gaussian) screen-space gradient records (44 B each), free after the call. */
+int dgs_render_batch_backward(const dgs_render_batch_args* args, long long R, const void* geom_buffer,
+                              const void* binning_buffer, const void* image_buffer,
+                              const float* dL_dimages, float* d_xyz, float* d_features,
+                              float* d_scaling, float* d_rotation, float* d_opacity,
+                              dgs_alloc_fn scratch_alloc, void* scratch_user, void* stream);
+
+/* Introspection used by the parity tests: copies of per-(view, Gaussian) / per-pixel forward state
+ * out of the opaque arenas into caller DEVICE buffers (any may be NULL):
+ * xy [N,2], depth [N], conic_opacity [N,4], rgb [N,3], tiles_touched [N] (N = n_views*P),
+ * point_list [R], ranges [n_views*tiles,2], final_T / n_contrib [n_views*H*W]. */
+int dgs_raster_export_state(int n_views, int P, int W, int H, long long R, const void* geom_buffer,
+                            const void* binning_buffer, const void* image_buffer, float* xy,
+                            float* depth, float* conic_opacity, float* rgb, uint32_t* tiles_touched,
+                            uint32_t* point_list, uint32_t* ranges, float* final_T,
+                            uint32_t* n_contrib, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGS_B200_H_INCLUDED */

@@ -1,0 +1,1245 @@
+// raster.cu -- batched differentiable 3D-Gaussian-splatting rasterizer for sm_100a (B200).
+//
+// One launch set renders ALL (sample, view) pairs of a step: projection -> scan -> key emission ->
+// one global radix sort keyed (view, tile, depth) -> tile ranges -> per-tile alpha blend; the backward
+// walks the SAME sorted tile lists back-to-front (no re-render), reduces gradients inside the warp and
+// the CTA before touching global memory, and folds camera construction and the exp / normalize /
+// sigmoid activations (and their Jacobians) into the per-Gaussian kernels.
+//
+// Numerical specification = the reference rasterizer (DGR = submodules/diff-gaussian-rasterization):
+//   projection   DGR/cuda_rasterizer/forward.cu:155-256, auxiliary.h:41-95,139-164
+//   binning      DGR/cuda_rasterizer/rasterizer_impl.cu:70-138,277-317 (stable (tile,depth) order)
+//   blend fwd    DGR/cuda_rasterizer/forward.cu:261-374
+//   blend bwd    DGR/cuda_rasterizer/backward.cu:399-557
+//   geometry bwd DGR/cuda_rasterizer/backward.cu:20-139,144-274,278-396
+//   camera/activations  diffusionGS/models/gsrenderer/gs_core.py:277-316,330-334,545-570,874-945
+// This file is an independent implementation (SoA float4 state, no glm, batched, fused); it shares
+// only the math with the reference.
+#include <cub/cub.cuh>
+
+#include <cstring>
+
+#include "dgs_internal.h"
+
+namespace dgs {
+
+constexpr int TILE = 16;            // DGR/cuda_rasterizer/config.h:16-17
+constexpr int TILE_PIX = TILE * TILE;
+constexpr float NEAR_Z = 0.2f;      // auxiliary.h:154
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr float T_EPS = 0.0001f;
+
+struct Camera {
+  float view[16];  // [4c+r] = W2C[r][c]
+  float proj[16];  // [4c+r] = (P W2C)[r][c]
+  float campos[3];
+  float tanx, tany, fx, fy;
+  float pad;
+};
+
+struct Problem {
+  int NV, V, P, D, M, W, H, gx, gy, tiles;
+  int raw;  // 1: inputs are raw renderer tensors -> apply exp / normalize / sigmoid in-kernel
+  float mod;
+  const float* means;
+  const float* shs;
+  const float* colors_pre;
+  const float* opac;
+  const float* scales;
+  const float* rots;
+  const float* cov_pre;
+  float bg[3];
+};
+
+struct GeomState {
+  float4* g0;        // {x_pix, y_pix, depth, radius (int bits)}
+  float4* g1;        // {conic A, B, C, opacity}
+  float4* g2;        // {r, g, b, clamped bits}
+  uint32_t* tiles;   // tiles touched
+  uint32_t* offsets; // inclusive scan of tiles
+  Camera* cams;
+  void* scan_temp;
+  size_t scan_bytes;
+  static GeomState carve(void* base, int NV, int P, size_t* total) {
+    GeomState s;
+    Carver c(base);
+    size_t N = (size_t)NV * P;
+    s.g0 = c.take<float4>(N);
+    s.g1 = c.take<float4>(N);
+    s.g2 = c.take<float4>(N);
+    s.tiles = c.take<uint32_t>(N);
+    s.offsets = c.take<uint32_t>(N);
+    s.cams = c.take<Camera>(NV);
+    s.scan_bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, s.scan_bytes, s.tiles, s.offsets, (int)N);
+    s.scan_temp = c.take<char>(s.scan_bytes);
+    if (total) *total = c.bytes();
+    return s;
+  }
+};
+
+struct BinState {
+  uint64_t* keys_in;
+  uint64_t* keys;
+  uint32_t* vals_in;
+  uint32_t* point_list;
+  void* sort_temp;
+  size_t sort_bytes;
+  static BinState carve(void* base, long long R, size_t* total) {
+    BinState s;
+    Carver c(base);
+    size_t n = (size_t)(R > 0 ? R : 1);
+    s.point_list = c.take<uint32_t>(n);
+    s.keys = c.take<uint64_t>(n);
+    s.keys_in = c.take<uint64_t>(n);
+    s.vals_in = c.take<uint32_t>(n);
+    s.sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, s.sort_bytes, s.keys_in, s.keys, s.vals_in, s.point_list, (int)n);
+    s.sort_temp = c.take<char>(s.sort_bytes);
+    if (total) *total = c.bytes();
+    return s;
+  }
+};
+
+struct ImgState {
+  float* final_T;
+  uint32_t* n_contrib;
+  uint2* ranges;
+  static ImgState carve(void* base, int NV, int W, int H, size_t* total) {
+    ImgState s;
+    Carver c(base);
+    size_t npix = (size_t)NV * W * H;
+    size_t ntiles = (size_t)NV * ceil_div(W, TILE) * ceil_div(H, TILE);
+    s.final_T = c.take<float>(npix);
+    s.n_contrib = c.take<uint32_t>(npix);
+    s.ranges = c.take<uint2>(ntiles);
+    if (total) *total = c.bytes();
+    return s;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// device math shared by forward and backward
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ndc_to_pix(float v, int S) {
+  // auxiliary.h:41-44: the reference's literals are double, so this is evaluated in fp64
+  return (float)((((double)v + 1.0) * (double)S - 1.0) * 0.5);
+}
+
+__device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx, int gy, int& x0,
+                                          int& y0, int& x1, int& y1) {  // auxiliary.h:46-56
+  x0 = min(gx, max(0, (int)((px - radius) / TILE)));
+  y0 = min(gy, max(0, (int)((py - radius) / TILE)));
+  x1 = min(gx, max(0, (int)((px + radius + TILE - 1) / TILE)));
+  y1 = min(gy, max(0, (int)((py + radius + TILE - 1) / TILE)));
+}
+
+__device__ __forceinline__ float3 xform43(const float* m, float3 p) {
+  return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                     m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+}
+__device__ __forceinline__ float4 xform44(const float* m, float3 p) {
+  return make_float4(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                     m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14], m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]);
+}
+
+__device__ __forceinline__ void quat_to_rot(float4 q, float R[3][3]) {  // (r,x,y,z), not re-normalised
+  float r = q.x, x = q.y, y = q.z, z = q.w;
+  R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
+  R[1][0] = 2.f * (x * y + r * z); R[1][1] = 1.f - 2.f * (x * x + z * z); R[1][2] = 2.f * (y * z - r * x);
+  R[2][0] = 2.f * (x * z - r * y); R[2][1] = 2.f * (y * z + r * x); R[2][2] = 1.f - 2.f * (x * x + y * y);
+}
+
+// Sigma = Rq diag(mod*s)^2 Rq^T, upper triangle (forward.cu:118-152)
+__device__ __forceinline__ void cov3d_from_scale_rot(float3 s, float mod, float4 q, float c6[6]) {
+  float R[3][3], M[3][3];
+  quat_to_rot(q, R);
+  float sv[3] = {mod * s.x, mod * s.y, mod * s.z};
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) M[i][j] = sv[i] * R[j][i];
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = a; b < 3; b++) c6[k++] = M[0][a] * M[0][b] + M[1][a] * M[1][b] + M[2][a] * M[2][b];
+}
+
+struct Ewa {
+  float A[2][3];  // J * Rw (screen-space Jacobian times world->view rotation)
+  float3 t;       // view-space mean, x/y clamped to the 1.3*tanfov frustum
+  float txtz, tytz, limx, limy;
+};
+
+__device__ __forceinline__ void ewa_setup(float3 mean, const Camera& cam, Ewa& e) {  // forward.cu:74-97
+  e.t = xform43(cam.view, mean);
+  e.limx = 1.3f * cam.tanx;
+  e.limy = 1.3f * cam.tany;
+  e.txtz = e.t.x / e.t.z;
+  e.tytz = e.t.y / e.t.z;
+  e.t.x = fminf(e.limx, fmaxf(-e.limx, e.txtz)) * e.t.z;
+  e.t.y = fminf(e.limy, fmaxf(-e.limy, e.tytz)) * e.t.z;
+  float tz = e.t.z;
+  float j00 = cam.fx / tz, j02 = -(cam.fx * e.t.x) / (tz * tz);
+  float j11 = cam.fy / tz, j12 = -(cam.fy * e.t.y) / (tz * tz);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    e.A[0][k] = cam.view[4 * k + 0] * j00 + cam.view[4 * k + 2] * j02;
+    e.A[1][k] = cam.view[4 * k + 1] * j11 + cam.view[4 * k + 2] * j12;
+  }
+}
+
+__device__ __forceinline__ void sym6(const float c[6], float V[3][3]) {
+  V[0][0] = c[0]; V[0][1] = V[1][0] = c[1]; V[0][2] = V[2][0] = c[2];
+  V[1][1] = c[3]; V[1][2] = V[2][1] = c[4]; V[2][2] = c[5];
+}
+
+__device__ __forceinline__ void cov2d(const Ewa& e, const float c6[6], float& a, float& b, float& c) {
+  float V[3][3], va0[3], va1[3];
+  sym6(c6, V);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    va0[k] = V[k][0] * e.A[0][0] + V[k][1] * e.A[0][1] + V[k][2] * e.A[0][2];
+    va1[k] = V[k][0] * e.A[1][0] + V[k][1] * e.A[1][1] + V[k][2] * e.A[1][2];
+  }
+  a = e.A[0][0] * va0[0] + e.A[0][1] * va0[1] + e.A[0][2] * va0[2] + 0.3f;  // forward.cu:110-111
+  b = e.A[0][0] * va1[0] + e.A[0][1] * va1[1] + e.A[0][2] * va1[2];
+  c = e.A[1][0] * va1[0] + e.A[1][1] * va1[1] + e.A[1][2] * va1[2] + 0.3f;
+}
+
+// real SH basis (degree <= 3) and its gradient w.r.t. the unit direction; public constants.
+__constant__ float kSH1 = 0.4886025119029199f;
+__constant__ float kSH2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                              -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float kSH3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                              0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                              -0.5900435899266435f};
+constexpr float kSH0 = 0.28209479177387814f;
+
+template <bool GRAD>
+__device__ inline void sh_basis(int deg, float x, float y, float z, float b[16], float db[16][3]) {
+  if (GRAD) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) db[k][0] = db[k][1] = db[k][2] = 0.f;
+  }
+  b[0] = kSH0;
+  if (deg > 0) {
+    b[1] = -kSH1 * y; b[2] = kSH1 * z; b[3] = -kSH1 * x;
+    if (GRAD) { db[1][1] = -kSH1; db[2][2] = kSH1; db[3][0] = -kSH1; }
+  }
+  if (deg > 1) {
+    float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = kSH2[0] * xy; b[5] = kSH2[1] * yz; b[6] = kSH2[2] * (2.0f * zz - xx - yy);
+    b[7] = kSH2[3] * xz; b[8] = kSH2[4] * (xx - yy);
+    if (GRAD) {
+      db[4][0] = kSH2[0] * y; db[4][1] = kSH2[0] * x;
+      db[5][1] = kSH2[1] * z; db[5][2] = kSH2[1] * y;
+      db[6][0] = kSH2[2] * 2.f * -x; db[6][1] = kSH2[2] * 2.f * -y; db[6][2] = kSH2[2] * 2.f * 2.f * z;
+      db[7][0] = kSH2[3] * z; db[7][2] = kSH2[3] * x;
+      db[8][0] = kSH2[4] * 2.f * x; db[8][1] = kSH2[4] * 2.f * -y;
+    }
+    if (deg > 2) {
+      b[9] = kSH3[0] * y * (3.0f * xx - yy);
+      b[10] = kSH3[1] * xy * z;
+      b[11] = kSH3[2] * y * (4.0f * zz - xx - yy);
+      b[12] = kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+      b[13] = kSH3[4] * x * (4.0f * zz - xx - yy);
+      b[14] = kSH3[5] * z * (xx - yy);
+      b[15] = kSH3[6] * x * (xx - 3.0f * yy);
+      if (GRAD) {
+        db[9][0] = kSH3[0] * 3.f * 2.f * xy; db[9][1] = kSH3[0] * 3.f * (xx - yy);
+        db[10][0] = kSH3[1] * yz; db[10][1] = kSH3[1] * xz; db[10][2] = kSH3[1] * xy;
+        db[11][0] = kSH3[2] * -2.f * xy; db[11][1] = kSH3[2] * (-3.f * yy + 4.f * zz - xx); db[11][2] = kSH3[2] * 4.f * 2.f * yz;
+        db[12][0] = kSH3[3] * -3.f * 2.f * xz; db[12][1] = kSH3[3] * -3.f * 2.f * yz; db[12][2] = kSH3[3] * 3.f * (2.f * zz - xx - yy);
+        db[13][0] = kSH3[4] * (-3.f * xx + 4.f * zz - yy); db[13][1] = kSH3[4] * -2.f * xy; db[13][2] = kSH3[4] * 4.f * 2.f * xz;
+        db[14][0] = kSH3[5] * 2.f * xz; db[14][1] = kSH3[5] * -2.f * yz; db[14][2] = kSH3[5] * (xx - yy);
+        db[15][0] = kSH3[6] * 3.f * (xx - yy); db[15][1] = kSH3[6] * -3.f * 2.f * xy;
+      }
+    }
+  }
+}
+
+// Activations of the reference's GaussianModel (gs_core.py:330-334,545-570)
+__device__ __forceinline__ float3 act_scale(float3 s) { return make_float3(expf(s.x), expf(s.y), expf(s.z)); }
+__device__ __forceinline__ float act_opacity(float o) { return 1.0f / (1.0f + expf(-o)); }
+__device__ __forceinline__ float4 act_rot(float4 q, float* inv_norm) {  // F.normalize, eps 1e-12
+  float n = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  float inv = 1.0f / fmaxf(n, 1e-12f);
+  if (inv_norm) *inv_norm = inv;
+  return make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+}
+
+__device__ __forceinline__ float3 ld3(const float* p, size_t i) { return make_float3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+__device__ __forceinline__ float4 ld4(const float* p, size_t i) {
+  return *reinterpret_cast<const float4*>(p + 4 * i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cameras
+// ---------------------------------------------------------------------------------------------
+// Batched: Camera(C2W, fxfycxcy, h, w) of gs_core.py:277-316, one thread per view.
+__global__ void build_cameras_kernel(int NV, const float* __restrict__ c2w, const float* __restrict__ fxfycxcy,
+                                     int W, int H, Camera* __restrict__ cams) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= NV) return;
+  // general 4x4 inverse (torch `C2W.inverse()`), Gauss-Jordan with partial pivoting in fp64
+  double a[4][8];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      a[r][c] = (double)c2w[16 * v + 4 * r + c];
+      a[r][4 + c] = (r == c) ? 1.0 : 0.0;
+    }
+  for (int col = 0; col < 4; col++) {
+    int piv = col;
+    double best = fabs(a[col][col]);
+    for (int r = col + 1; r < 4; r++)
+      if (fabs(a[r][col]) > best) { best = fabs(a[r][col]); piv = r; }
+    if (piv != col)
+      for (int c = 0; c < 8; c++) { double t = a[col][c]; a[col][c] = a[piv][c]; a[piv][c] = t; }
+    double inv = 1.0 / a[col][col];
+    for (int c = 0; c < 8; c++) a[col][c] *= inv;
+    for (int r = 0; r < 4; r++)
+      if (r != col) {
+        double f = a[r][col];
+        for (int c = 0; c < 8; c++) a[r][c] -= f * a[col][c];
+      }
+  }
+  float w2c[4][4];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) w2c[r][c] = (float)a[r][4 + c];
+  const float fx = fxfycxcy[4 * v + 0], fy = fxfycxcy[4 * v + 1], cx = fxfycxcy[4 * v + 2], cy = fxfycxcy[4 * v + 3];
+  const float zn = 0.01f, zf = 100.0f;  // gs_core.py:286-287
+  float Pm[4][4] = {{0}};
+  Pm[0][0] = 2 * fx / W;
+  Pm[1][1] = 2 * fy / H;
+  Pm[0][2] = 2 * (cx / W) - 1;
+  Pm[1][2] = 2 * (cy / H) - 1;
+  Pm[2][2] = -(zf + zn) / (zf - zn);
+  Pm[3][2] = 1.0f;
+  Pm[2][3] = -(2 * zf * zn) / (zf - zn);
+  Camera cam;
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      cam.view[4 * c + r] = w2c[r][c];
+      float s = 0.f;
+      for (int k = 0; k < 4; k++) s += Pm[r][k] * w2c[k][c];
+      cam.proj[4 * c + r] = s;
+    }
+  cam.campos[0] = c2w[16 * v + 3];
+  cam.campos[1] = c2w[16 * v + 7];
+  cam.campos[2] = c2w[16 * v + 11];
+  cam.tanx = W / (2 * fx);
+  cam.tany = H / (2 * fy);
+  cam.fx = W / (2.0f * cam.tanx);  // rasterizer_impl.cu:222-223
+  cam.fy = H / (2.0f * cam.tany);
+  cam.pad = 0.f;
+  cams[v] = cam;
+}
+
+// Single view: matrices already on the device (GaussianRasterizationSettings), tan(fov) from the host.
+__global__ void pack_camera_kernel(const float* __restrict__ view, const float* __restrict__ proj,
+                                   const float* __restrict__ campos, float tanx, float tany, int W, int H,
+                                   Camera* __restrict__ cam) {
+  int t = threadIdx.x;
+  if (t < 16) { cam->view[t] = view[t]; cam->proj[t] = proj[t]; }
+  if (t < 3) cam->campos[t] = campos[t];
+  if (t == 0) {
+    cam->tanx = tanx; cam->tany = tany;
+    cam->fx = W / (2.0f * tanx); cam->fy = H / (2.0f * tany);
+    cam->pad = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: projection, one thread per (view, Gaussian)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) project_kernel(Problem pb, GeomState gs, int* __restrict__ radii_out) {
+  __shared__ Camera cam;
+  const int view = blockIdx.y;
+  {
+    const float* src = reinterpret_cast<const float*>(gs.cams + view);
+    float* dst = reinterpret_cast<float*>(&cam);
+    for (int t = threadIdx.x; t < (int)(sizeof(Camera) / 4); t += blockDim.x) dst[t] = src[t];
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pb.P) return;
+  const size_t n = (size_t)view * pb.P + i;
+  const size_t si = (size_t)(view / pb.V) * pb.P + i;  // index into the per-sample parameter tensors
+
+  uint32_t tiles = 0;
+  float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0;
+  int radius_i = 0;
+  do {
+    const float3 p = ld3(pb.means, si);
+    const float3 pv = xform43(cam.view, p);
+    if (pv.z <= NEAR_Z) break;  // in_frustum, auxiliary.h:139-164
+    const float4 ph = xform44(cam.proj, p);
+    const float pw = 1.0f / (ph.w + 0.0000001f);
+    const float projx = ph.x * pw, projy = ph.y * pw;
+
+    float c6[6];
+    if (pb.cov_pre) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) c6[k] = pb.cov_pre[6 * si + k];
+    } else {
+      float3 s = ld3(pb.scales, si);
+      float4 q = ld4(pb.rots, si);
+      if (pb.raw) { s = act_scale(s); q = act_rot(q, nullptr); }
+      cov3d_from_scale_rot(s, pb.mod, q, c6);
+    }
+    Ewa e;
+    ewa_setup(p, cam, e);
+    float a, b, c;
+    cov2d(e, c6, a, b, c);
+    const float det = a * c - b * b;
+    if (det == 0.0f) break;
+    const float det_inv = 1.f / det;
+    const float mid = 0.5f * (a + c);
+    const float l1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+    const float l2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+    const float radius = ceilf(3.f * sqrtf(fmaxf(l1, l2)));
+    const float px = ndc_to_pix(projx, pb.W), py = ndc_to_pix(projy, pb.H);
+    int x0, y0, x1, y1;
+    tile_rect(px, py, (int)radius, pb.gx, pb.gy, x0, y0, x1, y1);
+    if ((x1 - x0) * (y1 - y0) == 0) break;
+
+    float rgb[3];
+    int clamped = 0;
+    if (pb.colors_pre) {
+      rgb[0] = pb.colors_pre[3 * si]; rgb[1] = pb.colors_pre[3 * si + 1]; rgb[2] = pb.colors_pre[3 * si + 2];
+    } else {
+      const float* sh = pb.shs + si * pb.M * 3;
+      if (pb.D == 0) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) rgb[ch] = kSH0 * sh[ch];
+      } else {
+        float dx = p.x - cam.campos[0], dy = p.y - cam.campos[1], dz = p.z - cam.campos[2];
+        float len = sqrtf(dx * dx + dy * dy + dz * dz);
+        float bs[16];
+        sh_basis<false>(pb.D, dx / len, dy / len, dz / len, bs, nullptr);
+        const int nb = (pb.D + 1) * (pb.D + 1);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) rgb[ch] = 0.f;
+        for (int k = 0; k < nb; k++)
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) rgb[ch] += bs[k] * sh[3 * k + ch];
+      }
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        rgb[ch] += 0.5f;
+        if (rgb[ch] < 0.f) clamped |= (1 << ch);
+        rgb[ch] = fmaxf(rgb[ch], 0.0f);
+      }
+    }
+    float op = pb.opac[si];
+    if (pb.raw) op = act_opacity(op);
+    radius_i = (int)radius;
+    o0 = make_float4(px, py, pv.z, __int_as_float(radius_i));
+    o1 = make_float4(c * det_inv, -b * det_inv, a * det_inv, op);
+    o2 = make_float4(rgb[0], rgb[1], rgb[2], __int_as_float(clamped));
+    tiles = (uint32_t)((y1 - y0) * (x1 - x0));
+  } while (false);
+  gs.g0[n] = o0;
+  gs.g1[n] = o1;
+  gs.g2[n] = o2;
+  gs.tiles[n] = tiles;
+  if (radii_out) radii_out[n] = radius_i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: key emission.  key = ((view * tiles + tile) << 32) | depth bits, value = Gaussian index in its
+// sample.  A warp first handles its lanes' small rects one thread each, then co-operates lane-parallel
+// on every large rect (balanced expansion; the reference's one-thread serial loop is imbalanced).
+// ---------------------------------------------------------------------------------------------
+constexpr int DUP_COOP_THRESHOLD = 32;
+
+__global__ void __launch_bounds__(256) emit_keys_kernel(Problem pb, GeomState gs, uint64_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ vals) {
+  const int view = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool in_range = i < pb.P;
+  const size_t n = (size_t)view * pb.P + (in_range ? i : 0);
+  uint32_t cnt = in_range ? gs.tiles[n] : 0;
+  uint32_t off = 0;
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  uint32_t dbits = 0;
+  if (cnt) {
+    off = (n == 0) ? 0u : gs.offsets[n - 1];
+    float4 g = gs.g0[n];
+    tile_rect(g.x, g.y, __float_as_int(g.w), pb.gx, pb.gy, x0, y0, x1, y1);
+    dbits = __float_as_uint(g.z);
+  }
+  const uint64_t tile_base = (uint64_t)view * pb.tiles;
+  if (cnt && cnt < DUP_COOP_THRESHOLD) {
+    for (int y = y0; y < y1; y++)
+      for (int x = x0; x < x1; x++) {
+        keys[off] = ((tile_base + (uint64_t)(y * pb.gx + x)) << 32) | dbits;
+        vals[off] = (uint32_t)i;
+        off++;
+      }
+  }
+  unsigned big = __ballot_sync(0xffffffffu, cnt >= DUP_COOP_THRESHOLD);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const uint32_t c_ = __shfl_sync(0xffffffffu, cnt, src);
+    const uint32_t o_ = __shfl_sync(0xffffffffu, off, src);
+    const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+    const int bx1 = __shfl_sync(0xffffffffu, x1, src);
+    const uint32_t db = __shfl_sync(0xffffffffu, dbits, src);
+    const uint32_t id = (uint32_t)(i - lane + src);
+    const int w = bx1 - bx0;
+    for (uint32_t t = lane; t < c_; t += 32) {
+      const int y = by0 + (int)(t / w), x = bx0 + (int)(t % w);
+      keys[o_ + t] = ((tile_base + (uint64_t)(y * pb.gx + x)) << 32) | db;
+      vals[o_ + t] = id;
+    }
+  }
+}
+
+// K5: tile ranges from the sorted keys (rasterizer_impl.cu:116-138)
+__global__ void tile_ranges_kernel(long long R, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R) return;
+  uint32_t cur = (uint32_t)(keys[idx] >> 32);
+  if (idx == 0) ranges[cur].x = 0;
+  else {
+    uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+    if (cur != prev) { ranges[prev].y = (uint32_t)idx; ranges[cur].x = (uint32_t)idx; }
+  }
+  if (idx == R - 1) ranges[cur].y = (uint32_t)R;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: per-tile front-to-back alpha blend (forward.cu:261-374), one CTA per (view, tile)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, GeomState gs, ImgState im,
+                                                                 const uint32_t* __restrict__ point_list,
+                                                                 float* __restrict__ out_color) {
+  const int tile_g = blockIdx.x;
+  const int view = tile_g / pb.tiles, tile = tile_g - view * pb.tiles;
+  const int tx = tile % pb.gx, ty = tile / pb.gx;
+  const int lx = threadIdx.x & (TILE - 1), ly = threadIdx.x >> 4;
+  const int x = tx * TILE + lx, y = ty * TILE + ly;
+  const bool inside = x < pb.W && y < pb.H;
+  const float pxf = (float)x, pyf = (float)y;
+  const uint2 range = im.ranges[tile_g];
+  const size_t gbase = (size_t)view * pb.P;
+
+  __shared__ float2 s_xy[TILE_PIX];
+  __shared__ float4 s_co[TILE_PIX];
+  __shared__ float4 s_rgb[TILE_PIX];
+
+  bool done = !inside;
+  float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+  uint32_t contributor = 0, last = 0;
+  int todo = (int)(range.y - range.x);
+  for (uint32_t start = range.x; start < range.y; start += TILE_PIX, todo -= TILE_PIX) {
+    if (__syncthreads_count(done) == TILE_PIX) break;
+    const uint32_t e = start + threadIdx.x;
+    if (e < range.y) {
+      const size_t g = gbase + point_list[e];
+      const float4 a0 = gs.g0[g];
+      s_xy[threadIdx.x] = make_float2(a0.x, a0.y);
+      s_co[threadIdx.x] = gs.g1[g];
+      s_rgb[threadIdx.x] = gs.g2[g];
+    }
+    __syncthreads();
+    const int nb = min(TILE_PIX, todo);
+    for (int j = 0; !done && j < nb; j++) {
+      contributor++;
+      const float2 xy = s_xy[j];
+      const float dx = xy.x - pxf, dy = xy.y - pyf;
+      const float4 co = s_co[j];
+      const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+      if (power > 0.0f) continue;
+      const float alpha = fminf(0.99f, co.w * expf(power));
+      if (alpha < ALPHA_MIN) continue;
+      const float test_T = T * (1 - alpha);
+      if (test_T < T_EPS) { done = true; continue; }
+      const float4 col = s_rgb[j];
+      const float w = alpha * T;
+      C0 += col.x * w; C1 += col.y * w; C2 += col.z * w;
+      T = test_T;
+      last = contributor;
+    }
+  }
+  if (inside) {
+    const size_t pid = (size_t)y * pb.W + x;
+    const size_t ibase = (size_t)view * pb.W * pb.H;
+    im.final_T[ibase + pid] = T;
+    im.n_contrib[ibase + pid] = last;
+    float* oc = out_color + 3 * ibase;
+    const size_t plane = (size_t)pb.W * pb.H;
+    oc[pid] = C0 + T * pb.bg[0];
+    oc[plane + pid] = C1 + T * pb.bg[1];
+    oc[2 * plane + pid] = C2 + T * pb.bg[2];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: per-tile back-to-front gradient replay (backward.cu:399-557).
+// Differences from the reference's data flow (not its math): starts at the deepest contributor of the
+// tile instead of the end of the list; per-(pixel, Gaussian) terms are summed across the warp with
+// shuffles, then across the CTA's 8 warps in shared memory, and only ONE atomic per gradient component
+// per (tile, Gaussian) instance reaches L2 (the reference issues 9 atomics per contributing pair).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int BWD_CHUNK = 64;  // Gaussians staged per round in the backward
+
+__global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(Problem pb, GeomState gs, ImgState im,
+                                                                  const uint32_t* __restrict__ point_list,
+                                                                  const float* __restrict__ dL_dpix,
+                                                                  float* __restrict__ dmean2D /*[N,3]*/,
+                                                                  float* __restrict__ dconic /*[N,4]*/,
+                                                                  float* __restrict__ dopac /*[N]*/,
+                                                                  float* __restrict__ dcolor /*[N,3]*/) {
+  const int tile_g = blockIdx.x;
+  const int view = tile_g / pb.tiles, tile = tile_g - view * pb.tiles;
+  const int tx = tile % pb.gx, ty = tile / pb.gx;
+  const int lx = threadIdx.x & (TILE - 1), ly = threadIdx.x >> 4;
+  const int x = tx * TILE + lx, y = ty * TILE + ly;
+  const bool inside = x < pb.W && y < pb.H;
+  const float pxf = (float)x, pyf = (float)y;
+  const uint2 range = im.ranges[tile_g];
+  const size_t gbase = (size_t)view * pb.P;
+  const size_t ibase = (size_t)view * pb.W * pb.H;
+  const size_t pid = (size_t)y * pb.W + x;
+  const size_t plane = (size_t)pb.W * pb.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  __shared__ uint32_t s_id[BWD_CHUNK];
+  __shared__ float2 s_xy[BWD_CHUNK];
+  __shared__ float4 s_co[BWD_CHUNK];
+  __shared__ float4 s_rgb[BWD_CHUNK];
+  __shared__ float s_acc[BWD_CHUNK][9];  // CTA-level partial sums, 9 components per staged Gaussian
+  __shared__ uint32_t s_max;
+
+  const float T_final = inside ? im.final_T[ibase + pid] : 0.f;
+  const uint32_t last = inside ? im.n_contrib[ibase + pid] : 0u;
+  float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+  if (inside) {
+    const float* d = dL_dpix + 3 * ibase;
+    dp0 = d[pid]; dp1 = d[plane + pid]; dp2 = d[2 * plane + pid];
+  }
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  {
+    uint32_t m = last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) atomicMax(&s_max, m);
+  }
+  __syncthreads();
+  const uint32_t deepest = s_max;  // entries [0, deepest) of this tile's list matter
+  if (deepest == 0) return;
+
+  float T = T_final;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
+  const float bg_dot = pb.bg[0] * dp0 + pb.bg[1] * dp1 + pb.bg[2] * dp2;
+  const float ddelx_dx = 0.5f * pb.W, ddely_dy = 0.5f * pb.H;
+
+  // walk positions deepest-1 ... 0 in chunks; within a chunk slot j holds position (top - j)
+  for (int top = (int)deepest - 1; top >= 0; top -= BWD_CHUNK) {
+    const int nb = min(BWD_CHUNK, top + 1);
+    __syncthreads();  // previous chunk's s_acc fully flushed, staging buffers free
+    if (threadIdx.x < nb) {
+      const uint32_t id = point_list[range.x + (uint32_t)(top - (int)threadIdx.x)];
+      const size_t g = gbase + id;
+      s_id[threadIdx.x] = id;
+      const float4 a0 = gs.g0[g];
+      s_xy[threadIdx.x] = make_float2(a0.x, a0.y);
+      s_co[threadIdx.x] = gs.g1[g];
+      s_rgb[threadIdx.x] = gs.g2[g];
+    }
+    for (int t = threadIdx.x; t < nb * 9; t += TILE_PIX) (&s_acc[0][0])[t] = 0.f;
+    __syncthreads();
+    for (int j = 0; j < nb; j++) {
+      const uint32_t pos = (uint32_t)(top - j);  // 0-based position in the tile list
+      float g_c0 = 0.f, g_c1 = 0.f, g_c2 = 0.f, g_mx = 0.f, g_my = 0.f, g_ca = 0.f, g_cb = 0.f, g_cc = 0.f, g_op = 0.f;
+      bool active = false;
+      if (pos < last) {
+        const float2 xy = s_xy[j];
+        const float dx = xy.x - pxf, dy = xy.y - pyf;
+        const float4 co = s_co[j];
+        const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+        if (power <= 0.0f) {
+          const float G = expf(power);
+          const float alpha = fminf(0.99f, co.w * G);
+          if (alpha >= ALPHA_MIN) {
+            active = true;
+            T = T / (1.f - alpha);
+            const float dch = alpha * T;
+            const float4 col = s_rgb[j];
+            acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = col.x;
+            acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = col.y;
+            acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = col.z;
+            float dL_dalpha = (col.x - acc0) * dp0 + (col.y - acc1) * dp1 + (col.z - acc2) * dp2;
+            g_c0 = dch * dp0; g_c1 = dch * dp1; g_c2 = dch * dp2;
+            dL_dalpha *= T;
+            last_alpha = alpha;
+            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+            const float dL_dG = co.w * dL_dalpha;
+            const float gdx = G * dx, gdy = G * dy;
+            const float dG_ddelx = -gdx * co.x - gdy * co.y;
+            const float dG_ddely = -gdy * co.z - gdx * co.y;
+            g_mx = dL_dG * dG_ddelx * ddelx_dx;
+            g_my = dL_dG * dG_ddely * ddely_dy;
+            g_ca = -0.5f * gdx * dx * dL_dG;
+            g_cb = -0.5f * gdx * dy * dL_dG;
+            g_cc = -0.5f * gdy * dy * dL_dG;
+            g_op = G * dL_dalpha;
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, active)) {
+        g_c0 = warp_sum(g_c0); g_c1 = warp_sum(g_c1); g_c2 = warp_sum(g_c2);
+        g_mx = warp_sum(g_mx); g_my = warp_sum(g_my);
+        g_ca = warp_sum(g_ca); g_cb = warp_sum(g_cb); g_cc = warp_sum(g_cc); g_op = warp_sum(g_op);
+        if (lane == 0) {
+          float* a = s_acc[j];
+          atomicAdd(a + 0, g_mx); atomicAdd(a + 1, g_my); atomicAdd(a + 2, g_ca); atomicAdd(a + 3, g_cb);
+          atomicAdd(a + 4, g_cc); atomicAdd(a + 5, g_op); atomicAdd(a + 6, g_c0); atomicAdd(a + 7, g_c1);
+          atomicAdd(a + 8, g_c2);
+        }
+      }
+    }
+    __syncthreads();
+    // flush: one global atomic per component per staged Gaussian
+    for (int t = threadIdx.x; t < nb * 9; t += TILE_PIX) {
+      const int j = t / 9, c = t - 9 * j;
+      const float v = s_acc[j][c];
+      if (v != 0.f) {
+        const size_t g = gbase + s_id[j];
+        float* dst;
+        switch (c) {
+          case 0: dst = dmean2D + 3 * g; break;
+          case 1: dst = dmean2D + 3 * g + 1; break;
+          case 2: dst = dconic + 4 * g; break;
+          case 3: dst = dconic + 4 * g + 1; break;
+          case 4: dst = dconic + 4 * g + 3; break;
+          case 5: dst = dopac + g; break;
+          default: dst = dcolor + 3 * g + (c - 6); break;
+        }
+        atomicAdd(dst, v);
+      }
+    }
+  }
+  (void)warp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8 + K9 fused, plus (raw mode) the activation Jacobians and the sum over a sample's views.
+// One thread per (sample, Gaussian); loops over that sample's V views.
+// ---------------------------------------------------------------------------------------------
+struct GeomGradOut {
+  float* dmeans;   // [S*P,3]
+  float* dcov3d;   // [S*P,6] or null (single-view API only)
+  float* dsh;      // [S*P,M,3] or null
+  float* dscale;   // [S*P,3] or null
+  float* drot;     // [S*P,4] or null
+  float* dopac_raw;  // [S*P] raw-opacity gradient (batched mode) or null
+};
+
+__global__ void __launch_bounds__(256) geometry_backward_kernel(Problem pb, GeomState gs, const int* __restrict__ radii_in,
+                                                                const float* __restrict__ dmean2D,
+                                                                const float* __restrict__ dconic,
+                                                                const float* __restrict__ dopac,
+                                                                const float* __restrict__ dcolor, GeomGradOut out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  if (i >= pb.P) return;
+  const size_t si = (size_t)s * pb.P + i;
+  const float3 mean = ld3(pb.means, si);
+  float3 scale = make_float3(0.f, 0.f, 0.f);
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f), q_raw = q;
+  float inv_norm = 1.f;
+  float c6[6];
+  const bool has_sr = pb.scales != nullptr;
+  if (has_sr) {
+    scale = ld3(pb.scales, si);
+    q_raw = ld4(pb.rots, si);
+    q = q_raw;
+    if (pb.raw) { scale = act_scale(scale); q = act_rot(q_raw, &inv_norm); }
+  }
+  if (pb.cov_pre) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) c6[k] = pb.cov_pre[6 * si + k];
+  } else {
+    cov3d_from_scale_rot(scale, pb.mod, q, c6);
+  }
+  float V[3][3];
+  sym6(c6, V);
+  const int nb = (pb.D + 1) * (pb.D + 1);
+  const bool sh_general = pb.shs && pb.D > 0;
+  float* dsh_out = (pb.shs && out.dsh) ? out.dsh + si * pb.M * 3 : nullptr;
+  if (sh_general)
+    for (int k = 0; k < pb.M * 3; k++) dsh_out[k] = 0.f;
+
+  float dm[3] = {0.f, 0.f, 0.f}, dc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dsh0[3] = {0.f, 0.f, 0.f};
+  float dop_sum = 0.f;
+
+  for (int v = 0; v < pb.V; v++) {
+    const int view = s * pb.V + v;
+    const size_t n = (size_t)view * pb.P + i;
+    const int radius = radii_in ? radii_in[n] : __float_as_int(gs.g0[n].w);
+    if (!(radius > 0)) continue;
+    const Camera& cam = gs.cams[view];
+    // ---- conic -> cov2D -> cov3D & mean (backward.cu:144-274) ----
+    Ewa e;
+    ewa_setup(mean, cam, e);
+    float a, b, c;
+    cov2d(e, c6, a, b, c);
+    const float xmul = (e.txtz < -e.limx || e.txtz > e.limx) ? 0.f : 1.f;
+    const float ymul = (e.tytz < -e.limy || e.tytz > e.limy) ? 0.f : 1.f;
+    const float dcx = dconic[4 * n], dcy = dconic[4 * n + 1], dcz = dconic[4 * n + 3];
+    const float denom = a * c - b * b;
+    float da = 0.f, db = 0.f, dc = 0.f;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    const float(*A)[3] = e.A;
+    if (denom2inv != 0) {
+      da = denom2inv * (-c * c * dcx + 2 * b * c * dcy + (denom - a * c) * dcz);
+      dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c) * dcx);
+      db = denom2inv * 2 * (b * c * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
+      dc6[0] += A[0][0] * A[0][0] * da + A[0][0] * A[1][0] * db + A[1][0] * A[1][0] * dc;
+      dc6[3] += A[0][1] * A[0][1] * da + A[0][1] * A[1][1] * db + A[1][1] * A[1][1] * dc;
+      dc6[5] += A[0][2] * A[0][2] * da + A[0][2] * A[1][2] * db + A[1][2] * A[1][2] * dc;
+      dc6[1] += 2 * A[0][0] * A[0][1] * da + (A[0][0] * A[1][1] + A[0][1] * A[1][0]) * db + 2 * A[1][0] * A[1][1] * dc;
+      dc6[2] += 2 * A[0][0] * A[0][2] * da + (A[0][0] * A[1][2] + A[0][2] * A[1][0]) * db + 2 * A[1][0] * A[1][2] * dc;
+      dc6[4] += 2 * A[0][2] * A[0][1] * da + (A[0][1] * A[1][2] + A[0][2] * A[1][1]) * db + 2 * A[1][1] * A[1][2] * dc;
+    }
+    float dA0[3], dA1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float va0 = A[0][0] * V[k][0] + A[0][1] * V[k][1] + A[0][2] * V[k][2];
+      const float va1 = A[1][0] * V[k][0] + A[1][1] * V[k][1] + A[1][2] * V[k][2];
+      dA0[k] = 2 * va0 * da + va1 * db;
+      dA1[k] = 2 * va1 * dc + va0 * db;
+    }
+    const float* vm = cam.view;
+    const float dJ00 = vm[0] * dA0[0] + vm[4] * dA0[1] + vm[8] * dA0[2];
+    const float dJ02 = vm[2] * dA0[0] + vm[6] * dA0[1] + vm[10] * dA0[2];
+    const float dJ11 = vm[1] * dA1[0] + vm[5] * dA1[1] + vm[9] * dA1[2];
+    const float dJ12 = vm[2] * dA1[0] + vm[6] * dA1[1] + vm[10] * dA1[2];
+    const float tz = 1.f / e.t.z, tz2 = tz * tz, tz3 = tz2 * tz;
+    const float dtx = xmul * -cam.fx * tz2 * dJ02;
+    const float dty = ymul * -cam.fy * tz2 * dJ12;
+    const float dtz = -cam.fx * tz2 * dJ00 - cam.fy * tz2 * dJ11 + (2 * cam.fx * e.t.x) * tz3 * dJ02 +
+                      (2 * cam.fy * e.t.y) * tz3 * dJ12;
+    float dmv[3];
+    dmv[0] = vm[0] * dtx + vm[1] * dty + vm[2] * dtz;
+    dmv[1] = vm[4] * dtx + vm[5] * dty + vm[6] * dtz;
+    dmv[2] = vm[8] * dtx + vm[9] * dty + vm[10] * dtz;
+    // ---- mean2D -> mean3D (backward.cu:366-387) ----
+    const float* pm = cam.proj;
+    const float4 mh = xform44(pm, mean);
+    const float mw = 1.0f / (mh.w + 0.0000001f);
+    const float mul1 = mh.x * mw * mw, mul2 = mh.y * mw * mw;
+    const float gx2 = dmean2D[3 * n], gy2 = dmean2D[3 * n + 1];
+    dmv[0] += (pm[0] * mw - pm[3] * mul1) * gx2 + (pm[1] * mw - pm[3] * mul2) * gy2;
+    dmv[1] += (pm[4] * mw - pm[7] * mul1) * gx2 + (pm[5] * mw - pm[7] * mul2) * gy2;
+    dmv[2] += (pm[8] * mw - pm[11] * mul1) * gx2 + (pm[9] * mw - pm[11] * mul2) * gy2;
+    // ---- colour -> SH (backward.cu:20-139) ----
+    if (pb.shs) {
+      const int clamped = __float_as_int(gs.g2[n].w);
+      float g[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) g[ch] = dcolor[3 * n + ch] * ((clamped >> ch) & 1 ? 0.f : 1.f);
+      if (!sh_general) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) dsh0[ch] += kSH0 * g[ch];
+      } else {
+        const float ox = mean.x - cam.campos[0], oy = mean.y - cam.campos[1], oz = mean.z - cam.campos[2];
+        const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+        float bs[16], dbs[16][3];
+        sh_basis<true>(pb.D, ox / len, oy / len, oz / len, bs, dbs);
+        const float* sh = pb.shs + si * pb.M * 3;
+        float ddir[3] = {0.f, 0.f, 0.f};
+        for (int k = 0; k < nb; k++) {
+          float dot = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            dsh_out[3 * k + ch] += bs[k] * g[ch];
+            dot += sh[3 * k + ch] * g[ch];
+          }
+#pragma unroll
+          for (int ax = 0; ax < 3; ax++) ddir[ax] += dbs[k][ax] * dot;
+        }
+        const float s2 = ox * ox + oy * oy + oz * oz;  // dnormvdv, auxiliary.h:107-117
+        const float inv32 = 1.0f / sqrtf(s2 * s2 * s2);
+        dmv[0] += ((+s2 - ox * ox) * ddir[0] - oy * ox * ddir[1] - oz * ox * ddir[2]) * inv32;
+        dmv[1] += (-ox * oy * ddir[0] + (s2 - oy * oy) * ddir[1] - oz * oy * ddir[2]) * inv32;
+        dmv[2] += (-ox * oz * ddir[0] - oy * oz * ddir[1] + (s2 - oz * oz) * ddir[2]) * inv32;
+      }
+    }
+    dm[0] += dmv[0]; dm[1] += dmv[1]; dm[2] += dmv[2];
+    dop_sum += dopac[n];
+  }
+
+  out.dmeans[3 * si] = dm[0]; out.dmeans[3 * si + 1] = dm[1]; out.dmeans[3 * si + 2] = dm[2];
+  if (out.dcov3d) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) out.dcov3d[6 * si + k] = dc6[k];
+  }
+  if (dsh_out && !sh_general) {
+    dsh_out[0] = dsh0[0]; dsh_out[1] = dsh0[1]; dsh_out[2] = dsh0[2];
+    for (int k = 3; k < pb.M * 3; k++) dsh_out[k] = 0.f;
+  }
+  if (out.dopac_raw) {
+    const float o = act_opacity(pb.opac[si]);
+    out.dopac_raw[si] = dop_sum * o * (1.f - o);
+  }
+  // ---- cov3D -> scale / rotation (backward.cu:278-341); linear in dL/dcov3D, so the per-view sum is
+  // pushed through once ----
+  if (has_sr && out.dscale) {
+    float R[3][3], Mm[3][3], dS[3][3], dM[3][3], E[3][3];
+    quat_to_rot(q, R);
+    const float sv[3] = {pb.mod * scale.x, pb.mod * scale.y, pb.mod * scale.z};
+#pragma unroll
+    for (int r_ = 0; r_ < 3; r_++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) Mm[r_][k] = sv[r_] * R[k][r_];
+    dS[0][0] = dc6[0]; dS[0][1] = dS[1][0] = 0.5f * dc6[1]; dS[0][2] = dS[2][0] = 0.5f * dc6[2];
+    dS[1][1] = dc6[3]; dS[1][2] = dS[2][1] = 0.5f * dc6[4]; dS[2][2] = dc6[5];
+#pragma unroll
+    for (int r_ = 0; r_ < 3; r_++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) dM[r_][k] = 2.0f * (Mm[r_][0] * dS[0][k] + Mm[r_][1] * dS[1][k] + Mm[r_][2] * dS[2][k]);
+    float dsc[3];
+#pragma unroll
+    for (int r_ = 0; r_ < 3; r_++) dsc[r_] = R[0][r_] * dM[r_][0] + R[1][r_] * dM[r_][1] + R[2][r_] * dM[r_][2];
+#pragma unroll
+    for (int a_ = 0; a_ < 3; a_++)
+#pragma unroll
+      for (int b_ = 0; b_ < 3; b_++) E[a_][b_] = sv[b_] * dM[b_][a_];
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    float dq[4];
+    dq[0] = 2 * z * (E[1][0] - E[0][1]) + 2 * y * (E[0][2] - E[2][0]) + 2 * x * (E[2][1] - E[1][2]);
+    dq[1] = 2 * y * (E[0][1] + E[1][0]) + 2 * z * (E[0][2] + E[2][0]) + 2 * r * (E[2][1] - E[1][2]) - 4 * x * (E[2][2] + E[1][1]);
+    dq[2] = 2 * x * (E[0][1] + E[1][0]) + 2 * r * (E[0][2] - E[2][0]) + 2 * z * (E[2][1] + E[1][2]) - 4 * y * (E[2][2] + E[0][0]);
+    dq[3] = 2 * r * (E[1][0] - E[0][1]) + 2 * x * (E[0][2] + E[2][0]) + 2 * y * (E[2][1] + E[1][2]) - 4 * z * (E[1][1] + E[0][0]);
+    if (pb.raw) {
+      // exp: d/ds_raw = d/dscale * scale ; normalize: (dq - q (q.dq)) / max(|q_raw|, eps)
+      dsc[0] *= scale.x; dsc[1] *= scale.y; dsc[2] *= scale.z;
+      const float dot = q.x * dq[0] + q.y * dq[1] + q.z * dq[2] + q.w * dq[3];
+      dq[0] = (dq[0] - q.x * dot) * inv_norm; dq[1] = (dq[1] - q.y * dot) * inv_norm;
+      dq[2] = (dq[2] - q.z * dot) * inv_norm; dq[3] = (dq[3] - q.w * dot) * inv_norm;
+    }
+    out.dscale[3 * si] = dsc[0]; out.dscale[3 * si + 1] = dsc[1]; out.dscale[3 * si + 2] = dsc[2];
+    *reinterpret_cast<float4*>(out.drot + 4 * si) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+  }
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ view,
+                                    uint8_t* __restrict__ present) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float3 pv = xform43(view, ld3(means, i));
+  present[i] = pv.z > NEAR_Z;
+}
+
+__global__ void export_geom_kernel(size_t N, GeomState gs, float* xy, float* depth, float* conic_opacity,
+                                   float* rgb, uint32_t* tiles) {
+  size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float4 a = gs.g0[n], b = gs.g1[n], c = gs.g2[n];
+  bool vis = __float_as_int(a.w) > 0;
+  if (xy) { xy[2 * n] = a.x; xy[2 * n + 1] = a.y; }
+  if (depth) depth[n] = a.z;
+  if (conic_opacity) { conic_opacity[4 * n] = b.x; conic_opacity[4 * n + 1] = b.y; conic_opacity[4 * n + 2] = b.z; conic_opacity[4 * n + 3] = b.w; }
+  if (rgb) { rgb[3 * n] = vis ? c.x : 0.f; rgb[3 * n + 1] = vis ? c.y : 0.f; rgb[3 * n + 2] = vis ? c.z : 0.f; }
+  if (tiles) tiles[n] = gs.tiles[n];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side pipeline
+// ---------------------------------------------------------------------------------------------
+static int bits_for(uint32_t n) {  // smallest b with (n >> b) == 0  (getHigherMsb, rasterizer_impl.cu:35-50)
+  int b = 0;
+  while (b < 32 && (n >> b)) b++;
+  return b;
+}
+
+struct ForwardPlan {
+  Problem pb;
+  GeomState gs;
+  ImgState im;
+  BinState bs;
+  long long R;
+};
+
+static int run_forward(Problem pb, bool build_cams, const float* c2w, const float* fxfycxcy, const float* view,
+                       const float* proj, const float* campos, float tanx, float tany, dgs_alloc_fn geom_alloc,
+                       void* geom_user, dgs_alloc_fn bin_alloc, void* bin_user, dgs_alloc_fn img_alloc,
+                       void* img_user, float* out_color, int* radii, long long* R_out, cudaStream_t st,
+                       int debug) {
+  const size_t N = (size_t)pb.NV * pb.P;
+  DGS_REQUIRE(N < (size_t)INT32_MAX, "n_views * P = %zu does not fit the 32-bit scan", N);
+  size_t gbytes = 0, ibytes = 0;
+  GeomState::carve(nullptr, pb.NV, pb.P, &gbytes);
+  ImgState::carve(nullptr, pb.NV, pb.W, pb.H, &ibytes);
+  void* gbuf = geom_alloc(gbytes, geom_user);
+  void* ibuf = img_alloc(ibytes, img_user);
+  if (!gbuf || !ibuf) { set_error("arena allocator returned NULL"); return DGS_ERR_ALLOC; }
+  GeomState gs = GeomState::carve(gbuf, pb.NV, pb.P, nullptr);
+  ImgState im = ImgState::carve(ibuf, pb.NV, pb.W, pb.H, nullptr);
+
+  if (build_cams) {
+    build_cameras_kernel<<<ceil_div(pb.NV, 64), 64, 0, st>>>(pb.NV, c2w, fxfycxcy, pb.W, pb.H, gs.cams);
+  } else {
+    pack_camera_kernel<<<1, 32, 0, st>>>(view, proj, campos, tanx, tany, pb.W, pb.H, gs.cams);
+  }
+  DGS_LAUNCH_OK(st, debug);
+  dim3 pgrid(ceil_div(pb.P, 256), pb.NV);
+  project_kernel<<<pgrid, 256, 0, st>>>(pb, gs, radii);
+  DGS_LAUNCH_OK(st, debug);
+  DGS_CUDA_OK(cub::DeviceScan::InclusiveSum(gs.scan_temp, gs.scan_bytes, gs.tiles, gs.offsets, (int)N, st));
+  uint32_t R32 = 0;
+  DGS_CUDA_OK(cudaMemcpyAsync(&R32, gs.offsets + N - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  DGS_CUDA_OK(cudaStreamSynchronize(st));  // the one host sync per batch
+  const long long R = (long long)R32;
+  if (R >= (long long)INT32_MAX) { set_error("instance count %lld exceeds 2^31-1", R); return DGS_ERR_OVERFLOW; }
+  *R_out = R;
+
+  size_t bbytes = 0;
+  BinState::carve(nullptr, R, &bbytes);
+  void* bbuf = bin_alloc(bbytes, bin_user);
+  if (!bbuf) { set_error("binning allocator returned NULL"); return DGS_ERR_ALLOC; }
+  BinState bs = BinState::carve(bbuf, R, nullptr);
+
+  const size_t ntiles = (size_t)pb.NV * pb.tiles;
+  DGS_CUDA_OK(cudaMemsetAsync(im.ranges, 0, ntiles * sizeof(uint2), st));
+  if (R > 0) {
+    emit_keys_kernel<<<pgrid, 256, 0, st>>>(pb, gs, bs.keys_in, bs.vals_in);
+    DGS_LAUNCH_OK(st, debug);
+    const int end_bit = 32 + bits_for((uint32_t)ntiles);
+    DGS_CUDA_OK(cub::DeviceRadixSort::SortPairs(bs.sort_temp, bs.sort_bytes, bs.keys_in, bs.keys, bs.vals_in,
+                                                bs.point_list, (int)R, 0, end_bit, st));
+    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, bs.keys, im.ranges);
+    DGS_LAUNCH_OK(st, debug);
+  }
+  blend_forward_kernel<<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bs.point_list, out_color);
+  DGS_LAUNCH_OK(st, debug);
+  return DGS_OK;
+}
+
+static Problem make_problem(int NV, int V, int P, int D, int M, int W, int H, int raw, float mod) {
+  Problem pb;
+  memset(&pb, 0, sizeof(pb));
+  pb.NV = NV; pb.V = V; pb.P = P; pb.D = D; pb.M = M; pb.W = W; pb.H = H;
+  pb.gx = ceil_div(W, TILE); pb.gy = ceil_div(H, TILE); pb.tiles = pb.gx * pb.gy;
+  pb.raw = raw; pb.mod = mod;
+  return pb;
+}
+
+}  // namespace dgs
+
+using namespace dgs;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+size_t dgs_raster_geom_bytes(int n_views, int P) {
+  size_t b = 0;
+  GeomState::carve(nullptr, n_views, P, &b);
+  return b;
+}
+size_t dgs_raster_binning_bytes(long long R) {
+  size_t b = 0;
+  BinState::carve(nullptr, R, &b);
+  return b;
+}
+size_t dgs_raster_image_bytes(int n_views, int W, int H) {
+  size_t b = 0;
+  ImgState::carve(nullptr, n_views, W, H, &b);
+  return b;
+}
+
+static int check_single_args(const dgs_raster_args* a) {
+  DGS_REQUIRE(a != nullptr, "args is NULL");
+  DGS_REQUIRE(a->P >= 0 && a->W > 0 && a->H > 0, "bad sizes P=%d W=%d H=%d", a->P, a->W, a->H);
+  DGS_REQUIRE(a->D >= 0 && a->D <= 3, "SH degree %d not in 0..3", a->D);
+  DGS_REQUIRE((a->shs != nullptr) != (a->colors_precomp != nullptr),
+              "Please provide exactly one of either SHs or precomputed colors!");
+  DGS_REQUIRE(((a->scales != nullptr && a->rotations != nullptr) != (a->cov3D_precomp != nullptr)) &&
+                  ((a->scales != nullptr) == (a->rotations != nullptr)),
+              "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+  DGS_REQUIRE(a->shs == nullptr || a->M >= (a->D + 1) * (a->D + 1), "M=%d too small for SH degree %d", a->M, a->D);
+  return DGS_OK;
+}
+
+static Problem single_problem(const dgs_raster_args* a, float bg[3]) {
+  Problem pb = make_problem(1, 1, a->P, a->D, a->M, a->W, a->H, 0, a->scale_modifier);
+  pb.means = a->means3D; pb.shs = a->shs; pb.colors_pre = a->colors_precomp; pb.opac = a->opacities;
+  pb.scales = a->scales; pb.rots = a->rotations; pb.cov_pre = a->cov3D_precomp;
+  pb.bg[0] = bg[0]; pb.bg[1] = bg[1]; pb.bg[2] = bg[2];
+  return pb;
+}
+
+int dgs_raster_forward(const dgs_raster_args* a, dgs_alloc_fn geom_alloc, void* geom_user, dgs_alloc_fn bin_alloc,
+                       void* bin_user, dgs_alloc_fn img_alloc, void* img_user, float* out_color, int* radii,
+                       int* num_rendered, void* stream) {
+  int rc = check_single_args(a);
+  if (rc) return rc;
+  DGS_REQUIRE(geom_alloc && bin_alloc && img_alloc && out_color && num_rendered, "NULL output/allocator");
+  cudaStream_t st = (cudaStream_t)stream;
+  *num_rendered = 0;
+  if (a->P == 0) return DGS_OK;  // legal: the caller's zero-filled outputs stand (rasterize_points.cu:81)
+  float bg[3];
+  DGS_CUDA_OK(cudaMemcpyAsync(bg, a->background, sizeof(bg), cudaMemcpyDeviceToHost, st));
+  DGS_CUDA_OK(cudaStreamSynchronize(st));
+  Problem pb = single_problem(a, bg);
+  long long R = 0;
+  rc = run_forward(pb, false, nullptr, nullptr, a->viewmatrix, a->projmatrix, a->campos, a->tan_fovx, a->tan_fovy,
+                   geom_alloc, geom_user, bin_alloc, bin_user, img_alloc, img_user, out_color, radii, &R, st,
+                   a->debug);
+  *num_rendered = (int)R;
+  return rc;
+}
+
+int dgs_raster_backward(const dgs_raster_args* a, int R, const int* radii, const void* geom_buffer,
+                        const void* binning_buffer, const void* image_buffer, const float* dL_dpix,
+                        float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                        float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                        void* stream) {
+  int rc = check_single_args(a);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->P == 0) return DGS_OK;
+  DGS_REQUIRE(geom_buffer && binning_buffer && image_buffer && dL_dpix, "NULL state buffer");
+  DGS_REQUIRE(dL_dmean2D && dL_dconic && dL_dopacity && dL_dcolor && dL_dmean3D, "NULL gradient buffer");
+  float bg[3];
+  DGS_CUDA_OK(cudaMemcpyAsync(bg, a->background, sizeof(bg), cudaMemcpyDeviceToHost, st));
+  DGS_CUDA_OK(cudaStreamSynchronize(st));
+  Problem pb = single_problem(a, bg);
+  GeomState gs = GeomState::carve(const_cast<void*>(geom_buffer), 1, a->P, nullptr);
+  ImgState im = ImgState::carve(const_cast<void*>(image_buffer), 1, a->W, a->H, nullptr);
+  BinState bs = BinState::carve(const_cast<void*>(binning_buffer), R, nullptr);
+  if (R > 0) {
+    blend_backward_kernel<<<pb.tiles, TILE_PIX, 0, st>>>(pb, gs, im, bs.point_list, dL_dpix, dL_dmean2D, dL_dconic,
+                                                          dL_dopacity, dL_dcolor);
+    DGS_LAUNCH_OK(st, a->debug);
+  }
+  GeomGradOut out;
+  out.dmeans = dL_dmean3D; out.dcov3d = dL_dcov3D; out.dsh = dL_dsh; out.dscale = dL_dscale; out.drot = dL_drot;
+  out.dopac_raw = nullptr;
+  geometry_backward_kernel<<<dim3(ceil_div(a->P, 256), 1), 256, 0, st>>>(pb, gs, radii, dL_dmean2D, dL_dconic,
+                                                                          dL_dopacity, dL_dcolor, out);
+  DGS_LAUNCH_OK(st, a->debug);
+  return DGS_OK;
+}
+
+int dgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream) {
+  (void)projmatrix;
+  DGS_REQUIRE(P >= 0, "bad P");
+  if (P == 0) return DGS_OK;
+  DGS_REQUIRE(means3D && viewmatrix && present, "NULL pointer");
+  mark_visible_kernel<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(P, means3D, viewmatrix, present);
+  DGS_LAUNCH_OK((cudaStream_t)stream, 0);
+  return DGS_OK;
+}
+
+static int check_batch_args(const dgs_render_batch_args* a) {
+  DGS_REQUIRE(a != nullptr, "args is NULL");
+  DGS_REQUIRE(a->B > 0 && a->V > 0 && a->P > 0 && a->W > 0 && a->H > 0, "bad sizes");
+  DGS_REQUIRE(a->D >= 0 && a->D <= 3 && a->M >= (a->D + 1) * (a->D + 1), "bad SH degree/M");
+  DGS_REQUIRE(a->xyz && a->features && a->scaling && a->rotation && a->opacity && a->c2w && a->fxfycxcy, "NULL input");
+  return DGS_OK;
+}
+
+static Problem batch_problem(const dgs_render_batch_args* a) {
+  Problem pb = make_problem(a->B * a->V, a->V, a->P, a->D, a->M, a->W, a->H, 1, a->scale_modifier);
+  pb.means = a->xyz; pb.shs = a->features; pb.opac = a->opacity; pb.scales = a->scaling; pb.rots = a->rotation;
+  pb.bg[0] = a->bg[0]; pb.bg[1] = a->bg[1]; pb.bg[2] = a->bg[2];
+  return pb;
+}
+
+int dgs_render_batch_forward(const dgs_render_batch_args* a, dgs_alloc_fn geom_alloc, void* geom_user,
+                             dgs_alloc_fn bin_alloc, void* bin_user, dgs_alloc_fn img_alloc, void* img_user,
+                             float* out_images, long long* num_rendered, void* stream) {
+  int rc = check_batch_args(a);
+  if (rc) return rc;
+  DGS_REQUIRE(geom_alloc && bin_alloc && img_alloc && out_images && num_rendered, "NULL output/allocator");
+  Problem pb = batch_problem(a);
+  return run_forward(pb, true, a->c2w, a->fxfycxcy, nullptr, nullptr, nullptr, 0.f, 0.f, geom_alloc, geom_user,
+                     bin_alloc, bin_user, img_alloc, img_user, out_images, nullptr, num_rendered,
+                     (cudaStream_t)stream, a->debug);
+}
+
+int dgs_render_batch_backward(const dgs_render_batch_args* a, long long R, const void* geom_buffer,
+                              const void* binning_buffer, const void* image_buffer, const float* dL_dimages,
+                              float* d_xyz, float* d_features, float* d_scaling, float* d_rotation,
+                              float* d_opacity, dgs_alloc_fn scratch_alloc, void* scratch_user, void* stream) {
+  int rc = check_batch_args(a);
+  if (rc) return rc;
+  DGS_REQUIRE(geom_buffer && binning_buffer && image_buffer && dL_dimages && scratch_alloc, "NULL state buffer");
+  DGS_REQUIRE(d_xyz && d_features && d_scaling && d_rotation && d_opacity, "NULL gradient buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  Problem pb = batch_problem(a);
+  GeomState gs = GeomState::carve(const_cast<void*>(geom_buffer), pb.NV, pb.P, nullptr);
+  ImgState im = ImgState::carve(const_cast<void*>(image_buffer), pb.NV, pb.W, pb.H, nullptr);
+  BinState bs = BinState::carve(const_cast<void*>(binning_buffer), R, nullptr);
+  // per-(view, Gaussian) screen-space gradient records: mean2D[3] conic[4] opacity[1] colour[3]
+  const size_t N = (size_t)pb.NV * pb.P;
+  Carver c(nullptr);
+  c.take<float>(N * 3); c.take<float>(N * 4); c.take<float>(N); c.take<float>(N * 3);
+  const size_t sbytes = c.bytes();
+  void* sbuf = scratch_alloc(sbytes, scratch_user);
+  if (!sbuf) { set_error("scratch allocator returned NULL"); return DGS_ERR_ALLOC; }
+  Carver cc(sbuf);
+  float* dmean2D = cc.take<float>(N * 3);
+  float* dconic = cc.take<float>(N * 4);
+  float* dopac = cc.take<float>(N);
+  float* dcolor = cc.take<float>(N * 3);
+  DGS_CUDA_OK(cudaMemsetAsync(sbuf, 0, sbytes, st));
+  if (R > 0) {
+    blend_backward_kernel<<<(unsigned)((size_t)pb.NV * pb.tiles), TILE_PIX, 0, st>>>(
+        pb, gs, im, bs.point_list, dL_dimages, dmean2D, dconic, dopac, dcolor);
+    DGS_LAUNCH_OK(st, a->debug);
+  }
+  GeomGradOut out;
+  out.dmeans = d_xyz; out.dcov3d = nullptr; out.dsh = d_features; out.dscale = d_scaling; out.drot = d_rotation;
+  out.dopac_raw = d_opacity;
+  geometry_backward_kernel<<<dim3(ceil_div(a->P, 256), a->B), 256, 0, st>>>(pb, gs, nullptr, dmean2D, dconic, dopac,
+                                                                             dcolor, out);
+  DGS_LAUNCH_OK(st, a->debug);
+  return DGS_OK;
+}
+
+int dgs_raster_export_state(int n_views, int P, int W, int H, long long R, const void* geom_buffer,
+                            const void* binning_buffer, const void* image_buffer, float* xy, float* depth,
+                            float* conic_opacity, float* rgb, uint32_t* tiles_touched, uint32_t* point_list,
+                            uint32_t* ranges, float* final_T, uint32_t* n_contrib, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DGS_REQUIRE(geom_buffer && image_buffer, "NULL state buffer");
+  GeomState gs = GeomState::carve(const_cast<void*>(geom_buffer), n_views, P, nullptr);
+  ImgState im = ImgState::carve(const_cast<void*>(image_buffer), n_views, W, H, nullptr);
+  const size_t N = (size_t)n_views * P;
+  if (N) {
+    export_geom_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, gs, xy, depth, conic_opacity, rgb, tiles_touched);
+    DGS_LAUNCH_OK(st, 0);
+  }
+  const size_t npix = (size_t)n_views * W * H, ntiles = (size_t)n_views * ceil_div(W, TILE) * ceil_div(H, TILE);
+  if (point_list && R > 0) {
+    DGS_REQUIRE(binning_buffer, "NULL binning buffer");
+    BinState bs = BinState::carve(const_cast<void*>(binning_buffer), R, nullptr);
+    DGS_CUDA_OK(cudaMemcpyAsync(point_list, bs.point_list, R * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  }
+  if (ranges) DGS_CUDA_OK(cudaMemcpyAsync(ranges, im.ranges, ntiles * sizeof(uint2), cudaMemcpyDeviceToDevice, st));
+  if (final_T) DGS_CUDA_OK(cudaMemcpyAsync(final_T, im.final_T, npix * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (n_contrib) DGS_CUDA_OK(cudaMemcpyAsync(n_contrib, im.n_contrib, npix * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  return DGS_OK;
+}
+
+}  // extern "C"

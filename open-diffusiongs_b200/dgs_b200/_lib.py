@@ -1,0 +1,74 @@
+"""ctypes binding of libdgs_b200.so (include/dgs_b200.h).  There is NO fallback: if the CUDA
+library is missing, importing any compute entry point raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdgs_b200.so")
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+class RasterArgs(C.Structure):
+    _fields_ = [("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("W", C.c_int), ("H", C.c_int),
+                ("background", C.c_void_p), ("means3D", C.c_void_p), ("shs", C.c_void_p),
+                ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p),
+                ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p),
+                ("projmatrix", C.c_void_p), ("campos", C.c_void_p), ("scale_modifier", C.c_float),
+                ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("prefiltered", C.c_int),
+                ("debug", C.c_int)]
+
+
+class RenderBatchArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("V", C.c_int), ("P", C.c_int), ("M", C.c_int), ("D", C.c_int),
+                ("W", C.c_int), ("H", C.c_int), ("xyz", C.c_void_p), ("features", C.c_void_p),
+                ("scaling", C.c_void_p), ("rotation", C.c_void_p), ("opacity", C.c_void_p),
+                ("c2w", C.c_void_p), ("fxfycxcy", C.c_void_p), ("scale_modifier", C.c_float),
+                ("bg", C.c_float * 3), ("debug", C.c_int)]
+
+
+_lib = None
+
+
+class DgsError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DgsError(
+                f"libdgs_b200.so not found at {LIB_PATH}: build it with "
+                "`python open-diffusiongs_b200/csrc/build.py` (there is no CPU/PyTorch fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.dgs_last_error.restype = C.c_char_p
+        L.dgs_version.restype = C.c_int
+        for name in ("dgs_raster_geom_bytes", "dgs_raster_binning_bytes", "dgs_raster_image_bytes"):
+            getattr(L, name).restype = C.c_size_t
+        L.dgs_raster_geom_bytes.argtypes = [C.c_int, C.c_int]
+        L.dgs_raster_binning_bytes.argtypes = [C.c_longlong]
+        L.dgs_raster_image_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+        vp = C.c_void_p
+        L.dgs_raster_forward.argtypes = [C.POINTER(RasterArgs), ALLOC_FN, vp, ALLOC_FN, vp, ALLOC_FN, vp,
+                                         vp, vp, C.POINTER(C.c_int), vp]
+        L.dgs_raster_backward.argtypes = [C.POINTER(RasterArgs), C.c_int] + [vp] * 15
+        L.dgs_mark_visible.argtypes = [C.c_int, vp, vp, vp, vp, vp]
+        L.dgs_render_batch_forward.argtypes = [C.POINTER(RenderBatchArgs), ALLOC_FN, vp, ALLOC_FN, vp,
+                                               ALLOC_FN, vp, vp, C.POINTER(C.c_longlong), vp]
+        L.dgs_render_batch_backward.argtypes = [C.POINTER(RenderBatchArgs), C.c_longlong] + [vp] * 9 + [ALLOC_FN, vp, vp]
+        L.dgs_raster_export_state.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong] + [vp] * 13
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DgsError(f"libdgs_b200 status {rc}: {lib().dgs_last_error().decode()}")
+
+
+EXPORTED = [  # every symbol include/dgs_b200.h declares (checked by tests/test_abi.py)
+    "dgs_version", "dgs_last_error", "dgs_raster_geom_bytes", "dgs_raster_binning_bytes",
+    "dgs_raster_image_bytes", "dgs_raster_forward", "dgs_raster_backward", "dgs_mark_visible",
+    "dgs_render_batch_forward", "dgs_render_batch_backward", "dgs_raster_export_state",
+]
