@@ -1,0 +1,305 @@
+// gemm_sm100.cu -- persistent, warp-specialised tcgen05 GEMM for the DiT linears (sm_100a).
+//
+//   C[M,N] = epilogue( A[M,K] (bf16, row-major) x W[N,K]^T (bf16, row-major = nn.Linear weight) )
+//
+// One CTA per SM, 192 threads:  warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma
+// issuer, warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  Operands are staged by TMA
+// into a 128-byte-swizzled shared-memory ring (BK = 64 bf16 = one swizzle row); fp32 accumulators live in
+// TMEM, double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+// Tile = 128 x BN (BN = 256 or 128), UMMA 128 x BN x 16, cta_group::1.
+//
+// Fused epilogues = the elementwise tails of the reference DiT block
+// (diffusionGS/models/transformers/utils_transformer.py:270-290, timm Attention/Mlp):
+//   EPI_BIAS_BF16       y = acc + b                         (qkv)
+//   EPI_BIAS_GELU_BF16  y = gelu_tanh(acc + b)              (mlp.fc1 + act)
+//   EPI_GATE_RESID_F32  x += gate[sample] * (acc + b)       (attn.proj / mlp.fc2 + gate + residual, fp32 stream)
+//   EPI_F32             y = acc (+ b), fp32                 (tokenizer, decoder head)
+#include <cstring>
+
+#include "dgs_internal.h"
+#include "dit_kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace dgs {
+
+using namespace ptx;
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)"); return DGS_ERR_CUDA; }
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DGS_ERR_CUDA; }
+  return DGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device
+// ---------------------------------------------------------------------------------------------
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers (512 or 256: powers of two)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_tanh(float x) {  // nn.GELU(approximate="tanh")
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
+                 int M, int N, int K) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n, num_k = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_k; kb++) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          mbar_arrive_expect_tx(full_bar + stage, Cfg::STAGE_BYTES);
+          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, full_bar + stage, kb * BK, m0);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, full_bar + stage, kb * BK, n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k; kb++) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES), 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; k++) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (>>4) address field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + stage);  // frees the smem slot once these MMAs have read it
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar + acc);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..5 =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+      const int row = m0 + quad * 32 + lane;
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const float* gate = nullptr;
+      if (EPI == EPI_GATE_RESID_F32 && row < M) gate = ep.gate + (size_t)(row / ep.rows_per_sample) * ep.gate_stride;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        const int n = n0 + c * 32;
+        if (n >= N) break;  // warp-uniform (N % 32 == 0)
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (row < M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+            if (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) v[j] = gelu_tanh(v[j]);
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              pk.x = pack_bf16(v[j], v[j + 1]); pk.y = pack_bf16(v[j + 2], v[j + 3]);
+              pk.z = pack_bf16(v[j + 4], v[j + 5]); pk.w = pack_bf16(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          } else if (EPI == EPI_GATE_RESID_F32) {
+            float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate + n + j));
+              float4 x4 = *reinterpret_cast<float4*>(o + j);
+              x4.x += g4.x * v[j]; x4.y += g4.y * v[j + 1]; x4.z += g4.z * v[j + 2]; x4.w += g4.w * v[j + 3];
+              *reinterpret_cast<float4*>(o + j) = x4;
+            }
+          } else {  // EPI_F32
+            float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int N, int K,
+                       cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  if (!g_num_sms) {
+    int dev = 0;
+    DGS_CUDA_OK(cudaGetDevice(&dev));
+    DGS_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, ep, M, N, K);
+  DGS_CUDA_OK(cudaGetLastError());
+  return DGS_OK;
+}
+
+int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st) {
+  DGS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %dx%dx%d", M, N, K);
+  DGS_REQUIRE(K % 8 == 0 && N % 32 == 0, "gemm: need K %% 8 == 0 and N %% 32 == 0 (got K=%d N=%d)", K, N);
+  DGS_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm: operands must be 16-byte aligned");
+  // wide tiles when they still fill the machine, else 128-wide tiles for more CTAs
+  const bool wide = (N % 256 == 0) && (ceil_div(M, BM) * (N / 256) >= 120);
+  const int BN = wide ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {BK, BM};
+    int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {BK, (uint32_t)BN};
+    int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
+    if (rc) return rc;
+  }
+#define DGS_GEMM_CASE(E)                                                                  \
+  case E:                                                                                 \
+    return wide ? launch_gemm<256, E>(tmA, tmB, ep, M, N, K, st) : launch_gemm<128, E>(tmA, tmB, ep, M, N, K, st);
+  switch (epi) {
+    DGS_GEMM_CASE(EPI_BIAS_BF16)
+    DGS_GEMM_CASE(EPI_BIAS_GELU_BF16)
+    DGS_GEMM_CASE(EPI_GATE_RESID_F32)
+    DGS_GEMM_CASE(EPI_F32)
+    default:
+      set_error("gemm: unknown epilogue %d", epi);
+      return DGS_ERR_INVALID_ARGUMENT;
+  }
+#undef DGS_GEMM_CASE
+}
+
+}  // namespace dgs
