@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Open-DiffusionGS hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+  (N > 1: launched by the driver as  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
+
+Metric (BASELINE.json): denoise-steps/s (+ rasterized-views/s) at 256x256.
+One "step" = the hot path over one synthetic batch = BASELINE configs[1], the object pipeline:
+  1 DiT denoise forward (24 layers, 4 views -> N = 4098 tokens -> P = 262,146 pixel-aligned Gaussians)
+  + the 4-view 256x256 splat render of those Gaussians  (DGSDenoiser.forward, denoiser.py:284-287),
+random-init weights by the reference's init rules, synthetic image/noise, orbit cameras.
+
+Prints ONE JSON line (rank 0).  Keys: the driver contract + `roofline` (dominant kernel, live CUDA-event
+timing through the library's per-family event hooks) + `cpu_baseline` (oracle on the host cores, bounded
+sample) + `e2e` (same metric through the public API with pinned-host inputs, H2D/D2H inside the timed region).
+`--impl reference` times the reference's CPU path = the oracle port (the reference has no CPU rasterizer and
+its Python package does not import offline) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "open-diffusiongs_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "denoise_steps_per_sec"
+UNIT = "steps/s"
+H = W = 256
+V = 4
+PATCH = 8
+LAYERS = 24
+D = 1024
+N_TOK = 2 + V * (H // PATCH) * (W // PATCH)
+P_GAUSS = 2 + V * H * W
+
+
+def dit_forward_flops(n_tok=N_TOK, layers=LAYERS, d=D):
+    """F_fwd(N) = L (24 N D^2 + 4 N^2 D + 12 D^2) + 2 (N-2) D (576 + 896)"""
+    return layers * (24 * n_tok * d * d + 4 * n_tok * n_tok * d + 12 * d * d) + 2 * (n_tok - 2) * d * (576 + 896)
+
+
+def attention_flops(n_tok=N_TOK, d=D):
+    return 4 * n_tok * n_tok * d  # QK^T + PV, all heads, one layer, one sample
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        j = json.load(open(path))
+        return dict(hbm_gbs=j["hbm_gbs"], bf16_tflops=j["bf16_tflops"],
+                    bf16_tflops_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic batch, built on the host with fixed seeds
+# ------------------------------------------------------------------------------------------------
+def make_batch(batch, seed):
+    import numpy as np
+    import torch
+    from dgs_b200 import synth
+    rng = np.random.default_rng(seed)
+    image = rng.uniform(0, 1, (batch, V, 3, H, W)).astype(np.float32)
+    image[:, 1:] = rng.normal(0, 1, (batch, V - 1, 3, H, W)).astype(np.float32)  # views 1..3 are pure noise at t
+    c2w, fx = synth.orbit_cameras(V, W, H, radius=3.0, el_deg=20.0)
+    c2w = np.broadcast_to(c2w, (batch, V, 4, 4)).copy()
+    fx = np.broadcast_to(fx, (batch, V, 4)).copy()
+    # rays (TransformInput, systems/utils.py:621-757): pixel centre +0.5, normalised, rotated by c2w
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float32) + 0.5, np.arange(W, dtype=np.float32) + 0.5, indexing="ij")
+    ray_o = np.zeros((batch, V, 3, H, W), np.float32)
+    ray_d = np.zeros((batch, V, 3, H, W), np.float32)
+    for b in range(batch):
+        for v in range(V):
+            f = fx[b, v]
+            d = np.stack([(xs - f[2]) / f[0], (ys - f[3]) / f[1], np.ones_like(xs)], 0)
+            d = np.einsum("ij,jhw->ihw", c2w[b, v, :3, :3], d)
+            ray_d[b, v] = d / np.linalg.norm(d, axis=0, keepdims=True)
+            ray_o[b, v] = c2w[b, v, :3, 3][:, None, None]
+    t = np.full((batch,), 500, np.int64)
+    tt = torch.from_numpy
+    return dict(image=tt(image), ray_o=tt(ray_o), ray_d=tt(ray_d), c2w=tt(c2w), fxfycxcy=tt(fx), t=tt(t))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (ts, r) in self.rows if t0 <= ts <= t1 + 0.2] or [r for (_, r) in self.rows[-3:]]
+        if not rows:
+            return None
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, c in zip(names, r[5:9]) if c.lower().startswith("active")})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(rows))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (reference restatement) on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+CPU_DIT_LAYERS_SAMPLED = 2
+CPU_VIEWS_SAMPLED = 1
+
+
+def cpu_reference_step(batch_np=None, threads=None):
+    """One bounded sample of the step on the CPU, extrapolated to a full step:
+      DiT: fp32 PyTorch oracle with 2 of the 24 blocks (block time x 12 + measured non-block time),
+      rasterizer: C oracle (OpenMP) on 1 of the 4 views of P = 262,146 init-like Gaussians (x 4).
+    -> (estimated seconds per full step, detail dict)"""
+    import numpy as np
+    import torch
+    from dgs_b200 import synth
+    from oracle import raster as orc
+    from oracle.dit import DenoiserOracle
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    b = make_batch(1, 0) if batch_np is None else batch_np
+    with torch.no_grad():
+        m2 = DenoiserOracle(layers=CPU_DIT_LAYERS_SAMPLED)
+        m0 = DenoiserOracle(layers=0)
+        m0.load_state_dict({k: v for k, v in m2.state_dict().items() if not k.startswith("transformer.")}, strict=True)
+        m2.image_to_gaussians(b["image"][:1, :, :, :64, :64], b["ray_o"][:1, :, :, :64, :64], b["ray_d"][:1, :, :, :64, :64], b["t"][:1])
+        t0 = time.perf_counter()
+        out, _ = m2.image_to_gaussians(b["image"][:1], b["ray_o"][:1], b["ray_d"][:1], b["t"][:1])
+        t_2 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        m0.image_to_gaussians(b["image"][:1], b["ray_o"][:1], b["ray_d"][:1], b["t"][:1])
+        t_0 = time.perf_counter() - t0
+    t_block = max(t_2 - t_0, 0.0) / CPU_DIT_LAYERS_SAMPLED
+    t_dit = t_0 + LAYERS * t_block
+    g = {k: v[0].numpy() for k, v in out.items()}
+    act = synth.activate(dict(xyz=g["xyz"], features=g["features"], scaling=g["scaling"], rotation=g["rotation"],
+                              opacity=g["opacity"]))
+    cam = synth.camera_matrices(b["c2w"][0, 0].numpy(), b["fxfycxcy"][0, 0].numpy(), H, W)
+    t0 = time.perf_counter()
+    st = orc.rasterize_forward(np.ones(3, np.float32), act["means3D"], None, act["opacities"], act["scales"],
+                               act["rotations"], 1.0, None, cam[0], cam[1], cam[3], cam[4], H, W, act["shs"], 0, cam[2])
+    t_view = time.perf_counter() - t0
+    t_step = t_dit + V * t_view
+    detail = dict(dit_s=t_dit, dit_block_s=t_block, dit_nonblock_s=t_0, raster_view_s=t_view,
+                  instances_per_view=int(st["num_rendered"]), threads=threads, omp_threads=orc.num_threads())
+    return t_step, detail
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    threads = os.cpu_count()
+    batch = make_batch(1, 0)
+    for _ in range(args.warmup):
+        cpu_reference_step(batch, threads)
+    ts = []
+    for _ in range(args.steps):
+        t, detail = cpu_reference_step(batch, threads)
+        ts.append(t)
+    t_step = statistics.mean(ts)
+    val = 1.0 / t_step
+    sample = (f"per step: fp32 PyTorch oracle DiT at N={N_TOK} with {CPU_DIT_LAYERS_SAMPLED}/{LAYERS} blocks "
+              f"(block time x{LAYERS} + non-block time) + C/OpenMP oracle rasterizer on {CPU_VIEWS_SAMPLED}/{V} views "
+              f"of P={P_GAUSS} (x{V}); extrapolated to one full step")
+    line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=t_step * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=workload_name(1), per_gpu_batch=1, parallelism="cpu", detail=detail),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port", sample=sample),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                views_per_sec=val * V, gpu_launches=0)
+    print(json.dumps(line))
+
+
+def workload_name(batch):
+    return (f"obj-256 denoise step (BASELINE configs[1]): 1 DiT forward (24 layers, {N_TOK} tokens) + {V}-view "
+            f"256x256 splat render of P={P_GAUSS} Gaussians, per-GPU batch {batch}, random-init weights")
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="samples per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from dgs_b200 import _lib
+    from dgs_b200.denoiser import DGSDenoiser
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    model = DGSDenoiser(dict(patch_size=PATCH)).to(dev)
+    model.packed_weights()
+    host = {k: v.pin_memory() for k, v in make_batch(args.batch, seed=rank).items()}
+    devb = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    L = _lib.lib()
+
+    def step(b):
+        params, _ = model.image_to_gaussians(b["image"], b["ray_o"], b["ray_d"], b["t"])
+        return model.render_gaussians(params, b["c2w"], b["fxfycxcy"], H, W)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        img = step(devb)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM, per-step CUDA events, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = L.dgs_kernel_launch_count()
+    barrier()
+    t_wall0 = time.time()
+    for a, b_ in ev:
+        flush.zero_()
+        a.record()
+        img = step(devb)
+        b_.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = L.dgs_kernel_launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    step_ms = [a.elapsed_time(b_) for a, b_ in ev]
+    total_s = torch.tensor([sum(step_ms) / 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_s, op=dist.ReduceOp.MAX)
+    total_s = float(total_s)
+    value = world * args.batch * args.steps / total_s
+
+    # ---- timed region 2: per-kernel-family device time, same steps with the library's event hooks on ----
+    L.dgs_profile_enable(1)
+    _lib.profile_read()
+    for _ in range(args.steps):
+        flush.zero_()
+        img = step(devb)
+    torch.cuda.synchronize(dev)
+    fam = _lib.profile_read()
+    L.dgs_profile_enable(0)
+    fam_ms = {k: v[0] / args.steps for k, v in fam.items() if v[1]}
+    fam_n = {k: v[1] // args.steps for k, v in fam.items() if v[1]}
+
+    # ---- timed region 3: end to end through the public API with pinned HOST buffers ----
+    def e2e_step():
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        out = step(b)
+        return out.to("cpu", non_blocking=False)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        out_host = e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = world * args.batch * args.steps / float(e2e_s)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family ----
+    peaks = load_peaks()
+    dom = max(fam_ms, key=fam_ms.get) if fam_ms else None
+    share = {k: round(v / sum(fam_ms.values()), 4) for k, v in sorted(fam_ms.items(), key=lambda kv: -kv[1])}
+    roof = None
+    if dom is not None:
+        per_launch_ms = fam_ms[dom] / max(fam_n[dom], 1)
+        flops = {"dit.attention": attention_flops() * args.batch,
+                 "dit.gemm_qkv": 2 * N_TOK * D * 3 * D * args.batch, "dit.gemm_proj": 2 * N_TOK * D * D * args.batch,
+                 "dit.gemm_fc1": 2 * N_TOK * D * 4 * D * args.batch, "dit.gemm_fc2": 2 * N_TOK * D * 4 * D * args.batch}
+        if dom in flops:
+            ach = flops[dom] / (per_launch_ms * 1e-3) / 1e12
+            pk = peaks["bf16_tflops_sustained"]
+            roof = dict(kernel=dom, bound="tensor", achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk, traffic=None,
+                        peak_source=peaks["source"] + " (sustained cuBLAS bf16, kernel timed inside a long step)",
+                        launch_ms=per_launch_ms, algorithmic_flops_per_launch=flops[dom])
+        else:
+            # rasterizer family: algorithmic bytes B_fwd = 159 P + 84 R + 20 N_pix per view
+            R = getattr(model.gs_renderer, "last_num_rendered", None)
+            nbytes = None if R is None else (159 * P_GAUSS * V + 84 * R + 20 * H * W * V) * args.batch
+            tot_ms = sum(v for k, v in fam_ms.items() if k.startswith("raster."))
+            ach = None if nbytes is None else nbytes / (tot_ms * 1e-3) / 1e9
+            roof = dict(kernel=dom, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s",
+                        frac=None if ach is None else ach / peaks["hbm_gbs"], traffic=None,
+                        peak_source=peaks["source"], launch_ms=per_launch_ms, note="whole rasterizer forward vs B_fwd")
+    dit_ms = sum(v for k, v in fam_ms.items() if k.startswith("dit."))
+    ras_ms = sum(v for k, v in fam_ms.items() if k.startswith("raster."))
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        t_cpu, detail = cpu_reference_step(None, os.cpu_count())
+        cpu = dict(value=1.0 / t_cpu, unit=UNIT, cores=os.cpu_count(), kind="port",
+                   sample=(f"one step: fp32 PyTorch oracle DiT with {CPU_DIT_LAYERS_SAMPLED}/{LAYERS} blocks timed "
+                           f"(x{LAYERS} + non-block time) + C/OpenMP oracle rasterizer on 1/{V} views (x{V}); "
+                           f"dit {detail['dit_s']:.1f}s + raster {V}x{detail['raster_view_s']:.1f}s"),
+                   detail=detail)
+
+    ms_per_step = total_s / args.steps * 1e3
+    line = dict(
+        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+        data="synthetic",
+        config=dict(workload=workload_name(args.batch), per_gpu_batch=args.batch, parallelism=f"replicas x{world}",
+                    l2="256 MB buffer written between timed steps (L2 flush); bf16 weights alone are 0.92 GB > 126 MB L2",
+                    dit_dtype="bf16 tensor-core GEMM/attention, fp32 residual/LN/softmax", raster_dtype="f32"),
+        views_per_sec=value * V,
+        e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+        gpu_launches=int(launches),
+        roofline=roof, cpu_baseline=cpu, clocks=clocks,
+        breakdown_ms=dict(dit=dit_ms, raster=ras_ms, families={k: round(v, 4) for k, v in fam_ms.items()},
+                          share=share, launches_per_step=fam_n),
+        dit_tflops=dit_forward_flops() * args.batch / (dit_ms * 1e-3) / 1e12 if dit_ms else None,
+        step_ms_min=min(step_ms), step_ms_max=max(step_ms),
+    )
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

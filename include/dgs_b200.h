@@ -39,6 +39,15 @@ typedef void* (*dgs_alloc_fn)(size_t bytes, void* user);
 
 int dgs_version(void);
 const char* dgs_last_error(void);
+/* Kernels of this library launched so far by the calling process (for bench.py's `gpu_launches`). */
+unsigned long long dgs_kernel_launch_count(void);
+/* Optional per-kernel-family device timing: when enabled, every entry point records CUDA events on the
+ * caller's stream around each kernel family it launches.  dgs_profile_read() waits for the recorded spans,
+ * writes the summed milliseconds and span counts per family (order: raster project, scan, emit_keys, sort,
+ * tile_ranges, blend_fwd, blend_bwd, geometry_bwd; dit input, conditioning, ln_modulate, gemm_qkv, attention,
+ * gemm_proj, gemm_fc1, gemm_fc2, heads), clears the record and returns the number of families. */
+int dgs_profile_enable(int on);
+int dgs_profile_read(float* ms_sum, int* span_count, int n_families);
 
 /* ------------------------------------------------------------------------------------------------
  * B1a. Single-view rasterizer: what `_C.rasterize_gaussians`, `_C.rasterize_gaussians_backward`
@@ -145,6 +154,70 @@ int dgs_raster_export_state(int n_views, int P, int W, int H, long long R, const
                             float* depth, float* conic_opacity, float* rgb, uint32_t* tiles_touched,
                             uint32_t* point_list, uint32_t* ranges, float* final_T,
                             uint32_t* n_contrib, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * B2. DiT denoiser forward: DGSDenoiser.image_to_gaussians
+ * (diffusionGS/models/denoiser/denoiser.py:306-416; scene twin denoiser_scene.py:314-429), i.e.
+ * posed-image patchify + tokenizer -> +2 learned tokens -> LayerNorm -> L x DiTBlock
+ * (utils_transformer.py:246-290 around timm Attention/Mlp) -> GaussiansUpsampler / ImageTokenDecoder
+ * heads -> to_gs + pixel alignment.  GEMMs and attention run on tcgen05 (bf16 in, fp32 accumulate),
+ * the residual stream, LayerNorm statistics and softmax stay fp32.
+ * Weights: GEMM matrices are bf16 row-major [out, in] (nn.Linear layout), per-layer tensors stacked
+ * along a leading L axis; vectors fp32.  state_dict key -> field mapping is in dgs_b200/denoiser.py.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int width, heads, layers, patch, n_gaussians, mlp_hidden; /* 1024, 16, 24, 8, 2, 4096 */
+  const void* tokenizer_w;  /* image_tokenizer.1.weight, split-bf16 [width, 3*patch*patch*9] = [hi|hi|lo] */
+  const float* pos_embed;   /* gaussians_pos_embedding             fp32 [n_gaussians, width]          */
+  const float* in_ln_w;     /* transformer_input_layernorm.weight  fp32 [width]                       */
+  const float* t0_w; const float* t0_b; /* t_embedder.mlp.0  fp32 [width,256], fp32 [width]          */
+  const float* t2_w; const float* t2_b; /* t_embedder.mlp.2  fp32 [width,width], fp32 [width]        */
+  const float* adaln_w;     /* all adaLN_modulation.1.weight stacked: L x [6*width] rows, then upsampler
+                               [2*width], then image_token_decoder [2*width]; fp32 [.., width]        */
+  const float* adaln_b;     /* same stacking, fp32                                                    */
+  const void* qkv_w;  const float* qkv_b;   /* transformer.{i}.attn.qkv   bf16 [L,3w,w], fp32 [L,3w] */
+  const void* proj_w; const float* proj_b;  /* transformer.{i}.attn.proj  bf16 [L,w,w],  fp32 [L,w]  */
+  const void* fc1_w;  const float* fc1_b;   /* transformer.{i}.mlp.fc1    bf16 [L,4w,w], fp32 [L,4w] */
+  const void* fc2_w;  const float* fc2_b;   /* transformer.{i}.mlp.fc2    bf16 [L,w,4w], fp32 [L,w]  */
+  const float* ups_ln_w; const void* ups_w; /* upsampler.layernorm.weight fp32 [w]; upsampler.linear.weight split-bf16 [14,3w] */
+  const float* dec_ln_w; const void* dec_w; /* image_token_decoder.*: fp32 [w]; split-bf16 [patch*patch*14, 3w]
+     "split-bf16 [n, 3k] = [hi|hi|lo]": hi = bf16(W), lo = bf16(W - hi); paired with activations laid out
+     [hi|lo|hi] the bf16 MMA then yields x_hi W_hi + x_lo W_hi + x_hi W_lo (fp32-accurate) -- used for the two
+     small GEMMs at the ends of the network whose rounding would otherwise dominate the output error. */
+} dgs_dit_weights;
+
+typedef struct {
+  int B, V, H, W;
+  int plucker_mode;          /* 0 = 'relative_plk' (object model), 1 = 'plk' (scene model)            */
+  int scene_depth;           /* 0: depth=(2s-1)*1.8 + (-o.d) ; 1: depth=s*(far-near)+near             */
+  float range_near, range_far;
+  const float* images;       /* [B,V,3,H,W] fp32 (view 0 clean, others noised)                        */
+  const float* ray_o;        /* [B,V,3,H,W]                                                           */
+  const float* ray_d;        /* [B,V,3,H,W]                                                           */
+  const float* t;            /* [B] timesteps as fp32                                                 */
+  float* xyz;                /* out [B,P,3],  P = n_gaussians + V*H*W                                 */
+  float* features;           /* out [B,P,1,3]                                                         */
+  float* scaling;            /* out [B,P,3]                                                           */
+  float* rotation;           /* out [B,P,4]                                                           */
+  float* opacity;            /* out [B,P,1]                                                           */
+  float* img_aligned_xyz;    /* out [B,V,3,H,W] or NULL                                               */
+  float* tokens_out;         /* optional debug out: final residual stream [B,N,width] fp32, or NULL   */
+} dgs_dit_io;
+
+size_t dgs_dit_workspace_bytes(const dgs_dit_weights* w, int B, int V, int H, int W);
+int dgs_dit_forward(const dgs_dit_weights* w, const dgs_dit_io* io, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* Building blocks, exported for the unit parity tests (same kernels dgs_dit_forward launches).
+ * epi: 0 = bias -> bf16, 1 = bias + GELU(tanh) -> bf16, 2 = out(fp32) += gate[row / rows_per_sample] * (acc + bias),
+ *      3 = (acc + bias) -> fp32.   A [M,K], W [N,K] bf16 row-major. */
+int dgs_gemm_bf16(const void* A, const void* W, const float* bias, const float* gate, void* out, int M, int N,
+                  int K, int epi, int ldc, int gate_stride, int rows_per_sample, void* stream);
+/* qkv [B,N,3,heads,64] bf16 -> out [B,N,heads*64] bf16 = softmax(q k^T / 8) v */
+int dgs_attention_fwd(const void* qkv, void* out, int B, int N, int heads, void* stream);
+/* h = (LN(x; eps) [* ln_w]) * (1 + scale[b]) + shift[b] -> bf16 ; x fp32 [B, rows, width] */
+int dgs_ln_modulate(const float* x, const float* ln_w, const float* shift, const float* scale, int mod_stride,
+                    void* h, int B, int rows, int width, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,261 @@
+// attention_sm100.cu -- non-causal multi-head attention forward on tcgen05 (sm_100a), head_dim 64.
+//
+//   out[b, n, h*64:(h+1)*64] = softmax(q k^T / 8) v      (timm Attention.forward -> F.scaled_dot_product_attention,
+//                                                         instantiated at utils_transformer.py:254-256)
+// reading q/k/v straight out of the fused qkv GEMM output [B, N, 3, H, 64] (bf16) through ONE 3-D TMA tensor
+// map (no head-major re-layout), N arbitrary (4098 = 32*128 + 2: the tail is zero-filled by TMA and masked).
+//
+// One CTA per (128-query block, head, sample); 256 threads:
+//   warp 0      TMA producer: Q once, K/V blocks of 128 keys through a 3-stage ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:  S_j = Q K_j^T  and  PV_j = P_j V_j
+//   warps 4..7  online softmax, one query row per thread: S_j (TMEM) -> p = exp2(..) -> P_j (bf16, swizzled smem,
+//               A operand of the PV MMA); O accumulated in registers from PV_j (TMEM), rescaled by exp2(m_old - m_new)
+// S and PV are double-buffered in TMEM so QK^T of block j+1 runs under the softmax of block j.
+#include "dgs_internal.h"
+#include "dit_kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace dgs {
+
+using namespace ptx;
+
+constexpr int ATT_BM = 128, ATT_BN = 128, ATT_HD = 64, ATT_KV_STAGES = 3, ATT_THREADS = 256;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // one [128 x 64] bf16 tile (Q, K, V, half of P)
+constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES + 4) + 1024 + 256;
+constexpr uint32_t TMEM_S = 0, TMEM_PV = 256, ATT_TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int N, int H) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;
+  uint8_t* sP = sV + ATT_KV_STAGES * ATT_TILE_BYTES;  // 2 buffers x (2 x [128 x 64]) bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = k_full + ATT_KV_STAGES;
+  uint64_t* kv_empty = v_full + ATT_KV_STAGES;
+  uint64_t* s_full = kv_empty + ATT_KV_STAGES;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* pv_full = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BM, h = blockIdx.y, b = blockIdx.z;
+  const int n_blocks = (N + ATT_BN - 1) / ATT_BN;
+  const int D = H * ATT_HD;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_qkv);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ATT_KV_STAGES; s++) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(kv_empty + s, 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(s_full + s, 1); mbar_init(p_full + s, 128); mbar_init(pv_full + s, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_3d(sQ, &tm_qkv, q_full, h * ATT_HD, q0, b);
+      for (int j = 0; j < n_blocks; j++) {
+        const int s = j % ATT_KV_STAGES;
+        const uint32_t use = (uint32_t)(j / ATT_KV_STAGES);
+        mbar_wait(kv_empty + s, (use & 1) ^ 1);
+        mbar_arrive_expect_tx(k_full + s, ATT_TILE_BYTES);
+        tma_load_3d(sK + s * ATT_TILE_BYTES, &tm_qkv, k_full + s, D + h * ATT_HD, j * ATT_BN, b);
+        mbar_arrive_expect_tx(v_full + s, ATT_TILE_BYTES);
+        tma_load_3d(sV + s * ATT_TILE_BYTES, &tm_qkv, v_full + s, 2 * D + h * ATT_HD, j * ATT_BN, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, false, false);   // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_HD, false, true);   // P (K-major) x V (MN-major)
+      const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      auto issue_s = [&](int j) {
+        const int s = j % ATT_KV_STAGES;
+        mbar_wait(k_full + s, (uint32_t)(j / ATT_KV_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s * ATT_TILE_BYTES), 16, 1024);
+        const uint32_t d = tmem_base + TMEM_S + (uint32_t)((j & 1) * ATT_BN);
+#pragma unroll
+        for (int k = 0; k < ATT_HD / 16; k++) umma_bf16(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
+        umma_commit(s_full + (j & 1));
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_blocks; j++) {
+        if (j + 1 < n_blocks) issue_s(j + 1);
+        const int s = j % ATT_KV_STAGES;
+        mbar_wait(p_full + (j & 1), (uint32_t)(j >> 1) & 1);
+        mbar_wait(v_full + s, (uint32_t)(j / ATT_KV_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t pbase = smem_u32(sP + (j & 1) * 2 * ATT_TILE_BYTES);
+        const uint32_t vbase = smem_u32(sV + s * ATT_TILE_BYTES);
+        const uint32_t d = tmem_base + TMEM_PV + (uint32_t)((j & 1) * ATT_HD);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; k++) {
+          // A = P: K-major, two 64-key sub-tiles; 16 keys = 32 bytes inside the swizzled 128-byte row
+          const uint64_t pdesc = make_smem_desc_sw128(pbase + (uint32_t)((k >> 2) * ATT_TILE_BYTES + (k & 3) * 32), 16, 1024);
+          // B = V: MN-major ([key][64 dims] rows of 128 bytes); 16 keys = 2 groups of 8 rows = 2048 bytes
+          const uint64_t vdesc = make_smem_desc_sw128(vbase + (uint32_t)(k * 2048), ATT_TILE_BYTES, 1024);
+          umma_bf16(d, pdesc, vdesc, idesc_pv, k ? 1u : 0u);
+        }
+        umma_commit(pv_full + (j & 1));
+        umma_commit(kv_empty + s);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax / output: one query row per thread =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    float o[ATT_HD];
+#pragma unroll
+    for (int i = 0; i < ATT_HD; i++) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+
+    for (int j = 0; j < n_blocks; j++) {
+      const int buf = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1;
+      mbar_wait(s_full + buf, ph);
+      tc_fence_after();
+      const uint32_t t_s = t_lane + TMEM_S + (uint32_t)(buf * ATT_BN);
+      const int kv_valid = N - j * ATT_BN;  // >= 1
+      // pass 1: row maximum
+      float m_blk = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < ATT_BN / 32; c++) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_s + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float v = (c * 32 + i < kv_valid) ? __uint_as_float(r[i]) : -INFINITY;
+          m_blk = fmaxf(m_blk, v);
+        }
+      }
+      const float m_new = fmaxf(m_run, m_blk);
+      const float alpha = exp2f((m_run - m_new) * sl2);  // exp2(-inf) = 0 on the first block
+      const float moff = m_new * sl2;
+      // pass 2: p = exp2(s*sl2 - moff) -> bf16 -> swizzled smem (K-major A operand), row sum
+      float l_blk = 0.f;
+      uint8_t* p_row = sP + buf * 2 * ATT_TILE_BYTES + row * 128;
+#pragma unroll 1
+      for (int c = 0; c < ATT_BN / 32; c++) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_s + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float v = exp2f(fmaf(__uint_as_float(r[i]), sl2, -moff));
+          p[i] = (c * 32 + i < kv_valid) ? v : 0.f;
+          l_blk += p[i];
+        }
+        uint8_t* blk = p_row + (c >> 1) * ATT_TILE_BYTES;  // 64-key sub-tile
+        const int chunk0 = (c & 1) * 4;                    // 16-byte chunk index inside the 128-byte row
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          uint4 pk;
+          pk.x = pack2_bf16(p[8 * q], p[8 * q + 1]); pk.y = pack2_bf16(p[8 * q + 2], p[8 * q + 3]);
+          pk.z = pack2_bf16(p[8 * q + 4], p[8 * q + 5]); pk.w = pack2_bf16(p[8 * q + 6], p[8 * q + 7]);
+          *reinterpret_cast<uint4*>(blk + (((chunk0 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
+        }
+      }
+      l_run = l_run * alpha + l_blk;
+      m_run = m_new;
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();    // our tcgen05.ld of S_j are complete before the issuer may overwrite S
+      mbar_arrive(p_full + buf);
+      // fold in PV_{j-1} (relative to the previous running max): O = O * alpha_{j-1} + PV_{j-1}
+      if (j > 0) {
+        const int pb = (j - 1) & 1;
+        mbar_wait(pv_full + pb, (uint32_t)((j - 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_pv = t_lane + TMEM_PV + (uint32_t)(pb * ATT_HD);
+#pragma unroll
+        for (int c = 0; c < ATT_HD / 32; c++) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_pv + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
+        }
+      }
+      alpha_prev = alpha;
+    }
+    {  // last block's PV
+      const int pb = (n_blocks - 1) & 1;
+      mbar_wait(pv_full + pb, (uint32_t)((n_blocks - 1) >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_pv = t_lane + TMEM_PV + (uint32_t)(pb * ATT_HD);
+#pragma unroll
+      for (int c = 0; c < ATT_HD / 32; c++) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_pv + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
+      }
+    }
+    if (q0 + row < N) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * D + h * ATT_HD;
+#pragma unroll
+      for (int i = 0; i < ATT_HD; i += 8) {
+        uint4 pk;
+        pk.x = pack2_bf16(o[i] * inv, o[i + 1] * inv); pk.y = pack2_bf16(o[i + 2] * inv, o[i + 3] * inv);
+        pk.z = pack2_bf16(o[i + 4] * inv, o[i + 5] * inv); pk.w = pack2_bf16(o[i + 6] * inv, o[i + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + i) = pk;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  }
+}
+
+int attention_fwd(const void* qkv, void* out, int B, int N, int H, cudaStream_t st) {
+  DGS_REQUIRE(B > 0 && N > 0 && H > 0, "attention: bad shape B=%d N=%d H=%d", B, N, H);
+  const int D = H * ATT_HD;
+  CUtensorMap tm;
+  uint64_t dims[3] = {(uint64_t)(3 * D), (uint64_t)N, (uint64_t)B};
+  uint64_t str[2] = {(uint64_t)(3 * D) * 2, (uint64_t)N * 3 * D * 2};
+  uint32_t box[3] = {ATT_HD, ATT_BN, 1};
+  int rc = make_tmap_bf16(&tm, qkv, 3, dims, str, box);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid(ceil_div(N, ATT_BM), H, B);
+  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), N, H);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+}  // namespace dgs

@@ -15,7 +15,7 @@ OUT_DIR = os.path.join(HERE, "..", "dgs_b200", "lib")
 OUT = os.path.abspath(os.path.join(OUT_DIR, "libdgs_b200.so"))
 SOURCES = ["core.cu", "raster.cu", "dit_misc.cu", "gemm_sm100.cu", "attention_sm100.cu", "dit_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v" if False else "-O3"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-O3"]
 
 
 def _stale(obj, deps):

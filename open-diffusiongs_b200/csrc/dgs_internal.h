@@ -21,12 +21,38 @@ void set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
-// after a kernel launch: always check the launch itself; in debug mode also synchronise
+// number of kernels of THIS library launched so far (dgs_kernel_launch_count)
+extern unsigned long long g_kernel_launches;
+
+// after a kernel launch: count it, always check the launch itself; in debug mode also synchronise
 #define DGS_LAUNCH_OK(stream, debug)                                   \
   do {                                                                 \
+    ::dgs::g_kernel_launches++;                                        \
     DGS_CUDA_OK(cudaGetLastError());                                   \
     if (debug) DGS_CUDA_OK(cudaStreamSynchronize(stream));             \
   } while (0)
+#define DGS_POST_LAUNCH()                  \
+  do {                                     \
+    ::dgs::g_kernel_launches++;            \
+    DGS_CUDA_OK(cudaGetLastError());       \
+  } while (0)
+
+// Optional per-kernel-family timing (dgs_profile_enable): CUDA events recorded on the launching stream
+// around each family's launches; a no-op (one predictable branch) when disabled.
+enum ProfFamily {
+  PROF_RASTER_PROJECT = 0, PROF_RASTER_SCAN, PROF_RASTER_EMIT, PROF_RASTER_SORT, PROF_RASTER_RANGES,
+  PROF_RASTER_BLEND_FWD, PROF_RASTER_BLEND_BWD, PROF_RASTER_GEOM_BWD,
+  PROF_DIT_INPUT, PROF_DIT_COND, PROF_DIT_LN, PROF_DIT_GEMM_QKV, PROF_DIT_ATTN, PROF_DIT_GEMM_PROJ,
+  PROF_DIT_GEMM_FC1, PROF_DIT_GEMM_FC2, PROF_DIT_HEADS, PROF_N
+};
+extern bool g_prof_on;
+void prof_begin(cudaStream_t st, int family);
+void prof_end(cudaStream_t st, int family);
+struct ProfScope {
+  cudaStream_t st; int fam;
+  ProfScope(cudaStream_t s, int f) : st(s), fam(f) { if (g_prof_on) prof_begin(st, fam); }
+  ~ProfScope() { if (g_prof_on) prof_end(st, fam); }
+};
 
 #define DGS_REQUIRE(cond, ...)             \
   do {                                     \

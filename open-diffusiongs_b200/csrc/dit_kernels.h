@@ -27,16 +27,19 @@ int attention_fwd(const void* qkv, void* out, int B, int N, int H, cudaStream_t 
 // ---- dit_misc.cu -------------------------------------------------------------------------------
 // h[r,:] = (LN(x[r,:]; eps) [* w]) * (1 + scale[b,:]) + shift[b,:]   -> bf16
 // rows are gathered: output row r (0..B*rows_out) reads x row  b*rows_in + row_off + (r % rows_out)
+// split != 0: the output row is [hi | lo | hi] (3*D bf16) with value = hi + lo (split-bf16 operand)
 int ln_modulate(const float* x, const float* ln_weight, const float* shift, const float* scale, int mod_stride,
-                __nv_bfloat16* h, int B, int rows_in, int row_off, int rows_out, int D, float eps, cudaStream_t st);
+                __nv_bfloat16* h, int B, int rows_in, int row_off, int rows_out, int D, float eps, int split,
+                cudaStream_t st);
 // plain LayerNorm with weight (no bias), fp32 -> fp32, in place over [rows, D]
 int ln_weight_inplace(float* x, const float* w, int rows, int D, float eps, cudaStream_t st);
-// out[b, n] = act_in(in[b,:]) . W[n,:] + bias[n], B <= 8, W bf16 [N,K]; act_in: 0 none, 1 SiLU
-int skinny_linear(const float* in, const __nv_bfloat16* W, const float* bias, float* out, int B, int N, int K,
+// out[b, n] = act_in(in[b,:]) . W[n,:] + bias[n], W fp32 [N,K]; act_in: 0 none, 1 SiLU
+int skinny_linear(const float* in, const float* W, const float* bias, float* out, int B, int N, int K,
                   int act_in, int act_out_silu, cudaStream_t st);
 // sinusoidal timestep embedding (denoiser.py:44-66): out [B, 256] = [cos(t f), sin(t f)]
 int timestep_embedding(const float* t, float* out, int B, int dim, cudaStream_t st);
-// Plücker-style posed image + patchify (denoiser.py:312-334, 210-216) -> bf16 tokens [B*V*hh*ww, p*p*9]
+// Plücker-style posed image + patchify (denoiser.py:312-334, 210-216) -> split-bf16 tokens
+// [B*V*hh*ww, 3*p*p*9] = [hi | lo | hi]
 int posed_patchify(const float* images, const float* ray_o, const float* ray_d, __nv_bfloat16* tokens, int B, int V,
                    int H, int W, int patch, int plucker_mode, cudaStream_t st);
 // x[b, 0:G] = pos_embed ; x[b, G:] = tok[b] ; (then the caller applies the input LayerNorm)

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
                                                           const float* __restrict__ shift,
                                                           const float* __restrict__ scale, int mod_stride,
                                                           __nv_bfloat16* __restrict__ h, int B, int rows_in,
-                                                          int row_off, int rows_out, float eps) {
+                                                          int row_off, int rows_out, float eps, int split) {
   constexpr int PER_LANE = D / 32;  // 32 for D = 1024
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * rows_out) return;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
   const float rstd = rsqrtf(warp_sum_f(q) * (1.0f / D) + eps);
   const float* sh = shift + (size_t)b * mod_stride;
   const float* sc = scale + (size_t)b * mod_stride;
-  __nv_bfloat16* hr = h + (size_t)warp * D;
+  __nv_bfloat16* hr = h + (size_t)warp * D * (split ? 3 : 1);
 #pragma unroll
   for (int i = 0; i < PER_LANE / 4; i++) {
     const int c = (i * 32 + lane) * 4;
@@ -61,17 +61,27 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
     pk.x = *reinterpret_cast<uint32_t*>(&p0);
     pk.y = *reinterpret_cast<uint32_t*>(&p1);
     *reinterpret_cast<uint2*>(hr + c) = pk;
+    if (split) {  // [hi | lo | hi]: x = hi + lo to ~2^-17 relative (split-bf16 operand of the head GEMMs)
+      const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+      __nv_bfloat162 q0 = __floats2bfloat162_rn(o0 - f0.x, o1 - f0.y), q1 = __floats2bfloat162_rn(o2 - f1.x, o3 - f1.y);
+      uint2 lo;
+      lo.x = *reinterpret_cast<uint32_t*>(&q0);
+      lo.y = *reinterpret_cast<uint32_t*>(&q1);
+      *reinterpret_cast<uint2*>(hr + D + c) = lo;
+      *reinterpret_cast<uint2*>(hr + 2 * D + c) = pk;
+    }
   }
 }
 
 int ln_modulate(const float* x, const float* ln_weight, const float* shift, const float* scale, int mod_stride,
-                __nv_bfloat16* h, int B, int rows_in, int row_off, int rows_out, int D, float eps, cudaStream_t st) {
+                __nv_bfloat16* h, int B, int rows_in, int row_off, int rows_out, int D, float eps, int split,
+                cudaStream_t st) {
   DGS_REQUIRE(D == 1024, "ln_modulate: width %d not supported (1024 only)", D);
   const long long warps = (long long)B * rows_out;
   const int blocks = (int)((warps * 32 + 255) / 256);
   ln_modulate_kernel<1024><<<blocks, 256, 0, st>>>(x, ln_weight, shift, scale, mod_stride, h, B, rows_in, row_off,
-                                                   rows_out, eps);
-  DGS_CUDA_OK(cudaGetLastError());
+                                                   rows_out, eps, split);
+  DGS_POST_LAUNCH();
   return DGS_OK;
 }
 
@@ -108,13 +118,15 @@ __global__ void __launch_bounds__(256) ln_weight_kernel(float* __restrict__ x, c
 int ln_weight_inplace(float* x, const float* w, int rows, int D, float eps, cudaStream_t st) {
   DGS_REQUIRE(D == 1024, "ln_weight: width %d not supported (1024 only)", D);
   ln_weight_kernel<1024><<<(int)(((long long)rows * 32 + 255) / 256), 256, 0, st>>>(x, w, rows, eps);
-  DGS_CUDA_OK(cudaGetLastError());
+  DGS_POST_LAUNCH();
   return DGS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Skinny linear: out[b, n] = act(in[b, :]) . W[n, :] + bias[n] for b < B <= 8.  HBM-bound on W
-// (each weight row read once, 16-byte loads); one warp per output column n, all B rows at once.
+// (each fp32 weight row read once, 16-byte loads); one warp per output column n, all B rows at once.
+// fp32 weights: the conditioning (shift / scale / gate of every block) multiplies every activation, so
+// bf16-rounding it would put a 1e-3 relative error on the whole network for a saving of ~50 us.
 // Used for the timestep MLP and for the adaLN modulation of ALL 24 blocks + 2 heads in one launch
 // (the conditioning vector is layer-invariant).
 // ---------------------------------------------------------------------------------------------
@@ -123,7 +135,7 @@ constexpr int SKINNY_MAXB = 8;
 __device__ __forceinline__ float silu(float v) { return v / (1.0f + __expf(-v)); }
 
 __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ in,
-                                                            const __nv_bfloat16* __restrict__ W,
+                                                            const float* __restrict__ W,
                                                             const float* __restrict__ bias, float* __restrict__ out,
                                                             int B, int N, int K, int act_in, int act_out) {
   extern __shared__ float s_in[];  // [B, K] activated input
@@ -138,13 +150,11 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
   float acc[SKINNY_MAXB];
 #pragma unroll
   for (int b = 0; b < SKINNY_MAXB; b++) acc[b] = 0.f;
-  const __nv_bfloat16* wr = W + (size_t)n * K;
+  const float* wr = W + (size_t)n * K;
   for (int k = lane * 8; k < K; k += 256) {
-    const uint4 pk = __ldg(reinterpret_cast<const uint4*>(wr + k));
-    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
-    float w[8];
-#pragma unroll
-    for (int j = 0; j < 4; j++) { const float2 f = __bfloat1622float2(p2[j]); w[2 * j] = f.x; w[2 * j + 1] = f.y; }
+    const float4 wa = __ldg(reinterpret_cast<const float4*>(wr + k));
+    const float4 wb = __ldg(reinterpret_cast<const float4*>(wr + k + 4));
+    const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
     for (int b = 0; b < SKINNY_MAXB; b++) {
       if (b < B) {
@@ -166,7 +176,7 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
   }
 }
 
-int skinny_linear(const float* in, const __nv_bfloat16* W, const float* bias, float* out, int B, int N, int K,
+int skinny_linear(const float* in, const float* W, const float* bias, float* out, int B, int N, int K,
                   int act_in, int act_out_silu, cudaStream_t st) {
   DGS_REQUIRE(B >= 1 && K % 8 == 0, "skinny_linear: bad shape B=%d K=%d", B, K);
   for (int b0 = 0; b0 < B; b0 += SKINNY_MAXB) {
@@ -174,7 +184,7 @@ int skinny_linear(const float* in, const __nv_bfloat16* W, const float* bias, fl
     const size_t smem = (size_t)nb * K * sizeof(float);
     skinny_linear_kernel<<<ceil_div(N, 8), 256, smem, st>>>(in + (size_t)b0 * K, W, bias, out + (size_t)b0 * N, nb, N,
                                                             K, act_in, act_out_silu);
-    DGS_CUDA_OK(cudaGetLastError());
+    DGS_POST_LAUNCH();
   }
   return DGS_OK;
 }
@@ -194,7 +204,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
 int timestep_embedding(const float* t, float* out, int B, int dim, cudaStream_t st) {
   DGS_REQUIRE(dim % 2 == 0, "timestep_embedding: odd dim");
   timestep_embedding_kernel<<<ceil_div(B * dim / 2, 128), 128, 0, st>>>(t, out, B, dim);
-  DGS_CUDA_OK(cudaGetLastError());
+  DGS_POST_LAUNCH();
   return DGS_OK;
 }
 
@@ -235,9 +245,19 @@ __global__ void __launch_bounds__(256) posed_patchify_kernel(const float* __rest
     c[3] = o1 * d2 - o2 * d1; c[4] = o2 * d0 - o0 * d2; c[5] = o0 * d1 - o1 * d0;
     c[6] = d0; c[7] = d1; c[8] = d2;
   }
-  __nv_bfloat16* o = tokens + idx * 9;
+  // split-bf16 token row [hi | lo | hi] (K = 3 * p*p*9): the tokenizer GEMM then computes
+  // x_hi W_hi + x_lo W_hi + x_hi W_lo, i.e. an fp32-accurate product on the bf16 tensor-core path
+  const int Kt = p * p * 9;
+  const long long token = idx / (p * p);
+  const int inner = (int)(idx % (p * p)) * 9;
+  __nv_bfloat16* o = tokens + token * 3 * Kt + inner;
 #pragma unroll
-  for (int k = 0; k < 9; k++) o[k] = __float2bfloat16_rn(c[k]);
+  for (int k = 0; k < 9; k++) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(c[k]);
+    o[k] = hi;
+    o[Kt + k] = __float2bfloat16_rn(c[k] - __bfloat162float(hi));
+    o[2 * Kt + k] = hi;
+  }
 }
 
 int posed_patchify(const float* images, const float* ray_o, const float* ray_d, __nv_bfloat16* tokens, int B, int V,
@@ -246,7 +266,7 @@ int posed_patchify(const float* images, const float* ray_o, const float* ray_d, 
   const long long total = (long long)B * V * H * W;
   posed_patchify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(images, ray_o, ray_d, tokens, B * V, H, W,
                                                                           patch, 3, plucker_mode);
-  DGS_CUDA_OK(cudaGetLastError());
+  DGS_POST_LAUNCH();
   return DGS_OK;
 }
 
@@ -266,7 +286,7 @@ __global__ void assemble_tokens_kernel(const float* __restrict__ tok, const floa
 int assemble_tokens(const float* tok, const float* pos_embed, float* x, int B, int G, int T, int D, cudaStream_t st) {
   const long long total = (long long)B * (G + T) * (D / 4);
   assemble_tokens_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tok, pos_embed, x, B, G, T, D / 4);
-  DGS_CUDA_OK(cudaGetLastError());
+  DGS_POST_LAUNCH();
   return DGS_OK;
 }
 
@@ -284,7 +304,7 @@ __global__ void tiny_linear_kernel(const __nv_bfloat16* __restrict__ h, const __
 int tiny_linear_bf16(const __nv_bfloat16* h, const __nv_bfloat16* W, float* out, int rows, int N, int K,
                      cudaStream_t st) {
   tiny_linear_kernel<<<ceil_div(rows * N * 32, 256), 256, 0, st>>>(h, W, out, rows, N, K);
-  DGS_CUDA_OK(cudaGetLastError());
+  DGS_POST_LAUNCH();
   return DGS_OK;
 }
 
@@ -354,7 +374,7 @@ int gaussians_epilogue(const float* gs_tokens, const float* img_gs, const float*
   const long long total = (long long)B * ((long long)G + (long long)V * H * W);
   gaussians_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gs_tokens, img_gs, ray_o, ray_d, out, B, G,
                                                                               V, H, W, patch, scene_mode, near_, far_);
-  DGS_CUDA_OK(cudaGetLastError());
+  DGS_POST_LAUNCH();
   return DGS_OK;
 }
 
@@ -366,7 +386,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
 int f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st) {
   if (n == 0) return DGS_OK;
   f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
-  DGS_CUDA_OK(cudaGetLastError());
+  DGS_POST_LAUNCH();
   return DGS_OK;
 }
 

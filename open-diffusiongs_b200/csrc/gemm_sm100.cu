@@ -263,7 +263,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, ep, M, N, K);
-  DGS_CUDA_OK(cudaGetLastError());
+  DGS_POST_LAUNCH();
   return DGS_OK;
 }
 

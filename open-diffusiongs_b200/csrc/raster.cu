@@ -999,9 +999,15 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
   }
   DGS_LAUNCH_OK(st, debug);
   dim3 pgrid(ceil_div(pb.P, 256), pb.NV);
-  project_kernel<<<pgrid, 256, 0, st>>>(pb, gs, radii);
-  DGS_LAUNCH_OK(st, debug);
-  DGS_CUDA_OK(cub::DeviceScan::InclusiveSum(gs.scan_temp, gs.scan_bytes, gs.tiles, gs.offsets, (int)N, st));
+  {
+    ProfScope ps(st, PROF_RASTER_PROJECT);
+    project_kernel<<<pgrid, 256, 0, st>>>(pb, gs, radii);
+    DGS_LAUNCH_OK(st, debug);
+  }
+  {
+    ProfScope ps(st, PROF_RASTER_SCAN);
+    DGS_CUDA_OK(cub::DeviceScan::InclusiveSum(gs.scan_temp, gs.scan_bytes, gs.tiles, gs.offsets, (int)N, st));
+  }
   uint32_t R32 = 0;
   DGS_CUDA_OK(cudaMemcpyAsync(&R32, gs.offsets + N - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   DGS_CUDA_OK(cudaStreamSynchronize(st));  // the one host sync per batch
@@ -1018,16 +1024,28 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
   const size_t ntiles = (size_t)pb.NV * pb.tiles;
   DGS_CUDA_OK(cudaMemsetAsync(im.ranges, 0, ntiles * sizeof(uint2), st));
   if (R > 0) {
-    emit_keys_kernel<<<pgrid, 256, 0, st>>>(pb, gs, bs.keys_in, bs.vals_in);
-    DGS_LAUNCH_OK(st, debug);
+    {
+      ProfScope ps(st, PROF_RASTER_EMIT);
+      emit_keys_kernel<<<pgrid, 256, 0, st>>>(pb, gs, bs.keys_in, bs.vals_in);
+      DGS_LAUNCH_OK(st, debug);
+    }
     const int end_bit = 32 + bits_for((uint32_t)ntiles);
-    DGS_CUDA_OK(cub::DeviceRadixSort::SortPairs(bs.sort_temp, bs.sort_bytes, bs.keys_in, bs.keys, bs.vals_in,
-                                                bs.point_list, (int)R, 0, end_bit, st));
-    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, bs.keys, im.ranges);
+    {
+      ProfScope ps(st, PROF_RASTER_SORT);
+      DGS_CUDA_OK(cub::DeviceRadixSort::SortPairs(bs.sort_temp, bs.sort_bytes, bs.keys_in, bs.keys, bs.vals_in,
+                                                  bs.point_list, (int)R, 0, end_bit, st));
+    }
+    {
+      ProfScope ps(st, PROF_RASTER_RANGES);
+      tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, bs.keys, im.ranges);
+      DGS_LAUNCH_OK(st, debug);
+    }
+  }
+  {
+    ProfScope ps(st, PROF_RASTER_BLEND_FWD);
+    blend_forward_kernel<<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bs.point_list, out_color);
     DGS_LAUNCH_OK(st, debug);
   }
-  blend_forward_kernel<<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bs.point_list, out_color);
-  DGS_LAUNCH_OK(st, debug);
   return DGS_OK;
 }
 
@@ -1204,6 +1222,7 @@ int dgs_render_batch_backward(const dgs_render_batch_args* a, long long R, const
   float* dcolor = cc.take<float>(N * 3);
   DGS_CUDA_OK(cudaMemsetAsync(sbuf, 0, sbytes, st));
   if (R > 0) {
+    ProfScope ps(st, PROF_RASTER_BLEND_BWD);
     blend_backward_kernel<<<(unsigned)((size_t)pb.NV * pb.tiles), TILE_PIX, 0, st>>>(
         pb, gs, im, bs.point_list, dL_dimages, dmean2D, dconic, dopac, dcolor);
     DGS_LAUNCH_OK(st, a->debug);
@@ -1211,9 +1230,12 @@ int dgs_render_batch_backward(const dgs_render_batch_args* a, long long R, const
   GeomGradOut out;
   out.dmeans = d_xyz; out.dcov3d = nullptr; out.dsh = d_features; out.dscale = d_scaling; out.drot = d_rotation;
   out.dopac_raw = d_opacity;
-  geometry_backward_kernel<<<dim3(ceil_div(a->P, 256), a->B), 256, 0, st>>>(pb, gs, nullptr, dmean2D, dconic, dopac,
-                                                                             dcolor, out);
-  DGS_LAUNCH_OK(st, a->debug);
+  {
+    ProfScope ps(st, PROF_RASTER_GEOM_BWD);
+    geometry_backward_kernel<<<dim3(ceil_div(a->P, 256), a->B), 256, 0, st>>>(pb, gs, nullptr, dmean2D, dconic, dopac,
+                                                                               dcolor, out);
+    DGS_LAUNCH_OK(st, a->debug);
+  }
   return DGS_OK;
 }
 

@@ -27,6 +27,21 @@ class RenderBatchArgs(C.Structure):
                 ("bg", C.c_float * 3), ("debug", C.c_int)]
 
 
+class DitWeights(C.Structure):
+    _fields_ = [("width", C.c_int), ("heads", C.c_int), ("layers", C.c_int), ("patch", C.c_int),
+                ("n_gaussians", C.c_int), ("mlp_hidden", C.c_int)] + [
+        (n, C.c_void_p) for n in (
+            "tokenizer_w", "pos_embed", "in_ln_w", "t0_w", "t0_b", "t2_w", "t2_b", "adaln_w", "adaln_b", "qkv_w",
+            "qkv_b", "proj_w", "proj_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ups_ln_w", "ups_w", "dec_ln_w", "dec_w")]
+
+
+class DitIO(C.Structure):
+    _fields_ = [("B", C.c_int), ("V", C.c_int), ("H", C.c_int), ("W", C.c_int), ("plucker_mode", C.c_int),
+                ("scene_depth", C.c_int), ("range_near", C.c_float), ("range_far", C.c_float)] + [
+        (n, C.c_void_p) for n in ("images", "ray_o", "ray_d", "t", "xyz", "features", "scaling", "rotation",
+                                  "opacity", "img_aligned_xyz", "tokens_out")]
+
+
 _lib = None
 
 
@@ -44,6 +59,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.dgs_last_error.restype = C.c_char_p
         L.dgs_version.restype = C.c_int
+        L.dgs_kernel_launch_count.restype = C.c_ulonglong
+        L.dgs_profile_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         for name in ("dgs_raster_geom_bytes", "dgs_raster_binning_bytes", "dgs_raster_image_bytes"):
             getattr(L, name).restype = C.c_size_t
         L.dgs_raster_geom_bytes.argtypes = [C.c_int, C.c_int]
@@ -58,8 +75,30 @@ def lib():
                                                ALLOC_FN, vp, vp, C.POINTER(C.c_longlong), vp]
         L.dgs_render_batch_backward.argtypes = [C.POINTER(RenderBatchArgs), C.c_longlong] + [vp] * 9 + [ALLOC_FN, vp, vp]
         L.dgs_raster_export_state.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong] + [vp] * 13
+        L.dgs_dit_workspace_bytes.restype = C.c_size_t
+        L.dgs_dit_workspace_bytes.argtypes = [C.POINTER(DitWeights), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.dgs_dit_forward.argtypes = [C.POINTER(DitWeights), C.POINTER(DitIO), vp, C.c_size_t, vp]
+        L.dgs_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, vp]
+        L.dgs_attention_fwd.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        L.dgs_ln_modulate.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
         _lib = L
     return _lib
+
+
+PROF_FAMILIES = ["raster.project", "raster.scan", "raster.emit_keys", "raster.sort", "raster.tile_ranges",
+                 "raster.blend_fwd", "raster.blend_bwd", "raster.geometry_bwd", "dit.input", "dit.conditioning",
+                 "dit.ln_modulate", "dit.gemm_qkv", "dit.attention", "dit.gemm_proj", "dit.gemm_fc1", "dit.gemm_fc2",
+                 "dit.heads"]
+
+
+def profile_read():
+    """-> {family: (total_ms, spans)} of everything recorded since the last read (synchronises)."""
+    n = len(PROF_FAMILIES)
+    ms = (C.c_float * n)()
+    cnt = (C.c_int * n)()
+    lib().dgs_profile_read(ms, cnt, n)
+    return {f: (float(ms[i]), int(cnt[i])) for i, f in enumerate(PROF_FAMILIES)}
 
 
 def check(rc):
@@ -68,7 +107,9 @@ def check(rc):
 
 
 EXPORTED = [  # every symbol include/dgs_b200.h declares (checked by tests/test_abi.py)
-    "dgs_version", "dgs_last_error", "dgs_raster_geom_bytes", "dgs_raster_binning_bytes",
+    "dgs_version", "dgs_last_error", "dgs_kernel_launch_count", "dgs_profile_enable", "dgs_profile_read",
+    "dgs_raster_geom_bytes", "dgs_raster_binning_bytes",
     "dgs_raster_image_bytes", "dgs_raster_forward", "dgs_raster_backward", "dgs_mark_visible",
     "dgs_render_batch_forward", "dgs_render_batch_backward", "dgs_raster_export_state",
+    "dgs_dit_workspace_bytes", "dgs_dit_forward", "dgs_gemm_bf16", "dgs_attention_fwd", "dgs_ln_modulate",
 ]

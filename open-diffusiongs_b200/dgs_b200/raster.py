@@ -12,6 +12,9 @@ from . import _lib
 from ._lib import ALLOC_FN, RasterArgs, RenderBatchArgs, check
 
 
+LAST_NUM_RENDERED = None  # instance count R of the most recent batched forward (bench/roofline bookkeeping)
+
+
 class _Arena:
     """dgs_alloc_fn backed by a torch uint8 tensor (the reference's resizeFunctional,
     rasterize_points.cu:27-33)."""
@@ -158,6 +161,8 @@ def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, f
         R = C.c_longlong(0)
         check(_lib.lib().dgs_render_batch_forward(C.byref(a), geom.cb, None, binning.cb, None, img.cb, None,
                                                   out.data_ptr(), C.byref(R), _stream(dev)))
+    global LAST_NUM_RENDERED
+    LAST_NUM_RENDERED = R.value
     state = dict(tensors=tens, geom=geom.tensor, binning=binning.tensor, img=img.tensor, R=R.value, H=int(H),
                  W=int(W), scale_modifier=scale_modifier)
     return out, state

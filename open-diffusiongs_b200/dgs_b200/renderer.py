@@ -99,8 +99,10 @@ class Renderer(nn.Module):
         C2W [b,v,4,4], fxfycxcy [b,v,4] -> [b,v,3,height,width] fp32.  `deferred` is accepted for
         signature parity: both reference branches compute the same images; here both map to the
         batched kernel set."""
-        return batched_gaussian_render(xyz, features, scaling, rotation, opacity, height, width, C2W, fxfycxcy,
-                                       self.scaling_modifier, getattr(self.config, "use_gssplat", False))
+        out = batched_gaussian_render(xyz, features, scaling, rotation, opacity, height, width, C2W, fxfycxcy,
+                                      self.scaling_modifier, getattr(self.config, "use_gssplat", False))
+        self.last_num_rendered = _raster.LAST_NUM_RENDERED
+        return out
 
     def new_gaussians_model(self):
         return copy.deepcopy(self.gaussians_model)

@@ -49,13 +49,37 @@ GRAD_NAMES = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dco
               "dL_drotations"]
 
 
-def check_grads(ours, ref, tag, skip=()):
+def check_grads(ours, ref, tag, skip=(), noise_floor=None):
+    """`noise_floor`: optional {name: rel_l2 of the REFERENCE kernels vs the fp64-accumulating oracle} on the same
+    inputs -- the fp32 atomics-order / cancellation noise of the specification itself (dL/drotation and dL/dscale are
+    differences of nearly equal terms).  We must be within max(1e-4, 2x that floor)."""
     for name, g in zip(GRAD_NAMES, ours):
         if name in skip or ref[name].size == 0:
             continue
         err = rel_l2(g.cpu().numpy(), ref[name])
-        print(f"  [{tag}] {name}: rel_l2={err:.3e} max_abs={max_abs(g.cpu().numpy(), ref[name]):.3e}")
-        assert err < TOL, (tag, name, err)
+        tol = TOL if not noise_floor else max(TOL, 2.0 * noise_floor.get(name, 0.0))
+        print(f"  [{tag}] {name}: rel_l2={err:.3e} max_abs={max_abs(g.cpu().numpy(), ref[name]):.3e} (tol {tol:.1e})")
+        assert err < tol, (tag, name, err)
+
+
+def reference_noise_floor(sc, st, dpix, sh, degree):
+    """rel_l2 of the reference kernels' own fp32 gradients vs the oracle (None if oracle/_ref is absent)."""
+    from oracle import build_ref
+    from oracle import raster as orc
+    ref = build_ref.load_module()
+    if ref is None:
+        return None
+    a = sc["act"]
+    e = torch.empty(0, device=DEV)
+    args = (T(np.ones(3)), T(a["means3D"]), e, T(a["opacities"]), T(a["scales"]), T(a["rotations"]), 1.0, e,
+            T(sc["view"]), T(sc["proj"]), float(sc["tanx"]), float(sc["tany"]), sc["H"], sc["W"], T(sh), degree,
+            T(sc["campos"]), False, False)
+    Rr, _, radii_r, geom_r, bin_r, img_r = ref.rasterize_gaussians(*args)
+    gr = ref.rasterize_gaussians_backward(args[0], args[1], radii_r, e, args[4], args[5], 1.0, e, args[8], args[9],
+                                          args[10], args[11], T(dpix), args[14], degree, args[16], geom_r, Rr, bin_r,
+                                          img_r, False)
+    g_or = orc.rasterize_backward(st, dpix)
+    return {n: rel_l2(t.cpu().numpy(), g_or[n]) for n, t in zip(GRAD_NAMES, gr) if g_or[n].size}
 
 
 @pytest.mark.parametrize("dist", ["trained", "init", "fine"])
@@ -130,7 +154,10 @@ def test_sh_degree3_colors_precomp_cov_precomp():
         st = oracle_forward(sc, sh=sh, degree=deg)
         fwd = ours_forward(sc, sh=sh, degree=deg)
         assert rel_l2(fwd[1].cpu().numpy(), st["color"]) < TOL
-        check_grads(ours_backward(sc, fwd, dpix, sh=sh, degree=deg), orc.rasterize_backward(st, dpix), f"sh{deg}")
+        floor = reference_noise_floor(sc, st, dpix, sh, deg)
+        print(f"  [sh{deg}] reference-kernel noise floor vs oracle: {floor}")
+        check_grads(ours_backward(sc, fwd, dpix, sh=sh, degree=deg), orc.rasterize_backward(st, dpix), f"sh{deg}",
+                    noise_floor=floor)
     cols = rng.uniform(0, 1, (sc["P"], 3)).astype(np.float32)
     st = oracle_forward(sc, colors=cols)
     fwd = ours_forward(sc, colors=cols)
