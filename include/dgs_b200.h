@@ -219,6 +219,24 @@ int dgs_attention_fwd(const void* qkv, void* out, int B, int N, int heads, void*
 int dgs_ln_modulate(const float* x, const float* ln_w, const float* shift, const float* scale, int mod_stride,
                     void* h, int B, int rows, int width, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * B3. The elementwise callers either side of the path.
+ * ---------------------------------------------------------------------------------------------- */
+/* TransformInput (diffusionGS/systems/utils.py:621-757, patch_size=None): per-pixel world-space rays.
+ * c2w [n_views,4,4] row-major, fxfycxcy [n_views,4] -> ray_o, ray_d [n_views,3,H,W] (ray_d normalised). */
+int dgs_rays_from_cameras(const float* c2w, const float* fxfycxcy, int n_views, int H, int W, float* ray_o,
+                          float* ray_d, void* stream);
+/* GaussianDiffusion.q_sample (gaussian_diffusion.py:268-284): out = sqrt_ac[t[b]]*x_start + sqrt_1mac[t[b]]*noise.
+ * Tables are DEVICE fp32 arrays indexed by timestep; t is int64 [B]; per_sample = elements per batch item. */
+int dgs_q_sample(const float* x_start, const float* noise, const float* sqrt_alphas_cumprod,
+                 const float* sqrt_one_minus_alphas_cumprod, const long long* t, int B, long long per_sample,
+                 float* out, void* stream);
+/* One ancestral step of p_sample with x0-prediction and FIXED_LARGE variance (gaussian_diffusion.py:291-312,
+ * 380-392, 505-516): out = coef1[t]*pred_xstart + coef2[t]*x_t + (t != 0) * exp(0.5*log_var[t]) * noise. */
+int dgs_p_sample_step(const float* pred_xstart, const float* x_t, const float* noise, const float* posterior_mean_coef1,
+                      const float* posterior_mean_coef2, const float* model_log_variance, const long long* t, int B,
+                      long long per_sample, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
