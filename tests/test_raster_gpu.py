@@ -62,7 +62,7 @@ def check_grads(ours, ref, tag, skip=(), noise_floor=None):
         assert err < tol, (tag, name, err)
 
 
-def reference_noise_floor(sc, st, dpix, sh, degree):
+def reference_noise_floor(sc, st, dpix, sh, degree, colors=None, cov3d=None):
     """rel_l2 of the reference kernels' own fp32 gradients vs the oracle (None if oracle/_ref is absent)."""
     from oracle import build_ref
     from oracle import raster as orc
@@ -71,11 +71,14 @@ def reference_noise_floor(sc, st, dpix, sh, degree):
         return None
     a = sc["act"]
     e = torch.empty(0, device=DEV)
-    args = (T(np.ones(3)), T(a["means3D"]), e, T(a["opacities"]), T(a["scales"]), T(a["rotations"]), 1.0, e,
-            T(sc["view"]), T(sc["proj"]), float(sc["tanx"]), float(sc["tany"]), sc["H"], sc["W"], T(sh), degree,
-            T(sc["campos"]), False, False)
+    col = e if colors is None else T(colors)
+    cov = e if cov3d is None else T(cov3d)
+    args = (T(np.ones(3)), T(a["means3D"]), col, T(a["opacities"]), e if cov3d is not None else T(a["scales"]),
+            e if cov3d is not None else T(a["rotations"]), 1.0, cov, T(sc["view"]), T(sc["proj"]), float(sc["tanx"]),
+            float(sc["tany"]), sc["H"], sc["W"], e if colors is not None else T(sh), degree, T(sc["campos"]), False,
+            False)
     Rr, _, radii_r, geom_r, bin_r, img_r = ref.rasterize_gaussians(*args)
-    gr = ref.rasterize_gaussians_backward(args[0], args[1], radii_r, e, args[4], args[5], 1.0, e, args[8], args[9],
+    gr = ref.rasterize_gaussians_backward(args[0], args[1], radii_r, col, args[4], args[5], 1.0, cov, args[8], args[9],
                                           args[10], args[11], T(dpix), args[14], degree, args[16], geom_r, Rr, bin_r,
                                           img_r, False)
     g_or = orc.rasterize_backward(st, dpix)
@@ -162,13 +165,15 @@ def test_sh_degree3_colors_precomp_cov_precomp():
     st = oracle_forward(sc, colors=cols)
     fwd = ours_forward(sc, colors=cols)
     assert rel_l2(fwd[1].cpu().numpy(), st["color"]) < TOL
-    check_grads(ours_backward(sc, fwd, dpix, colors=cols), orc.rasterize_backward(st, dpix), "colors_precomp")
+    check_grads(ours_backward(sc, fwd, dpix, colors=cols), orc.rasterize_backward(st, dpix), "colors_precomp",
+                noise_floor=reference_noise_floor(sc, st, dpix, None, 0, colors=cols))
     cov = oracle_forward(sc)["cov3D"]
     st = oracle_forward(sc, cov3d=cov)
     fwd = ours_forward(sc, cov3d=cov)
     assert rel_l2(fwd[1].cpu().numpy(), st["color"]) < TOL
     check_grads(ours_backward(sc, fwd, dpix, cov3d=cov), orc.rasterize_backward(st, dpix), "cov_precomp",
-                skip=("dL_dscales", "dL_drotations"))
+                skip=("dL_dscales", "dL_drotations"),
+                noise_floor=reference_noise_floor(sc, st, dpix, sc["act"]["shs"], 0, cov3d=cov))
 
 
 def test_edge_cases_empty_culled_ragged():
