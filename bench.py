@@ -214,7 +214,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -374,7 +374,7 @@ def main():
         breakdown_ms=dict(dit=dit_ms, raster=ras_ms, families={k: round(v, 4) for k, v in fam_ms.items()},
                           share=share, launches_per_step=fam_n),
         dit_tflops=dit_forward_flops() * args.batch / (dit_ms * 1e-3) / 1e12 if dit_ms else None,
-        step_ms_min=min(step_ms), step_ms_max=max(step_ms),
+        step_ms_min=min(step_ms), step_ms_max=max(step_ms), step_ms=[round(v, 3) for v in step_ms],
     )
     print(json.dumps(line))
     if world > 1:

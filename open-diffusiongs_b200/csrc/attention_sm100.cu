@@ -5,10 +5,11 @@
 // reading q/k/v straight out of the fused qkv GEMM output [B, N, 3, H, 64] (bf16) through ONE 3-D TMA tensor
 // map (no head-major re-layout), N arbitrary (4098 = 32*128 + 2: the tail is zero-filled by TMA and masked).
 //
-// One CTA per (128-query block, head, sample); 256 threads:
-//   warp 0      TMA producer: Q once, K/V blocks of 128 keys through a 3-stage ring
+// One CTA per (128-query block, head, sample); 192 threads, TWO CTAs resident per SM (96 KB smem, 256 TMEM columns,
+// <= 168 registers each) so one CTA's tensor-core work runs under the other's softmax:
+//   warp 0      TMA producer: Q once, K/V blocks of 64 keys through a 3-stage ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:  S_j = Q K_j^T  and  PV_j = P_j V_j
-//   warps 4..7  online softmax, one query row per thread: S_j (TMEM) -> p = exp2(..) -> P_j (bf16, swizzled smem,
+//   warps 2..5  online softmax, one query row per thread: S_j (TMEM) -> p = exp2(..) -> P_j (bf16, swizzled smem,
 //               A operand of the PV MMA); O accumulated in registers from PV_j (TMEM), rescaled by exp2(m_old - m_new)
 // S and PV are double-buffered in TMEM so QK^T of block j+1 runs under the softmax of block j.
 #include "dgs_internal.h"
@@ -19,26 +20,28 @@ namespace dgs {
 
 using namespace ptx;
 
-constexpr int ATT_BM = 128, ATT_BN = 128, ATT_HD = 64, ATT_KV_STAGES = 3, ATT_THREADS = 256;
-constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // one [128 x 64] bf16 tile (Q, K, V, half of P)
-constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES + 4) + 1024 + 256;
-constexpr uint32_t TMEM_S = 0, TMEM_PV = 256, ATT_TMEM_COLS = 512;
+constexpr int ATT_BM = 128, ATT_BN = 64, ATT_HD = 64, ATT_KV_STAGES = 3, ATT_THREADS = 192;
+constexpr int ATT_Q_BYTES = ATT_BM * ATT_HD * 2;    // [128 x 64] bf16 (Q, and one P buffer: 128 rows x 64 keys)
+constexpr int ATT_KV_BYTES = ATT_BN * ATT_HD * 2;   // [64 x 64] bf16 (one K or V block)
+constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES * 3 + 2 * ATT_KV_STAGES * ATT_KV_BYTES + 1024 + 256;
+constexpr uint32_t TMEM_S = 0, TMEM_PV = 2 * ATT_BN, ATT_TMEM_COLS = 256;
 
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int N, int H) {
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                     __nv_bfloat16* __restrict__ out, int N, int H) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_TILE_BYTES;
-  uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;
-  uint8_t* sP = sV + ATT_KV_STAGES * ATT_TILE_BYTES;  // 2 buffers x (2 x [128 x 64]) bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE_BYTES);
+  uint8_t* sP = sQ + ATT_Q_BYTES;                      // 2 buffers x [128 x 64] bf16
+  uint8_t* sK = sP + 2 * ATT_Q_BYTES;
+  uint8_t* sV = sK + ATT_KV_STAGES * ATT_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_KV_STAGES * ATT_KV_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* v_full = k_full + ATT_KV_STAGES;
@@ -54,7 +57,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* 
   const int D = H * ATT_HD;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tm_qkv);
+    prefetch_tmap(&tm_q);
+    prefetch_tmap(&tm_kv);
     mbar_init(q_full, 1);
     for (int s = 0; s < ATT_KV_STAGES; s++) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(kv_empty + s, 1); }
     for (int s = 0; s < 2; s++) { mbar_init(s_full + s, 1); mbar_init(p_full + s, 128); mbar_init(pv_full + s, 1); }
@@ -72,16 +76,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_3d(sQ, &tm_qkv, q_full, h * ATT_HD, q0, b);
+      mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
+      tma_load_3d(sQ, &tm_q, q_full, h * ATT_HD, q0, b);
       for (int j = 0; j < n_blocks; j++) {
         const int s = j % ATT_KV_STAGES;
         const uint32_t use = (uint32_t)(j / ATT_KV_STAGES);
         mbar_wait(kv_empty + s, (use & 1) ^ 1);
-        mbar_arrive_expect_tx(k_full + s, ATT_TILE_BYTES);
-        tma_load_3d(sK + s * ATT_TILE_BYTES, &tm_qkv, k_full + s, D + h * ATT_HD, j * ATT_BN, b);
-        mbar_arrive_expect_tx(v_full + s, ATT_TILE_BYTES);
-        tma_load_3d(sV + s * ATT_TILE_BYTES, &tm_qkv, v_full + s, 2 * D + h * ATT_HD, j * ATT_BN, b);
+        mbar_arrive_expect_tx(k_full + s, ATT_KV_BYTES);
+        tma_load_3d(sK + s * ATT_KV_BYTES, &tm_kv, k_full + s, D + h * ATT_HD, j * ATT_BN, b);
+        mbar_arrive_expect_tx(v_full + s, ATT_KV_BYTES);
+        tma_load_3d(sV + s * ATT_KV_BYTES, &tm_kv, v_full + s, 2 * D + h * ATT_HD, j * ATT_BN, b);
       }
     }
   } else if (warp == 1) {
@@ -94,7 +98,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* 
         const int s = j % ATT_KV_STAGES;
         mbar_wait(k_full + s, (uint32_t)(j / ATT_KV_STAGES) & 1);
         tc_fence_after();
-        const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s * ATT_TILE_BYTES), 16, 1024);
+        const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s * ATT_KV_BYTES), 16, 1024);
         const uint32_t d = tmem_base + TMEM_S + (uint32_t)((j & 1) * ATT_BN);
 #pragma unroll
         for (int k = 0; k < ATT_HD / 16; k++) umma_bf16(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
@@ -108,23 +112,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* 
         mbar_wait(p_full + (j & 1), (uint32_t)(j >> 1) & 1);
         mbar_wait(v_full + s, (uint32_t)(j / ATT_KV_STAGES) & 1);
         tc_fence_after();
-        const uint32_t pbase = smem_u32(sP + (j & 1) * 2 * ATT_TILE_BYTES);
-        const uint32_t vbase = smem_u32(sV + s * ATT_TILE_BYTES);
+        const uint32_t pbase = smem_u32(sP + (j & 1) * ATT_Q_BYTES);
+        const uint32_t vbase = smem_u32(sV + s * ATT_KV_BYTES);
         const uint32_t d = tmem_base + TMEM_PV + (uint32_t)((j & 1) * ATT_HD);
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; k++) {
-          // A = P: K-major, two 64-key sub-tiles; 16 keys = 32 bytes inside the swizzled 128-byte row
-          const uint64_t pdesc = make_smem_desc_sw128(pbase + (uint32_t)((k >> 2) * ATT_TILE_BYTES + (k & 3) * 32), 16, 1024);
+          // A = P: K-major [128 rows x 64 keys]; 16 keys = 32 bytes inside the swizzled 128-byte row
+          const uint64_t pdesc = make_smem_desc_sw128(pbase + (uint32_t)(k * 32), 16, 1024);
           // B = V: MN-major ([key][64 dims] rows of 128 bytes); 16 keys = 2 groups of 8 rows = 2048 bytes
-          const uint64_t vdesc = make_smem_desc_sw128(vbase + (uint32_t)(k * 2048), ATT_TILE_BYTES, 1024);
+          const uint64_t vdesc = make_smem_desc_sw128(vbase + (uint32_t)(k * 2048), ATT_KV_BYTES, 1024);
           umma_bf16(d, pdesc, vdesc, idesc_pv, k ? 1u : 0u);
         }
         umma_commit(pv_full + (j & 1));
         umma_commit(kv_empty + s);
       }
     }
-  } else if (warp >= 4) {
-    // ===================== softmax / output: one query row per thread =====================
+  } else {
+    // ===================== softmax / output (warps 2..5): one query row per thread =====================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -141,45 +145,40 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* 
       tc_fence_after();
       const uint32_t t_s = t_lane + TMEM_S + (uint32_t)(buf * ATT_BN);
       const int kv_valid = N - j * ATT_BN;  // >= 1
-      // pass 1: row maximum
+      // the whole 64-key row of S in registers: two TMEM loads in flight, one wait
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(t_s, r0);
+      tmem_ld_32x32(t_s + 32u, r1);
+      tmem_ld_wait();
       float m_blk = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < ATT_BN / 32; c++) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_s + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const float v = (c * 32 + i < kv_valid) ? __uint_as_float(r[i]) : -INFINITY;
-          m_blk = fmaxf(m_blk, v);
-        }
+      for (int i = 0; i < 32; i++) {
+        const float a = (i < kv_valid) ? __uint_as_float(r0[i]) : -INFINITY;
+        const float c = (32 + i < kv_valid) ? __uint_as_float(r1[i]) : -INFINITY;
+        m_blk = fmaxf(m_blk, fmaxf(a, c));
       }
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = exp2f((m_run - m_new) * sl2);  // exp2(-inf) = 0 on the first block
       const float moff = m_new * sl2;
-      // pass 2: p = exp2(s*sl2 - moff) -> bf16 -> swizzled smem (K-major A operand), row sum
+      // p = exp2(s*sl2 - moff) -> bf16 -> swizzled smem (K-major A operand), row sum
       float l_blk = 0.f;
-      uint8_t* p_row = sP + buf * 2 * ATT_TILE_BYTES + row * 128;
-#pragma unroll 1
-      for (int c = 0; c < ATT_BN / 32; c++) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_s + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
+      uint8_t* p_row = sP + buf * ATT_Q_BYTES + row * 128;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
         float p[32];
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-          const float v = exp2f(fmaf(__uint_as_float(r[i]), sl2, -moff));
-          p[i] = (c * 32 + i < kv_valid) ? v : 0.f;
+          const float sv = __uint_as_float(half ? r1[i] : r0[i]);
+          const float v = exp2f(fmaf(sv, sl2, -moff));
+          p[i] = (half * 32 + i < kv_valid) ? v : 0.f;
           l_blk += p[i];
         }
-        uint8_t* blk = p_row + (c >> 1) * ATT_TILE_BYTES;  // 64-key sub-tile
-        const int chunk0 = (c & 1) * 4;                    // 16-byte chunk index inside the 128-byte row
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           uint4 pk;
           pk.x = pack2_bf16(p[8 * q], p[8 * q + 1]); pk.y = pack2_bf16(p[8 * q + 2], p[8 * q + 3]);
           pk.z = pack2_bf16(p[8 * q + 4], p[8 * q + 5]); pk.w = pack2_bf16(p[8 * q + 6], p[8 * q + 7]);
-          *reinterpret_cast<uint4*>(blk + (((chunk0 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
+          *reinterpret_cast<uint4*>(p_row + (((half * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
         }
       }
       l_run = l_run * alpha + l_blk;
@@ -193,13 +192,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* 
         mbar_wait(pv_full + pb, (uint32_t)((j - 1) >> 1) & 1);
         tc_fence_after();
         const uint32_t t_pv = t_lane + TMEM_PV + (uint32_t)(pb * ATT_HD);
+        uint32_t q0r[32], q1r[32];
+        tmem_ld_32x32(t_pv, q0r);
+        tmem_ld_32x32(t_pv + 32u, q1r);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < ATT_HD / 32; c++) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_pv + (uint32_t)(c * 32), r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i++) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; i++) {
+          o[i] = fmaf(o[i], alpha_prev, __uint_as_float(q0r[i]));
+          o[32 + i] = fmaf(o[32 + i], alpha_prev, __uint_as_float(q1r[i]));
         }
       }
       alpha_prev = alpha;
@@ -241,11 +241,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* 
 int attention_fwd(const void* qkv, void* out, int B, int N, int H, cudaStream_t st) {
   DGS_REQUIRE(B > 0 && N > 0 && H > 0, "attention: bad shape B=%d N=%d H=%d", B, N, H);
   const int D = H * ATT_HD;
-  CUtensorMap tm;
+  CUtensorMap tm_q, tm_kv;
   uint64_t dims[3] = {(uint64_t)(3 * D), (uint64_t)N, (uint64_t)B};
   uint64_t str[2] = {(uint64_t)(3 * D) * 2, (uint64_t)N * 3 * D * 2};
-  uint32_t box[3] = {ATT_HD, ATT_BN, 1};
-  int rc = make_tmap_bf16(&tm, qkv, 3, dims, str, box);
+  uint32_t box_q[3] = {ATT_HD, ATT_BM, 1}, box_kv[3] = {ATT_HD, ATT_BN, 1};
+  int rc = make_tmap_bf16(&tm_q, qkv, 3, dims, str, box_q);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tm_kv, qkv, 3, dims, str, box_kv);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -253,7 +255,7 @@ int attention_fwd(const void* qkv, void* out, int B, int N, int H, cudaStream_t 
     configured = true;
   }
   dim3 grid(ceil_div(N, ATT_BM), H, B);
-  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), N, H);
+  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, reinterpret_cast<__nv_bfloat16*>(out), N, H);
   DGS_POST_LAUNCH();
   return DGS_OK;
 }
