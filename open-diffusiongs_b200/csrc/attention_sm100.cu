@@ -9,9 +9,12 @@
 // <= 168 registers each) so one CTA's tensor-core work runs under the other's softmax:
 //   warp 0      TMA producer: Q once, K/V blocks of 64 keys through a 3-stage ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:  S_j = Q K_j^T  and  PV_j = P_j V_j
-//   warps 2..5  online softmax, one query row per thread: S_j (TMEM) -> p = exp2(..) -> P_j (bf16, swizzled smem,
-//               A operand of the PV MMA); O accumulated in registers from PV_j (TMEM), rescaled by exp2(m_old - m_new)
-// S and PV are double-buffered in TMEM so QK^T of block j+1 runs under the softmax of block j.
+//   warps 2..5  online softmax, one query row per thread: S_j (TMEM) -> p = ex2(..) -> P_j (bf16, swizzled smem,
+//               A operand of the PV MMA).  O accumulates IN TMEM across all key blocks (the PV MMA adds into it);
+//               the softmax rows rescale it (tcgen05.ld / st) only when their running max grows by more than 2^8
+//               -- otherwise the stale max keeps being used, which is exact after the final 1/l normalisation.
+// S is double-buffered in TMEM so QK^T of block j+1 runs under the softmax of block j.  The softmax is bound by
+// the MUFU ex2 pipe (16/clk/SM), so the per-element instruction count is kept at max + fma + ex2 + add + cvt/2.
 #include "dgs_internal.h"
 #include "dit_kernels.h"
 #include "sm100_ptx.cuh"
@@ -24,7 +27,8 @@ constexpr int ATT_BM = 128, ATT_BN = 64, ATT_HD = 64, ATT_KV_STAGES = 3, ATT_THR
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_HD * 2;    // [128 x 64] bf16 (Q, and one P buffer: 128 rows x 64 keys)
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_HD * 2;   // [64 x 64] bf16 (one K or V block)
 constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES * 3 + 2 * ATT_KV_STAGES * ATT_KV_BYTES + 1024 + 256;
-constexpr uint32_t TMEM_S = 0, TMEM_PV = 2 * ATT_BN, ATT_TMEM_COLS = 256;
+constexpr uint32_t TMEM_S = 0, TMEM_O = 2 * ATT_BN, ATT_TMEM_COLS = 256;
+constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: rescale O only if the row max grew by > 2^8
 
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -114,14 +118,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tc_fence_after();
         const uint32_t pbase = smem_u32(sP + (j & 1) * ATT_Q_BYTES);
         const uint32_t vbase = smem_u32(sV + s * ATT_KV_BYTES);
-        const uint32_t d = tmem_base + TMEM_PV + (uint32_t)((j & 1) * ATT_HD);
+        const uint32_t d = tmem_base + TMEM_O;
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; k++) {
           // A = P: K-major [128 rows x 64 keys]; 16 keys = 32 bytes inside the swizzled 128-byte row
           const uint64_t pdesc = make_smem_desc_sw128(pbase + (uint32_t)(k * 32), 16, 1024);
           // B = V: MN-major ([key][64 dims] rows of 128 bytes); 16 keys = 2 groups of 8 rows = 2048 bytes
           const uint64_t vdesc = make_smem_desc_sw128(vbase + (uint32_t)(k * 2048), ATT_KV_BYTES, 1024);
-          umma_bf16(d, pdesc, vdesc, idesc_pv, k ? 1u : 0u);
+          umma_bf16(d, pdesc, vdesc, idesc_pv, (j | k) ? 1u : 0u);  // O += P_j V_j (first block overwrites)
         }
         umma_commit(pv_full + (j & 1));
         umma_commit(kv_empty + s);
@@ -133,45 +137,71 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    float o[ATT_HD];
-#pragma unroll
-    for (int i = 0; i < ATT_HD; i++) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    const uint32_t t_o = t_lane + TMEM_O;
+    float m_run = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < n_blocks; j++) {
       const int buf = j & 1;
-      const uint32_t ph = (uint32_t)(j >> 1) & 1;
-      mbar_wait(s_full + buf, ph);
+      mbar_wait(s_full + buf, (uint32_t)(j >> 1) & 1);
       tc_fence_after();
       const uint32_t t_s = t_lane + TMEM_S + (uint32_t)(buf * ATT_BN);
-      const int kv_valid = N - j * ATT_BN;  // >= 1
-      // the whole 64-key row of S in registers: two TMEM loads in flight, one wait
+      const int kv_valid = N - j * ATT_BN;  // >= 1; < ATT_BN only in the last block
       uint32_t r0[32], r1[32];
       tmem_ld_32x32(t_s, r0);
       tmem_ld_32x32(t_s + 32u, r1);
       tmem_ld_wait();
-      float m_blk = -INFINITY;
+      if (kv_valid < ATT_BN) {  // warp-uniform: mask the zero-filled tail keys
 #pragma unroll
-      for (int i = 0; i < 32; i++) {
-        const float a = (i < kv_valid) ? __uint_as_float(r0[i]) : -INFINITY;
-        const float c = (32 + i < kv_valid) ? __uint_as_float(r1[i]) : -INFINITY;
-        m_blk = fmaxf(m_blk, fmaxf(a, c));
+        for (int i = 0; i < 32; i++) {
+          if (i >= kv_valid) r0[i] = 0xff800000u;       // -inf
+          if (32 + i >= kv_valid) r1[i] = 0xff800000u;
+        }
       }
-      const float m_new = fmaxf(m_run, m_blk);
-      const float alpha = exp2f((m_run - m_new) * sl2);  // exp2(-inf) = 0 on the first block
-      const float moff = m_new * sl2;
-      // p = exp2(s*sl2 - moff) -> bf16 -> swizzled smem (K-major A operand), row sum
-      float l_blk = 0.f;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(r1[i])); mx3 = fmaxf(mx3, __uint_as_float(r1[i + 1]));
+      }
+      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // lazy rescale: keep the stale max unless it is exceeded by more than the threshold
+      float alpha = 1.0f;
+      const bool grow = (m_blk - m_run) * sl2 > ATT_RESCALE_THRESHOLD;  // true on the first block (m_run = -inf)
+      if (grow) {
+        alpha = ex2_approx((m_run - m_blk) * sl2);  // 0 on the first block
+        m_run = m_blk;
+      }
+      // P_{j-2} (same smem buffer) must have been consumed, and for a rescale O must hold every earlier block:
+      if (j >= 2) mbar_wait(pv_full + buf, (uint32_t)((j - 2) >> 1) & 1);
+      if (j >= 1 && __any_sync(0xffffffffu, grow)) {
+        mbar_wait(pv_full + (buf ^ 1), (uint32_t)((j - 1) >> 1) & 1);
+        tc_fence_after();
+        uint32_t q0r[32], q1r[32];
+        tmem_ld_32x32(t_o, q0r);
+        tmem_ld_32x32(t_o + 32u, q1r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          q0r[i] = __float_as_uint(__uint_as_float(q0r[i]) * alpha);
+          q1r[i] = __float_as_uint(__uint_as_float(q1r[i]) * alpha);
+        }
+        tmem_st_32x32(t_o, q0r);
+        tmem_st_32x32(t_o + 32u, q1r);
+        tmem_st_wait();
+      }
+      const float moff = m_run * sl2;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       uint8_t* p_row = sP + buf * ATT_Q_BYTES + row * 128;
 #pragma unroll
       for (int half = 0; half < 2; half++) {
         float p[32];
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const float sv = __uint_as_float(half ? r1[i] : r0[i]);
-          const float v = exp2f(fmaf(sv, sl2, -moff));
-          p[i] = (half * 32 + i < kv_valid) ? v : 0.f;
-          l_blk += p[i];
+        for (int i = 0; i < 32; i += 4) {
+          p[i] = ex2_approx(fmaf(__uint_as_float(half ? r1[i] : r0[i]), sl2, -moff));
+          p[i + 1] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 1] : r0[i + 1]), sl2, -moff));
+          p[i + 2] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 2] : r0[i + 2]), sl2, -moff));
+          p[i + 3] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 3] : r0[i + 3]), sl2, -moff));
+          l0 += p[i]; l1 += p[i + 1]; l2 += p[i + 2]; l3 += p[i + 3];
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -181,52 +211,40 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           *reinterpret_cast<uint4*>(p_row + (((half * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
         }
       }
-      l_run = l_run * alpha + l_blk;
-      m_run = m_new;
+      l_run = l_run * alpha + ((l0 + l1) + (l2 + l3));
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();    // our tcgen05.ld of S_j are complete before the issuer may overwrite S
+      tc_fence_before();    // our tcgen05.ld/st of S_j and O are complete before the issuer proceeds
       mbar_arrive(p_full + buf);
-      // fold in PV_{j-1} (relative to the previous running max): O = O * alpha_{j-1} + PV_{j-1}
-      if (j > 0) {
-        const int pb = (j - 1) & 1;
-        mbar_wait(pv_full + pb, (uint32_t)((j - 1) >> 1) & 1);
-        tc_fence_after();
-        const uint32_t t_pv = t_lane + TMEM_PV + (uint32_t)(pb * ATT_HD);
-        uint32_t q0r[32], q1r[32];
-        tmem_ld_32x32(t_pv, q0r);
-        tmem_ld_32x32(t_pv + 32u, q1r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          o[i] = fmaf(o[i], alpha_prev, __uint_as_float(q0r[i]));
-          o[32 + i] = fmaf(o[32 + i], alpha_prev, __uint_as_float(q1r[i]));
-        }
-      }
-      alpha_prev = alpha;
     }
-    {  // last block's PV
-      const int pb = (n_blocks - 1) & 1;
-      mbar_wait(pv_full + pb, (uint32_t)((n_blocks - 1) >> 1) & 1);
+    {  // all blocks accumulated -> normalise and store
+      const int last = n_blocks - 1;
+      mbar_wait(pv_full + (last & 1), (uint32_t)(last >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_pv = t_lane + TMEM_PV + (uint32_t)(pb * ATT_HD);
+      uint32_t q0r[32], q1r[32];
+      tmem_ld_32x32(t_o, q0r);
+      tmem_ld_32x32(t_o + 32u, q1r);
+      tmem_ld_wait();
+      if (q0 + row < N) {
+        const float inv = 1.0f / l_run;
+        __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * D + h * ATT_HD;
 #pragma unroll
-      for (int c = 0; c < ATT_HD / 32; c++) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_pv + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk;
+          pk.x = pack2_bf16(__uint_as_float(q0r[i]) * inv, __uint_as_float(q0r[i + 1]) * inv);
+          pk.y = pack2_bf16(__uint_as_float(q0r[i + 2]) * inv, __uint_as_float(q0r[i + 3]) * inv);
+          pk.z = pack2_bf16(__uint_as_float(q0r[i + 4]) * inv, __uint_as_float(q0r[i + 5]) * inv);
+          pk.w = pack2_bf16(__uint_as_float(q0r[i + 6]) * inv, __uint_as_float(q0r[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + i) = pk;
+        }
 #pragma unroll
-        for (int i = 0; i < 32; i++) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
-      }
-    }
-    if (q0 + row < N) {
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * D + h * ATT_HD;
-#pragma unroll
-      for (int i = 0; i < ATT_HD; i += 8) {
-        uint4 pk;
-        pk.x = pack2_bf16(o[i] * inv, o[i + 1] * inv); pk.y = pack2_bf16(o[i + 2] * inv, o[i + 3] * inv);
-        pk.z = pack2_bf16(o[i + 4] * inv, o[i + 5] * inv); pk.w = pack2_bf16(o[i + 6] * inv, o[i + 7] * inv);
-        *reinterpret_cast<uint4*>(dst + i) = pk;
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk;
+          pk.x = pack2_bf16(__uint_as_float(q1r[i]) * inv, __uint_as_float(q1r[i + 1]) * inv);
+          pk.y = pack2_bf16(__uint_as_float(q1r[i + 2]) * inv, __uint_as_float(q1r[i + 3]) * inv);
+          pk.z = pack2_bf16(__uint_as_float(q1r[i + 4]) * inv, __uint_as_float(q1r[i + 5]) * inv);
+          pk.w = pack2_bf16(__uint_as_float(q1r[i + 6]) * inv, __uint_as_float(q1r[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 32 + i) = pk;
+        }
       }
     }
   }
