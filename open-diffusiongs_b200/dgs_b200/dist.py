@@ -1,0 +1,123 @@
+"""Data-parallel plumbing of the hot path.
+
+The reference's only collective is Lightning DDP's gradient all-reduce (`strategy: ddp_find_unused_parameters_true`,
+diffusionGS/configs/diffusionGS_rel.yaml:80): 460,391,424 fp32 gradients per step, default 25 MB buckets, then a local
+grad-norm clip at 0.5 (diffusionGS_rel.yaml:77).  Here the gradients live in ONE flat, pre-allocated arena (each
+`param.grad` is a view into it, so backward kernels write their results in place and nothing is copied or bucketed
+at step time); the all-reduce is issued per DiT block in REVERSE order (the order the backward produces them) on a
+side stream over NCCL / NVLink, and the clip is a single fused norm over the arena.  One process per GPU.
+
+Everything is torch.distributed: `nccl` on GPUs, `gloo` in the CPU tests (world_size 2).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None, device=None):
+    """Rendezvous from torchrun's RANK / WORLD_SIZE / MASTER_* (127.0.0.1 when unset)."""
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if not dist.is_initialized():
+        kw = {}
+        if backend == "nccl" and device is not None:
+            kw["device_id"] = device
+        dist.init_process_group(backend, **kw)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def max_over_ranks(value: float, device="cpu") -> float:
+    """Device-time aggregation rule of bench.py: a multi-GPU time is the MAX over ranks."""
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+def whole_job_throughput(units_per_rank: float, seconds_local: float, device="cpu") -> float:
+    """value = units processed by ALL ranks / max-over-ranks time (weak scaling, no data-path collective)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    return world * units_per_rank / max_over_ranks(seconds_local, device)
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous, balanced partition of a batch of independent samples over ranks (the path shards by sample)."""
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+class GradArena:
+    """Flat gradient arena + bucketed (per transformer block, reverse order) all-reduce + fused clip."""
+
+    def __init__(self, module: torch.nn.Module, dtype=torch.float32, bucket_key=None):
+        params = [p for p in module.parameters() if p.requires_grad]
+        names = {id(p): n for n, p in module.named_parameters()}
+        self.params = params
+        total = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.flat = torch.zeros(total, dtype=dtype, device=dev)
+        # bucket = "transformer.<i>" for block parameters, "other" for the rest (tokenizer, heads, embedder)
+        key = bucket_key or (lambda n: ".".join(n.split(".")[:2]) if n.startswith("transformer.") else "other")
+        self.buckets = {}  # name -> [start, end) in arena order
+        off, last_base, last_name = 0, None, None
+        for p in params:
+            base = key(names[id(p)])
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            if base == last_base:  # contiguous run of the same key: extend
+                self.buckets[last_name][1] = off + n
+            else:                  # new run (a key that re-appears later gets a suffixed bucket of its own)
+                last_name = base if base not in self.buckets else f"{base}#{off}"
+                self.buckets[last_name] = [off, off + n]
+                last_base = base
+            off += n
+        self.total = total
+        self._stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def reverse_bucket_order(self):
+        """transformer.23 ... transformer.0, then the remaining parameters (what finishes last in the backward)."""
+        blk = sorted((k for k in self.buckets if k.startswith("transformer.")),
+                     key=lambda k: -int(k.split(".")[1].split("#")[0]))
+        return blk + [k for k in self.buckets if not k.startswith("transformer.")]
+
+    def allreduce_mean_(self, group=None):
+        """sum over ranks / world, bucket by bucket in reverse order; async on a side stream on GPUs."""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            return self
+        works = []
+        if self._stream is not None:
+            self._stream.wait_stream(torch.cuda.current_stream(self.flat.device))
+        ctx = torch.cuda.stream(self._stream) if self._stream is not None else _null()
+        with ctx:
+            for k in self.reverse_bucket_order():
+                a, b = self.buckets[k]
+                works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True))
+            for w in works:
+                w.wait()
+            self.flat.mul_(1.0 / world)
+        if self._stream is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._stream)
+        return self
+
+    def clip_grad_norm_(self, max_norm: float, eps: float = 1e-6) -> torch.Tensor:
+        """torch.nn.utils.clip_grad_norm_ semantics (L2, scale = max_norm / (norm + eps), clamped to 1) on the arena.
+        Identical on every rank after the all-reduce, so no further collective."""
+        norm = torch.linalg.vector_norm(self.flat.float())
+        self.flat.mul_(torch.clamp(max_norm / (norm + eps), max=1.0).to(self.flat.dtype))
+        return norm
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

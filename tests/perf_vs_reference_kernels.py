@@ -29,7 +29,7 @@ def T(x):
     return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32, device=DEV)
 
 
-def timeit(fn, iters, warmup=2):
+def timeit(fn, iters, warmup=3):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -106,7 +106,7 @@ def main():
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
-    cases = [(262146, 256, 4, "init"), (10000, 256, 1, "trained"), (50000, 256, 8, "trained"), (200000, 512, 8, "trained"),
+    cases = [(10000, 256, 1, "trained"), (50000, 256, 8, "trained"), (262146, 256, 4, "init"), (200000, 512, 8, "trained"),
              (200000, 512, 8, "fine"), (1000000, 512, 8, "fine")]
     if not quick:
         cases += [(1000000, 1024, 8, "trained"), (2000000, 1024, 8, "fine"), (500000, 256, 8, "init")]
