@@ -102,7 +102,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "250", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:  # noqa: BLE001
             self.proc = None

@@ -5,12 +5,11 @@
 // reading q/k/v straight out of the fused qkv GEMM output [B, N, 3, H, 64] (bf16) through ONE 3-D TMA tensor
 // map (no head-major re-layout), N arbitrary (4098 = 32*128 + 2: the tail is zero-filled by TMA and masked).
 //
-// One CTA per (128-query block, head, sample); 320 threads, TWO CTAs resident per SM (96 KB smem, 256 TMEM columns,
-// <= 96 registers each) so there are 16 softmax warps per SM to hide the MUFU / TMEM / mbarrier latencies:
+// One CTA per (128-query block, head, sample); 192 threads, TWO CTAs resident per SM (96 KB smem, 256 TMEM columns,
+// <= 168 registers each) so one CTA's tensor-core work runs under the other's softmax:
 //   warp 0      TMA producer: Q once, K/V blocks of 64 keys through a 3-stage ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:  S_j = Q K_j^T  and  PV_j = P_j V_j
-//   warps 2..9  online softmax, TWO threads per query row (32 keys each; the row max is exchanged through shared
-//               memory and a 64-thread named barrier): S_j (TMEM) -> p = ex2(..) -> P_j (bf16, swizzled smem,
+//   warps 2..5  online softmax, one query row per thread: S_j (TMEM) -> p = ex2(..) -> P_j (bf16, swizzled smem,
 //               A operand of the PV MMA).  O accumulates IN TMEM across all key blocks (the PV MMA adds into it);
 //               the softmax rows rescale it (tcgen05.ld / st) only when their running max grows by more than 2^8
 //               -- otherwise the stale max keeps being used, which is exact after the final 1/l normalisation.
@@ -24,10 +23,10 @@ namespace dgs {
 
 using namespace ptx;
 
-constexpr int ATT_BM = 128, ATT_BN = 64, ATT_HD = 64, ATT_KV_STAGES = 3, ATT_THREADS = 320;
+constexpr int ATT_BM = 128, ATT_BN = 64, ATT_HD = 64, ATT_KV_STAGES = 3, ATT_THREADS = 192;
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_HD * 2;    // [128 x 64] bf16 (Q, and one P buffer: 128 rows x 64 keys)
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_HD * 2;   // [64 x 64] bf16 (one K or V block)
-constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES * 3 + 2 * ATT_KV_STAGES * ATT_KV_BYTES + 1024 + 256 + 2 * 2 * 128 * 4;
+constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES * 3 + 2 * ATT_KV_STAGES * ATT_KV_BYTES + 1024 + 256;
 constexpr uint32_t TMEM_S = 0, TMEM_O = 2 * ATT_BN, ATT_TMEM_COLS = 256;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: rescale O only if the row max grew by > 2^8
 
@@ -55,7 +54,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint64_t* p_full = s_full + 2;
   uint64_t* pv_full = p_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
-  float* s_xchg = reinterpret_cast<float*>(bars + 32);  // [2 parities][2 halves][128 rows] row-max / row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATT_BM, h = blockIdx.y, b = blockIdx.z;
@@ -67,7 +65,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     prefetch_tmap(&tm_kv);
     mbar_init(q_full, 1);
     for (int s = 0; s < ATT_KV_STAGES; s++) { mbar_init(k_full + s, 1); mbar_init(v_full + s, 1); mbar_init(kv_empty + s, 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(s_full + s, 1); mbar_init(p_full + s, 256); mbar_init(pv_full + s, 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(s_full + s, 1); mbar_init(p_full + s, 128); mbar_init(pv_full + s, 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -134,44 +132,39 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
     }
   } else {
-    // ===================== softmax / output (warps 2..9): two threads per query row =====================
-    const int quad = warp & 3;              // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;       // which 32 of the 64 keys (and of the 64 output dims) this thread owns
+    // ===================== softmax / output (warps 2..5): one query row per thread =====================
+    const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    const uint32_t t_o = t_lane + TMEM_O + (uint32_t)(half * 32);
-    const int pair_bar = 1 + quad;          // named barrier shared by the two warps that own the same 32 rows
+    const uint32_t t_o = t_lane + TMEM_O;
     float m_run = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < n_blocks; j++) {
       const int buf = j & 1;
       mbar_wait(s_full + buf, (uint32_t)(j >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_s = t_lane + TMEM_S + (uint32_t)(buf * ATT_BN + half * 32);
-      const int kv_valid = N - j * ATT_BN - half * 32;  // valid keys among this thread's 32 (<= 0: none)
-      uint32_t r[32];
-      tmem_ld_32x32(t_s, r);
+      const uint32_t t_s = t_lane + TMEM_S + (uint32_t)(buf * ATT_BN);
+      const int kv_valid = N - j * ATT_BN;  // >= 1; < ATT_BN only in the last block
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(t_s, r0);
+      tmem_ld_32x32(t_s + 32u, r1);
       tmem_ld_wait();
-      if (kv_valid < 32) {  // warp-uniform: mask the zero-filled tail keys
+      if (kv_valid < ATT_BN) {  // warp-uniform: mask the zero-filled tail keys
 #pragma unroll
-        for (int i = 0; i < 32; i++)
-          if (i >= kv_valid) r[i] = 0xff800000u;  // -inf
+        for (int i = 0; i < 32; i++) {
+          if (i >= kv_valid) r0[i] = 0xff800000u;       // -inf
+          if (32 + i >= kv_valid) r1[i] = 0xff800000u;
+        }
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+      for (int i = 0; i < 32; i += 2) {
+        mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(r1[i])); mx3 = fmaxf(mx3, __uint_as_float(r1[i + 1]));
       }
-      float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      {  // exchange the partial row max with the thread that owns the other 32 keys of this row
-        float* x = s_xchg + buf * 256;
-        x[half * 128 + row] = m_blk;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        m_blk = fmaxf(m_blk, x[(half ^ 1) * 128 + row]);
-      }
-      // lazy rescale: keep the stale max unless it is exceeded by more than the threshold (same decision in both halves)
+      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // lazy rescale: keep the stale max unless it is exceeded by more than the threshold
       float alpha = 1.0f;
       const bool grow = (m_blk - m_run) * sl2 > ATT_RESCALE_THRESHOLD;  // true on the first block (m_run = -inf)
       if (grow) {
@@ -183,59 +176,74 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       if (j >= 1 && __any_sync(0xffffffffu, grow)) {
         mbar_wait(pv_full + (buf ^ 1), (uint32_t)((j - 1) >> 1) & 1);
         tc_fence_after();
-        uint32_t q[32];
-        tmem_ld_32x32(t_o, q);
+        uint32_t q0r[32], q1r[32];
+        tmem_ld_32x32(t_o, q0r);
+        tmem_ld_32x32(t_o + 32u, q1r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i++) q[i] = __float_as_uint(__uint_as_float(q[i]) * alpha);
-        tmem_st_32x32(t_o, q);
+        for (int i = 0; i < 32; i++) {
+          q0r[i] = __float_as_uint(__uint_as_float(q0r[i]) * alpha);
+          q1r[i] = __float_as_uint(__uint_as_float(q1r[i]) * alpha);
+        }
+        tmem_st_32x32(t_o, q0r);
+        tmem_st_32x32(t_o + 32u, q1r);
         tmem_st_wait();
       }
       const float moff = m_run * sl2;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       uint8_t* p_row = sP + buf * ATT_Q_BYTES + row * 128;
-      float p[32];
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        p[i] = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -moff));
-        p[i + 1] = ex2_approx(fmaf(__uint_as_float(r[i + 1]), sl2, -moff));
-        p[i + 2] = ex2_approx(fmaf(__uint_as_float(r[i + 2]), sl2, -moff));
-        p[i + 3] = ex2_approx(fmaf(__uint_as_float(r[i + 3]), sl2, -moff));
-        l0 += p[i]; l1 += p[i + 1]; l2 += p[i + 2]; l3 += p[i + 3];
-      }
+      for (int half = 0; half < 2; half++) {
+        float p[32];
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        uint4 pk;
-        pk.x = pack2_bf16(p[8 * q], p[8 * q + 1]); pk.y = pack2_bf16(p[8 * q + 2], p[8 * q + 3]);
-        pk.z = pack2_bf16(p[8 * q + 4], p[8 * q + 5]); pk.w = pack2_bf16(p[8 * q + 6], p[8 * q + 7]);
-        *reinterpret_cast<uint4*>(p_row + (((half * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
+        for (int i = 0; i < 32; i += 4) {
+          p[i] = ex2_approx(fmaf(__uint_as_float(half ? r1[i] : r0[i]), sl2, -moff));
+          p[i + 1] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 1] : r0[i + 1]), sl2, -moff));
+          p[i + 2] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 2] : r0[i + 2]), sl2, -moff));
+          p[i + 3] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 3] : r0[i + 3]), sl2, -moff));
+          l0 += p[i]; l1 += p[i + 1]; l2 += p[i + 2]; l3 += p[i + 3];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          uint4 pk;
+          pk.x = pack2_bf16(p[8 * q], p[8 * q + 1]); pk.y = pack2_bf16(p[8 * q + 2], p[8 * q + 3]);
+          pk.z = pack2_bf16(p[8 * q + 4], p[8 * q + 5]); pk.w = pack2_bf16(p[8 * q + 6], p[8 * q + 7]);
+          *reinterpret_cast<uint4*>(p_row + (((half * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
+        }
       }
       l_run = l_run * alpha + ((l0 + l1) + (l2 + l3));
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();    // our tcgen05.ld/st of S_j and O are complete before the issuer proceeds
       mbar_arrive(p_full + buf);
     }
-    {  // all blocks accumulated -> combine the two half-row sums, normalise and store this thread's 32 dims
+    {  // all blocks accumulated -> normalise and store
       const int last = n_blocks - 1;
-      float* x = s_xchg + ((last + 1) & 1) * 256;
-      x[half * 128 + row] = l_run;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      const float inv = 1.0f / (l_run + x[(half ^ 1) * 128 + row]);
       mbar_wait(pv_full + (last & 1), (uint32_t)(last >> 1) & 1);
       tc_fence_after();
-      uint32_t q[32];
-      tmem_ld_32x32(t_o, q);
+      uint32_t q0r[32], q1r[32];
+      tmem_ld_32x32(t_o, q0r);
+      tmem_ld_32x32(t_o + 32u, q1r);
       tmem_ld_wait();
       if (q0 + row < N) {
-        __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * D + h * ATT_HD + half * 32;
+        const float inv = 1.0f / l_run;
+        __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * D + h * ATT_HD;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 pk;
-          pk.x = pack2_bf16(__uint_as_float(q[i]) * inv, __uint_as_float(q[i + 1]) * inv);
-          pk.y = pack2_bf16(__uint_as_float(q[i + 2]) * inv, __uint_as_float(q[i + 3]) * inv);
-          pk.z = pack2_bf16(__uint_as_float(q[i + 4]) * inv, __uint_as_float(q[i + 5]) * inv);
-          pk.w = pack2_bf16(__uint_as_float(q[i + 6]) * inv, __uint_as_float(q[i + 7]) * inv);
+          pk.x = pack2_bf16(__uint_as_float(q0r[i]) * inv, __uint_as_float(q0r[i + 1]) * inv);
+          pk.y = pack2_bf16(__uint_as_float(q0r[i + 2]) * inv, __uint_as_float(q0r[i + 3]) * inv);
+          pk.z = pack2_bf16(__uint_as_float(q0r[i + 4]) * inv, __uint_as_float(q0r[i + 5]) * inv);
+          pk.w = pack2_bf16(__uint_as_float(q0r[i + 6]) * inv, __uint_as_float(q0r[i + 7]) * inv);
           *reinterpret_cast<uint4*>(dst + i) = pk;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk;
+          pk.x = pack2_bf16(__uint_as_float(q1r[i]) * inv, __uint_as_float(q1r[i + 1]) * inv);
+          pk.y = pack2_bf16(__uint_as_float(q1r[i + 2]) * inv, __uint_as_float(q1r[i + 3]) * inv);
+          pk.z = pack2_bf16(__uint_as_float(q1r[i + 4]) * inv, __uint_as_float(q1r[i + 5]) * inv);
+          pk.w = pack2_bf16(__uint_as_float(q1r[i + 6]) * inv, __uint_as_float(q1r[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 32 + i) = pk;
         }
       }
     }

@@ -1,0 +1,303 @@
+// gemm2_sm100.cu -- CTA-pair (cta_group::2) variant of the DiT GEMM:  256 x 256 output tile per 2-CTA cluster.
+//
+// Why: at 128 x 256 tiles per CTA the single-CTA kernel (gemm_sm100.cu) is bound by L2 -> shared-memory operand
+// traffic (48 KB per 128x256x64 MAC block = 43 MAC/B), not by the tensor pipe.  With a CTA pair each CTA stages only
+// its 128 rows of A and HALF of the B tile (128 of the 256 weight rows); one tcgen05.mma.cta_group::2 of shape
+// 256 x 256 x 16, issued by the leader CTA, reads both CTAs' shared memory and writes 128 x 256 fp32 accumulators into
+// EACH CTA's TMEM.  Operand traffic drops to 32 KB per CTA per k-block (64 MAC/B).
+//
+// Protocol (leader = cluster rank 0):
+//   full[s]    lives in the LEADER: count 2 = leader producer's arrive.expect_tx(2 x 32 KB) + peer producer's remote
+//              arrive; both CTAs' TMA loads complete_tx on it (cp.async.bulk.tensor ... cta_group::2, leader address)
+//   empty[s]   one per CTA, released by the leader's tcgen05.commit ... multicast::cluster (mask 0b11)
+//   tfull[a]   one per CTA, same multicast commit when an accumulator is complete
+//   tempty[a]  lives in the leader: count 256 = both CTAs' 128 epilogue threads (the peer's arrive remotely)
+// Same fused epilogues as gemm_sm100.cu (each CTA drains its own 128 rows).
+#include "dgs_internal.h"
+#include "dit_kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace dgs {
+
+using namespace ptx;
+
+namespace g2 {
+
+constexpr int BM_CTA = 128, BN = 256, BN_CTA = 128, BK = 64, UMMA_K = 16, STAGES = 6, THREADS = 192;
+constexpr int A_BYTES = BM_CTA * BK * 2, B_BYTES = BN_CTA * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int TMEM_COLS = 2 * BN;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar_cluster_addr,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (x + k1 * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
+                      int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_m = (M + 2 * BM_CTA - 1) / (2 * BM_CTA), num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n, num_k = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 2); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 256); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // both CTAs' barriers are initialised before any remote arrive / multicast commit / 2SM TMA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one per CTA) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / num_n) * (2 * BM_CTA) + (int)rank * BM_CTA;
+        const int n0 = (tile % num_n) * BN + (int)rank * BN_CTA;
+        for (int kb = 0; kb < num_k; kb++) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          const uint32_t leader_full = mapa(smem_u32(full_bar + stage), 0);
+          if (leader) mbar_arrive_expect_tx(full_bar + stage, 2 * STAGE_BYTES);
+          else mbar_arrive_remote(leader_full);
+          tma_load_2d_2sm(sA + stage * A_BYTES, &tmA, leader_full, kb * BK, m0);
+          tma_load_2d_2sm(sB + stage * B_BYTES, &tmB, leader_full, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one thread of the LEADER CTA =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM_CTA, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k; kb++) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * A_BYTES), 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * B_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; k++)
+            umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit_2sm(empty_bar + stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(tfull_bar + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..5 (each CTA drains its own 128 rows) =====================
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / num_n) * (2 * BM_CTA) + (int)rank * BM_CTA, n0 = (tile % num_n) * BN;
+      const int row = m0 + quad * 32 + lane;
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const float* gate = nullptr;
+      if (EPI == EPI_GATE_RESID_F32 && row < M) gate = ep.gate + (size_t)(row / ep.rows_per_sample) * ep.gate_stride;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        const int n = n0 + c * 32;
+        if (n >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (row < M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+            if (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) v[j] = gelu_tanh_fast(v[j]);
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              pk.x = pack_bf16(v[j], v[j + 1]); pk.y = pack_bf16(v[j + 2], v[j + 3]);
+              pk.z = pack_bf16(v[j + 4], v[j + 5]); pk.w = pack_bf16(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          } else if (EPI == EPI_GATE_RESID_F32) {
+            float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate + n + j));
+              float4 x4 = *reinterpret_cast<float4*>(o + j);
+              x4.x += g4.x * v[j]; x4.y += g4.y * v[j + 1]; x4.z += g4.z * v[j + 2]; x4.w += g4.w * v[j + 3];
+              *reinterpret_cast<float4*>(o + j) = x4;
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      if (leader) mbar_arrive(tempty_bar + acc);
+      else mbar_arrive_remote(mapa(smem_u32(tempty_bar + acc), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();  // neither CTA leaves (or frees TMEM) while its peer may still touch its smem / barriers / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace g2
+
+template <int EPI>
+static int launch_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int N, int K,
+                       int num_sms, cudaStream_t st) {
+  auto kern = g2::gemm_bf16_2cta_kernel<EPI>;
+  static bool configured = false;
+  if (!configured) {
+    DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = ceil_div(M, 2 * g2::BM_CTA) * ceil_div(N, g2::BN);
+  int clusters = num_sms / 2;
+  if (tiles < clusters) clusters = tiles;
+  kern<<<2 * clusters, g2::THREADS, g2::SMEM_BYTES, st>>>(tmA, tmB, ep, M, N, K);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+// same contract as gemm_bf16(); requires N % 256 == 0
+int gemm_bf16_2cta(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    DGS_CUDA_OK(cudaGetDevice(&dev));
+    DGS_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {g2::BK, g2::BM_CTA};
+    int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {g2::BK, g2::BN_CTA};
+    int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  switch (epi) {
+    case EPI_BIAS_BF16: return launch_2cta<EPI_BIAS_BF16>(tmA, tmB, ep, M, N, K, num_sms, st);
+    case EPI_BIAS_GELU_BF16: return launch_2cta<EPI_BIAS_GELU_BF16>(tmA, tmB, ep, M, N, K, num_sms, st);
+    case EPI_GATE_RESID_F32: return launch_2cta<EPI_GATE_RESID_F32>(tmA, tmB, ep, M, N, K, num_sms, st);
+    case EPI_F32: return launch_2cta<EPI_F32>(tmA, tmB, ep, M, N, K, num_sms, st);
+    default: set_error("gemm: unknown epilogue %d", epi); return DGS_ERR_INVALID_ARGUMENT;
+  }
+}
+
+}  // namespace dgs

@@ -14,6 +14,7 @@
 //   EPI_BIAS_GELU_BF16  y = gelu_tanh(acc + b)              (mlp.fc1 + act)
 //   EPI_GATE_RESID_F32  x += gate[sample] * (acc + b)       (attn.proj / mlp.fc2 + gate + residual, fp32 stream)
 //   EPI_F32             y = acc (+ b), fp32                 (tokenizer, decoder head)
+#include <cstdlib>
 #include <cstring>
 
 #include "dgs_internal.h"
@@ -275,6 +276,14 @@ int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const 
   DGS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %dx%dx%d", M, N, K);
   DGS_REQUIRE(K % 8 == 0 && N % 32 == 0, "gemm: need K %% 8 == 0 and N %% 32 == 0 (got K=%d N=%d)", K, N);
   DGS_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm: operands must be 16-byte aligned");
+  // CTA-pair kernel (256 x 256 tiles, half the operand traffic per CTA) whenever the shape fills the machine with them;
+  // DGS_GEMM_2CTA=0 forces the single-CTA kernel (A/B comparisons)
+  static int use_2cta = -1;
+  if (use_2cta < 0) {
+    const char* e = getenv("DGS_GEMM_2CTA");
+    use_2cta = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_2cta && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_2cta(A, W, M, N, K, epi, ep, st);
   // wide tiles when they still fill the machine, else 128-wide tiles for more CTAs
   const bool wide = (N % 256 == 0) && (ceil_div(M, BM) * (N / 256) >= 120);
   const int BN = wide ? 256 : 128;

@@ -212,7 +212,9 @@ class DGSDenoiser(nn.Module):
             nbytes = L.dgs_dit_workspace_bytes(C.byref(w), B, V, H, W)
             if nbytes == 0:
                 raise _lib.DgsError(L.dgs_last_error().decode())
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ws = getattr(self, "_workspace", None)  # grow-only, re-used step after step
+            if ws is None or ws.numel() < nbytes or ws.device != dev:
+                ws = self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             io = DitIO(B=B, V=V, H=H, W=W, plucker_mode=0 if c.ray_pe_type == "relative_plk" else 1,
                        scene_depth=1 if self.SCENE else 0, range_near=float(c.range_setting_near),
                        range_far=float(c.range_setting_far), images=images.data_ptr(), ray_o=ray_o.data_ptr(),

@@ -19,13 +19,21 @@ class _Arena:
     """dgs_alloc_fn backed by a torch uint8 tensor (the reference's resizeFunctional,
     rasterize_points.cu:27-33)."""
 
-    def __init__(self, device):
+    def __init__(self, device, cache=None, key=None):
         self.device = device
+        self.cache, self.key = cache, key   # optional grow-only buffer re-used across calls (inference path)
         self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
         self.cb = ALLOC_FN(self._alloc)
 
     def _alloc(self, nbytes, _user):
         try:
+            if self.cache is not None:
+                t = self.cache.get(self.key)
+                if t is None or t.numel() < nbytes or t.device != self.device:
+                    t = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+                    self.cache[self.key] = t
+                self.tensor = t
+                return t.data_ptr()
             self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
             return self.tensor.data_ptr()
         except Exception:  # noqa: BLE001  (propagated as DGS_ERR_ALLOC by the C side)
@@ -148,15 +156,18 @@ def _batch_args(xyz, features, scaling, rotation, opacity, C2W, fxfycxcy, H, W, 
     return a
 
 
-def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, fxfycxcy, scale_modifier=None):
-    """All (sample, view) pairs in one launch set -> (images [B,V,3,H,W] fp32, state)."""
+def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, fxfycxcy, scale_modifier=None,
+                         arena_cache=None):
+    """All (sample, view) pairs in one launch set -> (images [B,V,3,H,W] fp32, state).
+    `arena_cache` (a dict): re-use grow-only arenas across calls -- only valid when no backward will follow (the
+    inference / denoise-step path); stream order makes the re-use safe."""
     _require_cuda(xyz, "xyz")
     dev = xyz.device
     tens = [_f32c(t) for t in (xyz, features, scaling, rotation, opacity, C2W, fxfycxcy)]
     B, V = tens[5].shape[0], tens[5].shape[1]
     with torch.cuda.device(dev):
         out = torch.empty(B, V, 3, int(H), int(W), dtype=torch.float32, device=dev)
-        geom, binning, img = _Arena(dev), _Arena(dev), _Arena(dev)
+        geom, binning, img = (_Arena(dev, arena_cache, k) for k in ("geom", "binning", "img"))
         a = _batch_args(*tens, H, W, scale_modifier)
         R = C.c_longlong(0)
         check(_lib.lib().dgs_render_batch_forward(C.byref(a), geom.cb, None, binning.cb, None, img.cb, None,

@@ -20,10 +20,12 @@ class BatchedGaussianRender(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, features, scaling, rotation, opacity, height, width, C2W, fxfycxcy,
-                scaling_modifier=None, use_gssplat=False):
+                scaling_modifier=None, use_gssplat=False, arena_cache=None):
+        needs_bwd = any(ctx.needs_input_grad[:5])
         with torch.no_grad():
             images, state = _raster.render_batch_forward(xyz, features, scaling, rotation, opacity, height, width,
-                                                         C2W, fxfycxcy, scaling_modifier)
+                                                         C2W, fxfycxcy, scaling_modifier,
+                                                         arena_cache=None if needs_bwd else arena_cache)
         ctx.state = state
         ctx.in_dtypes = (xyz.dtype, features.dtype, scaling.dtype, rotation.dtype, opacity.dtype)
         ctx.num_rendered = state["R"]
@@ -34,7 +36,7 @@ class BatchedGaussianRender(torch.autograd.Function):
         grads = _raster.render_batch_backward(ctx.state, grad_output)
         ctx.state = None  # release the arenas
         grads = tuple(g.to(dt) for g, dt in zip(grads, ctx.in_dtypes))
-        return (*grads, None, None, None, None, None, None)
+        return (*grads, None, None, None, None, None, None, None)
 
 
 batched_gaussian_render = BatchedGaussianRender.apply
@@ -92,6 +94,7 @@ class Renderer(nn.Module):
         self.scaling_modifier = None
         sh_degree = getattr(config, "gaussians_sh_degree", 0)
         self.gaussians_model = GaussianModel(sh_degree, self.scaling_modifier)
+        self._arena_cache = {}  # inference-path arenas, grown on demand, re-used step after step
 
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(self, xyz, features, scaling, rotation, opacity, height, width, C2W, fxfycxcy, deferred=True):
@@ -100,7 +103,8 @@ class Renderer(nn.Module):
         signature parity: both reference branches compute the same images; here both map to the
         batched kernel set."""
         out = batched_gaussian_render(xyz, features, scaling, rotation, opacity, height, width, C2W, fxfycxcy,
-                                      self.scaling_modifier, getattr(self.config, "use_gssplat", False))
+                                      self.scaling_modifier, getattr(self.config, "use_gssplat", False),
+                                      self._arena_cache)
         self.last_num_rendered = _raster.LAST_NUM_RENDERED
         return out
 
