@@ -15,6 +15,7 @@
 // Same fused epilogues as gemm_sm100.cu (each CTA drains its own 128 rows).
 #include "dgs_internal.h"
 #include "dit_kernels.h"
+#include "gemm_epilogue.cuh"
 #include "sm100_ptx.cuh"
 
 namespace dgs {
@@ -26,7 +27,7 @@ namespace g2 {
 constexpr int BM_CTA = 128, BN = 256, BN_CTA = 128, BK = 64, UMMA_K = 16, STAGES = 6, THREADS = 192;
 constexpr int A_BYTES = BM_CTA * BK * 2, B_BYTES = BN_CTA * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int TMEM_COLS = 2 * BN;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2 * 2 * BN * 4;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -78,17 +79,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                : "memory");
 }
 
-__device__ __forceinline__ float gelu_tanh_fast(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float u = k0 * (x + k1 * x * x * x);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  return 0.5f * x * (1.0f + t);
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -176,69 +166,26 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else {
-    // ===================== epilogue warps 2..5 (each CTA drains its own 128 rows) =====================
+    // ===================== epilogue warps 2..5: each CTA drains its own 128 rows (gemm_epilogue.cuh) ==========
     const int quad = warp & 3;
+    const int et = (warp - 2) * 32 + lane;
+    float* s_vec_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
+    const uint32_t leader_tempty0 = mapa(smem_u32(tempty_bar), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m0 = (tile / num_n) * (2 * BM_CTA) + (int)rank * BM_CTA, n0 = (tile % num_n) * BN;
       const int row = m0 + quad * 32 + lane;
+      float* s_vec = s_vec_all + acc * 2 * BN;
+      bool uniform_gate;
+      epilogue_stage_vectors<EPI, BN>(ep, s_vec, et, m0, n0, M, N, &uniform_gate);  // under the main loop
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      const float* gate = nullptr;
-      if (EPI == EPI_GATE_RESID_F32 && row < M) gate = ep.gate + (size_t)(row / ep.rows_per_sample) * ep.gate_stride;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
-        const int n = n0 + c * 32;
-        if (n >= N) break;
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
-        if (row < M) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
-          if (ep.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
-          if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
-            if (EPI == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-              for (int j = 0; j < 32; j++) v[j] = gelu_tanh_fast(v[j]);
-            }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldc + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              pk.x = pack_bf16(v[j], v[j + 1]); pk.y = pack_bf16(v[j + 2], v[j + 3]);
-              pk.z = pack_bf16(v[j + 4], v[j + 5]); pk.w = pack_bf16(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = pk;
-            }
-          } else if (EPI == EPI_GATE_RESID_F32) {
-            float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldc + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate + n + j));
-              float4 x4 = *reinterpret_cast<float4*>(o + j);
-              x4.x += g4.x * v[j]; x4.y += g4.y * v[j + 1]; x4.z += g4.z * v[j + 2]; x4.w += g4.w * v[j + 3];
-              *reinterpret_cast<float4*>(o + j) = x4;
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldc + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-        }
-      }
+      epilogue_drain_row<EPI, BN>(ep, s_vec, uniform_gate, t_row, row, n0, M, N);
       tc_fence_before();
       if (leader) mbar_arrive(tempty_bar + acc);
-      else mbar_arrive_remote(mapa(smem_u32(tempty_bar + acc), 0));
+      else mbar_arrive_remote(leader_tempty0 + (uint32_t)(acc * 8));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

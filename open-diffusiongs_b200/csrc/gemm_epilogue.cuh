@@ -1,0 +1,116 @@
+// gemm_epilogue.cuh -- the fused epilogue shared by the single-CTA and the CTA-pair GEMM kernels.
+//
+// 128 epilogue threads (warps 2..5) drain one 128 x BN fp32 accumulator tile from TMEM, one output row per thread,
+// 32 columns at a time.  ncu (profiles/r1_ncu_gemm2cta_v1.txt) showed the first version of this loop exposed a
+// dependent global-load latency per 32-column chunk (bias via __ldg, plus the fp32 residual read of the gate+residual
+// epilogue), which made the epilogue LONGER than the tile's MMA main loop and starved the tensor pipe.  Now:
+//   * bias / gate rows of the tile are staged once per tile in shared memory (double-buffered by accumulator index)
+//     by the epilogue threads themselves, BEFORE they wait for the accumulator -- i.e. under the main loop;
+//   * the residual stream values of chunk c+1 are prefetched into registers while chunk c is processed.
+#pragma once
+#include "dit_kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace dgs {
+
+__device__ __forceinline__ float epi_gelu_tanh(float x) {  // nn.GELU(approximate="tanh"), tanh on the MUFU pipe
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (x + k1 * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
+__device__ __forceinline__ uint32_t epi_pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Stage bias[n0 .. n0+BN) and (gate epilogue) gate[sample(row0)][n0 .. n0+BN) into shared memory.
+// `s_vec` = this accumulator buffer's [2][BN] floats.  All 128 epilogue threads call it.
+// NOTE gate: a 128-row tile may straddle two samples; rows then read their own sample's gate directly from global
+// memory (rare: one tile per sample boundary), signalled by *uniform_gate == false.
+template <int EPI, int BN>
+__device__ __forceinline__ void epilogue_stage_vectors(const GemmEpilogue& ep, float* s_vec, int et /*0..127*/, int m0,
+                                                       int n0, int M, int N, bool* uniform_gate) {
+  const int last_row = min(m0 + 127, M - 1);
+  const bool uni = (EPI != EPI_GATE_RESID_F32) || (m0 / ep.rows_per_sample == last_row / ep.rows_per_sample);
+  *uniform_gate = uni;
+  for (int i = et; i < BN; i += 128) {
+    const int n = n0 + i;
+    s_vec[i] = (ep.bias && n < N) ? __ldg(ep.bias + n) : 0.f;
+    if (EPI == EPI_GATE_RESID_F32)
+      s_vec[BN + i] = (uni && n < N) ? __ldg(ep.gate + (size_t)(m0 / ep.rows_per_sample) * ep.gate_stride + n) : 0.f;
+  }
+  epi_bar_sync();
+}
+
+// Drain one accumulator row (this thread's) of BN columns.
+template <int EPI, int BN>
+__device__ __forceinline__ void epilogue_drain_row(const GemmEpilogue& ep, const float* s_vec, bool uniform_gate,
+                                                   uint32_t t_row, int row, int n0, int M, int N) {
+  using namespace ptx;
+  const bool valid = row < M;
+  const float* gate_row = nullptr;
+  if (EPI == EPI_GATE_RESID_F32 && valid && !uniform_gate)
+    gate_row = ep.gate + (size_t)(row / ep.rows_per_sample) * ep.gate_stride;
+  float4 xn[8];  // residual prefetch (gate epilogue only)
+  float* xrow = (EPI == EPI_GATE_RESID_F32 && valid) ? reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldc : nullptr;
+  if (EPI == EPI_GATE_RESID_F32 && valid && n0 < N) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) xn[j] = *reinterpret_cast<const float4*>(xrow + n0 + 4 * j);
+  }
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; c++) {
+    const int n = n0 + c * 32;
+    if (n >= N) break;  // warp-uniform (N % 32 == 0)
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
+    float4 xc[8];
+    if (EPI == EPI_GATE_RESID_F32 && valid) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) xc[j] = xn[j];
+      if (n + 32 < N && c + 1 < BN / 32) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) xn[j] = *reinterpret_cast<const float4*>(xrow + n + 32 + 4 * j);
+      }
+    }
+    tmem_ld_wait();
+    if (!valid) continue;
+    float v[32];
+    const float* sb = s_vec + c * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + sb[j];
+    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+      if (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = epi_gelu_tanh(v[j]);
+      }
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldc + n;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        pk.x = epi_pack_bf16(v[j], v[j + 1]); pk.y = epi_pack_bf16(v[j + 2], v[j + 3]);
+        pk.z = epi_pack_bf16(v[j + 4], v[j + 5]); pk.w = epi_pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(o + j) = pk;
+      }
+    } else if (EPI == EPI_GATE_RESID_F32) {
+      const float* sg = s_vec + BN + c * 32;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float4 g4;
+        if (uniform_gate) g4 = make_float4(sg[4 * j], sg[4 * j + 1], sg[4 * j + 2], sg[4 * j + 3]);
+        else g4 = __ldg(reinterpret_cast<const float4*>(gate_row + n + 4 * j));
+        float4 x4 = xc[j];
+        x4.x += g4.x * v[4 * j]; x4.y += g4.y * v[4 * j + 1]; x4.z += g4.z * v[4 * j + 2]; x4.w += g4.w * v[4 * j + 3];
+        *reinterpret_cast<float4*>(xrow + n + 4 * j) = x4;
+      }
+    } else {  // EPI_F32
+      float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldc + n;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+}
+
+}  // namespace dgs
