@@ -14,7 +14,10 @@
 //               the softmax rows rescale it (tcgen05.ld / st) only when their running max grows by more than 2^8
 //               -- otherwise the stale max keeps being used, which is exact after the final 1/l normalisation.
 // S is double-buffered in TMEM so QK^T of block j+1 runs under the softmax of block j.  The softmax is bound by
-// the MUFU ex2 pipe (16/clk/SM), so the per-element instruction count is kept at max + fma + ex2 + add + cvt/2.
+// the MUFU ex2 pipe (16/clk/SM), so the per-element instruction count is kept at max/2 + fma + ex2 + cvt/2: even the
+// softmax DENOMINATOR is computed by the tensor core -- a second tiny MMA  L += P_j x ONES  (N = 16, a constant
+// all-ones K-major tile) accumulates the row sums of the SAME bf16-rounded probabilities that enter P V, in 16 extra
+// TMEM columns next to O (ncu: the per-element FADD of the register row-sum was 13% of all issued instructions).
 #include "dgs_internal.h"
 #include "dit_kernels.h"
 #include "sm100_ptx.cuh"
@@ -26,8 +29,9 @@ using namespace ptx;
 constexpr int ATT_BM = 128, ATT_BN = 64, ATT_HD = 64, ATT_KV_STAGES = 3, ATT_THREADS = 192;
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_HD * 2;    // [128 x 64] bf16 (Q, and one P buffer: 128 rows x 64 keys)
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_HD * 2;   // [64 x 64] bf16 (one K or V block)
-constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES * 3 + 2 * ATT_KV_STAGES * ATT_KV_BYTES + 1024 + 256;
-constexpr uint32_t TMEM_S = 0, TMEM_O = 2 * ATT_BN, ATT_TMEM_COLS = 256;
+constexpr int ATT_ONES_BYTES = 16 * 128;           // [16 x 64] bf16 ones, K-major (B operand of the row-sum MMA)
+constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES * 3 + 2 * ATT_KV_STAGES * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;
+constexpr uint32_t TMEM_S = 0, TMEM_O = 2 * ATT_BN, TMEM_L = TMEM_O + ATT_HD, ATT_TMEM_COLS = 256;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: rescale O only if the row max grew by > 2^8
 
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
@@ -45,7 +49,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint8_t* sP = sQ + ATT_Q_BYTES;                      // 2 buffers x [128 x 64] bf16
   uint8_t* sK = sP + 2 * ATT_Q_BYTES;
   uint8_t* sV = sK + ATT_KV_STAGES * ATT_KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_KV_STAGES * ATT_KV_BYTES);
+  uint8_t* sOnes = sV + ATT_KV_STAGES * ATT_KV_BYTES;  // 2 KB, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ATT_ONES_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* v_full = k_full + ATT_KV_STAGES;
@@ -72,6 +77,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     tmem_alloc(tmem_slot, ATT_TMEM_COLS);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < ATT_ONES_BYTES / 4; i += ATT_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+  fence_proxy_async();  // the ones tile is read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -97,6 +104,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, false, false);   // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_HD, false, true);   // P (K-major) x V (MN-major)
+      constexpr uint32_t idesc_l = make_idesc_bf16(ATT_BM, 16, false, false);      // P (K-major) x ONES (K-major)
+      const uint64_t odesc = make_smem_desc_sw128(smem_u32(sOnes), 16, 1024);
       const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       auto issue_s = [&](int j) {
         const int s = j % ATT_KV_STAGES;
@@ -126,6 +135,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           // B = V: MN-major ([key][64 dims] rows of 128 bytes); 16 keys = 2 groups of 8 rows = 2048 bytes
           const uint64_t vdesc = make_smem_desc_sw128(vbase + (uint32_t)(k * 2048), ATT_KV_BYTES, 1024);
           umma_bf16(d, pdesc, vdesc, idesc_pv, (j | k) ? 1u : 0u);  // O += P_j V_j (first block overwrites)
+          umma_bf16(tmem_base + TMEM_L, pdesc, odesc + (uint64_t)(2 * k), idesc_l, (j | k) ? 1u : 0u);  // L += rowsum(P_j)
         }
         umma_commit(pv_full + (j & 1));
         umma_commit(kv_empty + s);
@@ -137,8 +147,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    const uint32_t t_o = t_lane + TMEM_O;
-    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t t_o = t_lane + TMEM_O, t_l = t_lane + TMEM_L;
+    float m_run = -INFINITY;
 
     for (int j = 0; j < n_blocks; j++) {
       const int buf = j & 1;
@@ -185,12 +195,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           q0r[i] = __float_as_uint(__uint_as_float(q0r[i]) * alpha);
           q1r[i] = __float_as_uint(__uint_as_float(q1r[i]) * alpha);
         }
+        const uint32_t lsum = tmem_ld_32x1(t_l);
+        tmem_ld_wait();
         tmem_st_32x32(t_o, q0r);
         tmem_st_32x32(t_o + 32u, q1r);
+        tmem_st_32x1(t_l, __float_as_uint(__uint_as_float(lsum) * alpha));
         tmem_st_wait();
       }
       const float moff = m_run * sl2;
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       uint8_t* p_row = sP + buf * ATT_Q_BYTES + row * 128;
 #pragma unroll
       for (int half = 0; half < 2; half++) {
@@ -201,7 +213,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           p[i + 1] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 1] : r0[i + 1]), sl2, -moff));
           p[i + 2] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 2] : r0[i + 2]), sl2, -moff));
           p[i + 3] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 3] : r0[i + 3]), sl2, -moff));
-          l0 += p[i]; l1 += p[i + 1]; l2 += p[i + 2]; l3 += p[i + 3];
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -211,7 +222,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           *reinterpret_cast<uint4*>(p_row + (((half * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
         }
       }
-      l_run = l_run * alpha + ((l0 + l1) + (l2 + l3));
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();    // our tcgen05.ld/st of S_j and O are complete before the issuer proceeds
       mbar_arrive(p_full + buf);
@@ -223,9 +233,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       uint32_t q0r[32], q1r[32];
       tmem_ld_32x32(t_o, q0r);
       tmem_ld_32x32(t_o + 32u, q1r);
+      const uint32_t lsum = tmem_ld_32x1(t_l);
       tmem_ld_wait();
       if (q0 + row < N) {
-        const float inv = 1.0f / l_run;
+        const float inv = 1.0f / __uint_as_float(lsum);
         __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * D + h * ATT_HD;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {

@@ -218,12 +218,13 @@ int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const 
   DGS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %dx%dx%d", M, N, K);
   DGS_REQUIRE(K % 8 == 0 && N % 32 == 0, "gemm: need K %% 8 == 0 and N %% 32 == 0 (got K=%d N=%d)", K, N);
   DGS_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm: operands must be 16-byte aligned");
-  // CTA-pair kernel (256 x 256 tiles, half the operand traffic per CTA) whenever the shape fills the machine with them;
-  // DGS_GEMM_2CTA=0 forces the single-CTA kernel (A/B comparisons)
+  // CTA-pair kernel (gemm2_sm100.cu: 256 x 256 tiles, 2/3 of the operand traffic per CTA).  It is CORRECT (all parity
+  // tests pass with DGS_GEMM_2CTA=1) but on B200 it currently runs ~1.6x SLOWER than this single-CTA kernel
+  // (profiles/r1_ncu_gemm2cta.txt: tensor pipe 29 % active, L2 26 %): opt-in until that is understood.
   static int use_2cta = -1;
   if (use_2cta < 0) {
     const char* e = getenv("DGS_GEMM_2CTA");
-    use_2cta = (e && e[0] == '0') ? 0 : 1;
+    use_2cta = (e && e[0] == '1') ? 1 : 0;
   }
   if (use_2cta && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_2cta(A, W, M, N, K, epi, ep, st);
   // wide tiles when they still fill the machine, else 128-wide tiles for more CTAs

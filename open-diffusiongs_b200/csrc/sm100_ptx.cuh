@@ -37,15 +37,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must trap (visible error) instead of hanging the GPU.
-#ifndef DGS_MBAR_TIMEOUT_CYCLES
-#define DGS_MBAR_TIMEOUT_CYCLES 4000000000ll  // ~2 s at 2 GHz
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~hint ns elapse,
+// so a waiting role costs (almost) no issue slots of the SM sub-partition it shares with the math warps.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must trap (visible error) instead of hanging the GPU.  The bound is a count of
+// ~20 us sleeps (no clock reads in the loop).
+#ifndef DGS_MBAR_TIMEOUT_SPINS
+#define DGS_MBAR_TIMEOUT_SPINS 200000u  // x ~20 us = ~4 s
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > DGS_MBAR_TIMEOUT_CYCLES) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (++spins > DGS_MBAR_TIMEOUT_SPINS) {
       printf("[dgs] mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
@@ -125,6 +139,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// single column per lane (32 lanes x 1 column)
+__device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
 // 2^x on the MUFU pipe (ex2.approx.ftz: 2 ulp, flushes denormals) -- softmax probabilities are rounded to bf16 next
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
