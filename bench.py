@@ -50,6 +50,13 @@ def attention_flops(n_tok=N_TOK, d=D):
     return 4 * n_tok * n_tok * d  # QK^T + PV, all heads, one layer, one sample
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel family, from the committed
+    `ncu --set full` captures (profiles/r1_ncu_traffic.json); null when a family has no capture."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -241,6 +248,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("DGS_NCCL_DEBUG", "WARN")  # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
@@ -339,7 +347,8 @@ def main():
         if dom in flops:
             ach = flops[dom] / (per_launch_ms * 1e-3) / 1e12
             pk = peaks["bf16_tflops_sustained"]
-            roof = dict(kernel=dom, bound="tensor", achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk, traffic=None,
+            roof = dict(kernel=dom, bound="tensor", achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk,
+                        traffic=load_traffic().get(dom),
                         peak_source=peaks["source"] + " (sustained cuBLAS bf16, kernel timed inside a long step)",
                         launch_ms=per_launch_ms, algorithmic_flops_per_launch=flops[dom])
         else:

@@ -150,15 +150,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t t_o = t_lane + TMEM_O, t_l = t_lane + TMEM_L;
     float m_run = -INFINITY;
 
+    // S_0 -> registers; every later block is prefetched at the end of the previous iteration, so that the TMEM-load
+    // latency runs under the pack / store / fence / arrive tail instead of in front of the exponentials
+    uint32_t r0[32], r1[32];
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    tmem_ld_32x32(t_lane + TMEM_S, r0);
+    tmem_ld_32x32(t_lane + TMEM_S + 32u, r1);
+
     for (int j = 0; j < n_blocks; j++) {
       const int buf = j & 1;
-      mbar_wait(s_full + buf, (uint32_t)(j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t_s = t_lane + TMEM_S + (uint32_t)(buf * ATT_BN);
       const int kv_valid = N - j * ATT_BN;  // >= 1; < ATT_BN only in the last block
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(t_s, r0);
-      tmem_ld_32x32(t_s + 32u, r1);
       tmem_ld_wait();
       if (kv_valid < ATT_BN) {  // warp-uniform: mask the zero-filled tail keys
 #pragma unroll
@@ -204,26 +206,42 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       const float moff = m_run * sl2;
       uint8_t* p_row = sP + buf * ATT_Q_BYTES + row * 128;
+      // exponentials: 3 of every 4 on the MUFU pipe (ex2.approx), 1 of 4 as a polynomial on the FMA pipe -- the two
+      // softmax warps that share an SM sub-partition are otherwise serialised on its one MUFU unit
+      uint32_t pk0[16], pk1[16];
 #pragma unroll
-      for (int half = 0; half < 2; half++) {
-        float p[32];
+      for (int i = 0; i < 32; i += 4) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(r0[i]), sl2, -moff));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(r0[i + 1]), sl2, -moff));
+        const float e2 = ex2_approx(fmaf(__uint_as_float(r0[i + 2]), sl2, -moff));
+        const float e3 = ex2_poly3(fmaf(__uint_as_float(r0[i + 3]), sl2, -moff));
+        pk0[i / 2] = pack2_bf16(e0, e1);
+        pk0[i / 2 + 1] = pack2_bf16(e2, e3);
+      }
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          p[i] = ex2_approx(fmaf(__uint_as_float(half ? r1[i] : r0[i]), sl2, -moff));
-          p[i + 1] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 1] : r0[i + 1]), sl2, -moff));
-          p[i + 2] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 2] : r0[i + 2]), sl2, -moff));
-          p[i + 3] = ex2_approx(fmaf(__uint_as_float(half ? r1[i + 3] : r0[i + 3]), sl2, -moff));
-        }
+      for (int i = 0; i < 32; i += 4) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(r1[i]), sl2, -moff));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(r1[i + 1]), sl2, -moff));
+        const float e2 = ex2_approx(fmaf(__uint_as_float(r1[i + 2]), sl2, -moff));
+        const float e3 = ex2_poly3(fmaf(__uint_as_float(r1[i + 3]), sl2, -moff));
+        pk1[i / 2] = pack2_bf16(e0, e1);
+        pk1[i / 2 + 1] = pack2_bf16(e2, e3);
+      }
+      // S_j is now dead in registers: prefetch S_{j+1} (its QK^T was issued one iteration ago)
+      if (j + 1 < n_blocks) {
+        mbar_wait(s_full + (buf ^ 1), (uint32_t)((j + 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_next = t_lane + TMEM_S + (uint32_t)((buf ^ 1) * ATT_BN);
+        tmem_ld_32x32(t_next, r0);
+        tmem_ld_32x32(t_next + 32u, r1);
+      }
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          uint4 pk;
-          pk.x = pack2_bf16(p[8 * q], p[8 * q + 1]); pk.y = pack2_bf16(p[8 * q + 2], p[8 * q + 3]);
-          pk.z = pack2_bf16(p[8 * q + 4], p[8 * q + 5]); pk.w = pack2_bf16(p[8 * q + 6], p[8 * q + 7]);
-          *reinterpret_cast<uint4*>(p_row + (((half * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
-        }
+      for (int q = 0; q < 4; q++) {
+        *reinterpret_cast<uint4*>(p_row + ((q ^ (row & 7)) << 4)) = make_uint4(pk0[4 * q], pk0[4 * q + 1], pk0[4 * q + 2], pk0[4 * q + 3]);
+        *reinterpret_cast<uint4*>(p_row + (((4 + q) ^ (row & 7)) << 4)) = make_uint4(pk1[4 * q], pk1[4 * q + 1], pk1[4 * q + 2], pk1[4 * q + 3]);
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();    // our tcgen05.ld/st of S_j and O are complete before the issuer proceeds
+      tc_fence_before();    // tcgen05.ld/st of S_j and O issued so far are ordered before the issuer proceeds
       mbar_arrive(p_full + buf);
     }
     {  // all blocks accumulated -> normalise and store

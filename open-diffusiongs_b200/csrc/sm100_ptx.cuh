@@ -155,6 +155,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f via the 1.5*2^23 magic constant, degree-3
+// near-minimax polynomial for 2^f on [-0.5, 0.5] (max rel err 7.7e-5), exponent patched in with integer adds.
+// x <= ~100; -inf and very negative inputs clamp to 2^-126 (~1e-38, i.e. zero at bf16/fp32-sum precision).
+__device__ __forceinline__ float ex2_poly3(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  const float p = fmaf(fmaf(fmaf(0.0550886838f, f, 0.2426040515f), f, 0.6932762417f), f, 0.9999289404f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // ---- descriptors ----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle, tile rows of exactly 128 bytes (64 bf16), tile base
 // 1024-byte aligned.  bits: [0,14) addr>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout.
