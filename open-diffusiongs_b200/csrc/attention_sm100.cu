@@ -18,6 +18,8 @@
 // softmax DENOMINATOR is computed by the tensor core -- a second tiny MMA  L += P_j x ONES  (N = 16, a constant
 // all-ones K-major tile) accumulates the row sums of the SAME bf16-rounded probabilities that enter P V, in 16 extra
 // TMEM columns next to O (ncu: the per-element FADD of the register row-sum was 13% of all issued instructions).
+#include <cstdlib>
+
 #include "dgs_internal.h"
 #include "dit_kernels.h"
 #include "sm100_ptx.cuh"
@@ -32,13 +34,17 @@ constexpr int ATT_KV_BYTES = ATT_BN * ATT_HD * 2;   // [64 x 64] bf16 (one K or 
 constexpr int ATT_ONES_BYTES = 16 * 128;           // [16 x 64] bf16 ones, K-major (B operand of the row-sum MMA)
 constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES * 3 + 2 * ATT_KV_STAGES * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;
 constexpr uint32_t TMEM_S = 0, TMEM_O = 2 * ATT_BN, TMEM_L = TMEM_O + ATT_HD, ATT_TMEM_COLS = 256;
-constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: rescale O only if the row max grew by > 2^8
+constexpr float ATT_RESCALE_THRESHOLD = 8.0f;
+// exponentials per 8 evaluated as an FMA-pipe polynomial instead of MUFU ex2: template parameter POLY_OF_8,
+// selected at run time by DGS_ATT_POLY (0, 2 or 4; default below)
+constexpr int ATT_POLY_DEFAULT = 0;  // log2 units: rescale O only if the row max grew by > 2^8
 
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+template <int ATT_POLY_OF_8>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      __nv_bfloat16* __restrict__ out, int N, int H) {
@@ -150,17 +156,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t t_o = t_lane + TMEM_O, t_l = t_lane + TMEM_L;
     float m_run = -INFINITY;
 
-    // S_0 -> registers; every later block is prefetched at the end of the previous iteration, so that the TMEM-load
-    // latency runs under the pack / store / fence / arrive tail instead of in front of the exponentials
-    uint32_t r0[32], r1[32];
-    mbar_wait(s_full, 0);
-    tc_fence_after();
-    tmem_ld_32x32(t_lane + TMEM_S, r0);
-    tmem_ld_32x32(t_lane + TMEM_S + 32u, r1);
-
     for (int j = 0; j < n_blocks; j++) {
       const int buf = j & 1;
+      mbar_wait(s_full + buf, (uint32_t)(j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_s = t_lane + TMEM_S + (uint32_t)(buf * ATT_BN);
       const int kv_valid = N - j * ATT_BN;  // >= 1; < ATT_BN only in the last block
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(t_s, r0);
+      tmem_ld_32x32(t_s + 32u, r1);
       tmem_ld_wait();
       if (kv_valid < ATT_BN) {  // warp-uniform: mask the zero-filled tail keys
 #pragma unroll
@@ -206,42 +210,25 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       const float moff = m_run * sl2;
       uint8_t* p_row = sP + buf * ATT_Q_BYTES + row * 128;
-      // exponentials: 3 of every 4 on the MUFU pipe (ex2.approx), 1 of 4 as a polynomial on the FMA pipe -- the two
-      // softmax warps that share an SM sub-partition are otherwise serialised on its one MUFU unit
-      uint32_t pk0[16], pk1[16];
+      // exponentials: ATT_POLY_OF_8 of every 8 as a polynomial on the FMA pipe, the rest on the MUFU pipe (ex2.approx)
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(r0[i]), sl2, -moff));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(r0[i + 1]), sl2, -moff));
-        const float e2 = ex2_approx(fmaf(__uint_as_float(r0[i + 2]), sl2, -moff));
-        const float e3 = ex2_poly3(fmaf(__uint_as_float(r0[i + 3]), sl2, -moff));
-        pk0[i / 2] = pack2_bf16(e0, e1);
-        pk0[i / 2 + 1] = pack2_bf16(e2, e3);
-      }
+      for (int half = 0; half < 2; half++) {
+        float p[32];
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(r1[i]), sl2, -moff));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(r1[i + 1]), sl2, -moff));
-        const float e2 = ex2_approx(fmaf(__uint_as_float(r1[i + 2]), sl2, -moff));
-        const float e3 = ex2_poly3(fmaf(__uint_as_float(r1[i + 3]), sl2, -moff));
-        pk1[i / 2] = pack2_bf16(e0, e1);
-        pk1[i / 2 + 1] = pack2_bf16(e2, e3);
-      }
-      // S_j is now dead in registers: prefetch S_{j+1} (its QK^T was issued one iteration ago)
-      if (j + 1 < n_blocks) {
-        mbar_wait(s_full + (buf ^ 1), (uint32_t)((j + 1) >> 1) & 1);
-        tc_fence_after();
-        const uint32_t t_next = t_lane + TMEM_S + (uint32_t)((buf ^ 1) * ATT_BN);
-        tmem_ld_32x32(t_next, r0);
-        tmem_ld_32x32(t_next + 32u, r1);
-      }
+        for (int i = 0; i < 32; i++) {
+          const float x = fmaf(__uint_as_float(half ? r1[i] : r0[i]), sl2, -moff);
+          p[i] = ((i & 7) < ATT_POLY_OF_8) ? ex2_poly3(x) : ex2_approx(x);
+        }
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        *reinterpret_cast<uint4*>(p_row + ((q ^ (row & 7)) << 4)) = make_uint4(pk0[4 * q], pk0[4 * q + 1], pk0[4 * q + 2], pk0[4 * q + 3]);
-        *reinterpret_cast<uint4*>(p_row + (((4 + q) ^ (row & 7)) << 4)) = make_uint4(pk1[4 * q], pk1[4 * q + 1], pk1[4 * q + 2], pk1[4 * q + 3]);
+        for (int q = 0; q < 4; q++) {
+          uint4 pk;
+          pk.x = pack2_bf16(p[8 * q], p[8 * q + 1]); pk.y = pack2_bf16(p[8 * q + 2], p[8 * q + 3]);
+          pk.z = pack2_bf16(p[8 * q + 4], p[8 * q + 5]); pk.w = pack2_bf16(p[8 * q + 6], p[8 * q + 7]);
+          *reinterpret_cast<uint4*>(p_row + (((half * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
+        }
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();    // tcgen05.ld/st of S_j and O issued so far are ordered before the issuer proceeds
+      tc_fence_before();    // our tcgen05.ld/st of S_j and O are complete before the issuer proceeds
       mbar_arrive(p_full + buf);
     }
     {  // all blocks accumulated -> normalise and store
@@ -296,13 +283,19 @@ int attention_fwd(const void* qkv, void* out, int B, int N, int H, cudaStream_t 
   if (rc) return rc;
   rc = make_tmap_bf16(&tm_kv, qkv, 3, dims, str, box_kv);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    configured = true;
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("DGS_ATT_POLY");
+    poly = e ? atoi(e) : ATT_POLY_DEFAULT;
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
   }
   dim3 grid(ceil_div(N, ATT_BM), H, B);
-  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, reinterpret_cast<__nv_bfloat16*>(out), N, H);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (poly >= 4) attention_fwd_kernel<4><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, N, H);
+  else if (poly >= 2) attention_fwd_kernel<2><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, N, H);
+  else attention_fwd_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, N, H);
   DGS_POST_LAUNCH();
   return DGS_OK;
 }
