@@ -130,17 +130,24 @@ typedef struct {
   float scale_modifier; /* 1.0 when the reference passes scaling_modifier=None */
   float bg[3];          /* (1,1,1) in render_opencv_cam, gs_core.py:880 */
   int debug;
+  int near_log2;        /* 0: one binning pass over all instances.  k > 0: two-phase binning -- phase A bins and blends
+                           only the nearest P >> k Gaussians of every view; if every pixel saturates there (dense scenes)
+                           the remaining instances are never emitted or sorted, otherwise phase B continues from the
+                           saved per-pixel state.  Same images, final_T, n_contrib and gradients either way. */
 } dgs_render_batch_args;
 
 int dgs_render_batch_forward(const dgs_render_batch_args* args, dgs_alloc_fn geom_alloc, void* geom_user,
                              dgs_alloc_fn binning_alloc, void* binning_user, dgs_alloc_fn image_alloc,
                              void* image_user, float* out_images, long long* num_rendered,
+                             long long* chunk_instances /* out [2]: instances binned in phase A / phase B */,
                              void* stream);
 
 /* d_* are caller-allocated, same shapes as the inputs; they are fully overwritten.  scratch_alloc
  * provides the per-(view, Gaussian) screen-space gradient records (44 B each), free after the call. */
-int dgs_render_batch_backward(const dgs_render_batch_args* args, long long R, const void* geom_buffer,
-                              const void* binning_buffer, const void* image_buffer,
+int dgs_render_batch_backward(const dgs_render_batch_args* args, long long R,
+                              const long long* chunk_instances /* [2] from the forward */, const void* geom_buffer,
+                              const void* binning_buffer /* 1st binning_alloc result */,
+                              const void* binning_buffer_b /* 2nd (phase B) or NULL */, const void* image_buffer,
                               const float* dL_dimages, float* d_xyz, float* d_features,
                               float* d_scaling, float* d_rotation, float* d_opacity,
                               dgs_alloc_fn scratch_alloc, void* scratch_user, void* stream);
@@ -148,7 +155,8 @@ int dgs_render_batch_backward(const dgs_render_batch_args* args, long long R, co
 /* Introspection used by the parity tests: copies of per-(view, Gaussian) / per-pixel forward state
  * out of the opaque arenas into caller DEVICE buffers (any may be NULL):
  * xy [N,2], depth [N], conic_opacity [N,4], rgb [N,3], tiles_touched [N] (N = n_views*P),
- * point_list [R], ranges [n_views*tiles,2], final_T / n_contrib [n_views*H*W]. */
+ * point_list [R], ranges [n_views*tiles,2], final_T / n_contrib [n_views*H*W].  point_list / ranges describe a
+ * single-pass binning (near_log2 == 0); the per-pixel and per-Gaussian outputs are valid in both modes. */
 int dgs_raster_export_state(int n_views, int P, int W, int H, long long R, const void* geom_buffer,
                             const void* binning_buffer, const void* image_buffer, float* xy,
                             float* depth, float* conic_opacity, float* rgb, uint32_t* tiles_touched,

@@ -40,6 +40,7 @@ struct Camera {
 struct Problem {
   int NV, V, P, D, M, W, H, gx, gy, tiles;
   int raw;  // 1: inputs are raw renderer tensors -> apply exp / normalize / sigmoid in-kernel
+  int near_log2;  // > 0: two-phase binning, phase A = the nearest P >> near_log2 Gaussians of every view
   float mod;
   const float* means;
   const float* shs;
@@ -63,6 +64,8 @@ struct GeomState {
   uint32_t* perm;      // sorted: Gaussian index at each depth rank
   uint32_t* tiles_sorted;  // tiles touched in depth-rank order
   uint32_t* offsets;       // inclusive scan of tiles_sorted
+  uint32_t* view_meta;     // [NV][4] two-phase binning: {startA, startB, baseA, baseB} instance offsets per view
+  uint32_t* totals;        // [4] {R, R_near, tiles not finished after phase A, -}
   Camera* cams;
   void* scan_temp;
   size_t scan_bytes;
@@ -80,6 +83,8 @@ struct GeomState {
     s.perm = c.take<uint32_t>(N);
     s.tiles_sorted = c.take<uint32_t>(N);
     s.offsets = c.take<uint32_t>(N);
+    s.view_meta = c.take<uint32_t>((size_t)NV * 4);
+    s.totals = c.take<uint32_t>(4);
     s.cams = c.take<Camera>(NV);
     size_t scan_b = 0, sort_b = 0;
     cub::DeviceScan::InclusiveSum(nullptr, scan_b, s.tiles_sorted, s.offsets, (int)N);
@@ -118,6 +123,9 @@ struct ImgState {
   float* final_T;
   uint32_t* n_contrib;
   uint2* ranges;
+  uint2* ranges_b;     // phase-B tile ranges (two-phase binning)
+  float4* acc;         // per-pixel blend state between the phases: {C.r, C.g, C.b, T}
+  uint32_t* contrib;   // entries visited so far | (finished << 31)
   static ImgState carve(void* base, int NV, int W, int H, size_t* total) {
     ImgState s;
     Carver c(base);
@@ -126,6 +134,9 @@ struct ImgState {
     s.final_T = c.take<float>(npix);
     s.n_contrib = c.take<uint32_t>(npix);
     s.ranges = c.take<uint2>(ntiles);
+    s.ranges_b = c.take<uint2>(ntiles);
+    s.acc = c.take<float4>(npix);
+    s.contrib = c.take<uint32_t>(npix);
     if (total) *total = c.bytes();
     return s;
   }
@@ -481,18 +492,44 @@ __global__ void gather_tiles_kernel(size_t N, int P, GeomState gs) {
 // ---------------------------------------------------------------------------------------------
 constexpr int DUP_COOP_THRESHOLD = 32;
 
+// Two-phase binning bookkeeping: per view, where its near (ranks < Pn) and far instances start in the global scan and
+// in the two compact per-phase buffers; totals[0] = R, totals[1] = R_near.  One block, NV is small.
+__global__ void chunk_meta_kernel(int NV, int P, int Pn, const uint32_t* __restrict__ offsets,
+                                  uint32_t* __restrict__ view_meta, uint32_t* __restrict__ totals) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t baseA = 0, baseB = 0;
+  for (int v = 0; v < NV; v++) {
+    const size_t k0 = (size_t)v * P;
+    const uint32_t startA = (k0 == 0) ? 0u : offsets[k0 - 1];
+    const uint32_t startB = offsets[k0 + Pn - 1];
+    const uint32_t end = offsets[k0 + P - 1];
+    view_meta[4 * v + 0] = startA; view_meta[4 * v + 1] = startB;
+    view_meta[4 * v + 2] = baseA; view_meta[4 * v + 3] = baseB;
+    baseA += startB - startA;
+    baseB += end - startB;
+  }
+  totals[0] = baseA + baseB;
+  totals[1] = baseA;
+  totals[2] = 0;
+}
+
+// phase 0: every rank, global scan offsets; phase 1: ranks [0, Pn) into the compact near buffer; phase 2: ranks
+// [Pn, P) into the compact far buffer
 __global__ void __launch_bounds__(256) emit_keys_kernel(Problem pb, GeomState gs, uint32_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ vals) {
+                                                        uint32_t* __restrict__ vals, int phase, int rank_lo,
+                                                        int rank_hi) {
   const int view = blockIdx.y;
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;  // depth rank inside the view
+  const int r = rank_lo + blockIdx.x * blockDim.x + threadIdx.x;  // depth rank inside the view
   const int lane = threadIdx.x & 31;
-  const bool in_range = r < pb.P;
-  const size_t k = (size_t)view * pb.P + (in_range ? r : 0);
+  const bool in_range = r < rank_hi;
+  const size_t k = (size_t)view * pb.P + (in_range ? r : rank_lo);
   uint32_t cnt = in_range ? gs.tiles_sorted[k] : 0;
   uint32_t off = 0, id = 0;
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   if (cnt) {
     off = (k == 0) ? 0u : gs.offsets[k - 1];
+    if (phase == 1) off = off - gs.view_meta[4 * view + 0] + gs.view_meta[4 * view + 2];
+    else if (phase == 2) off = off - gs.view_meta[4 * view + 1] + gs.view_meta[4 * view + 3];
     id = gs.perm[k];
     const float4 g = gs.g0[(size_t)view * pb.P + id];
     tile_rect(g.x, g.y, __float_as_int(g.w), pb.gx, pb.gy, x0, y0, x1, y1);
@@ -540,6 +577,9 @@ __global__ void tile_ranges_kernel(long long R, const uint32_t* __restrict__ key
 // ---------------------------------------------------------------------------------------------
 // K6: per-tile front-to-back alpha blend (forward.cu:261-374), one CTA per (view, tile)
 // ---------------------------------------------------------------------------------------------
+// MODE 0: the whole list in one pass.  MODE 1: phase A of two (the nearest Gaussians); saves the per-pixel blend state
+// and counts the tiles that still have unfinished pixels.  MODE 2: phase B, continues from that state.
+template <int MODE>
 __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, GeomState gs, ImgState im,
                                                                  const uint32_t* __restrict__ point_list,
                                                                  float* __restrict__ out_color) {
@@ -550,8 +590,9 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, Geo
   const int x = tx * TILE + lx, y = ty * TILE + ly;
   const bool inside = x < pb.W && y < pb.H;
   const float pxf = (float)x, pyf = (float)y;
-  const uint2 range = im.ranges[tile_g];
+  const uint2 range = (MODE == 2) ? im.ranges_b[tile_g] : im.ranges[tile_g];
   const size_t gbase = (size_t)view * pb.P;
+  const size_t pix_g = (size_t)view * pb.W * pb.H + (size_t)y * pb.W + x;
 
   __shared__ float2 s_xy[TILE_PIX];
   __shared__ float4 s_co[TILE_PIX];
@@ -560,6 +601,14 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, Geo
   bool done = !inside;
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
   uint32_t contributor = 0, last = 0;
+  if (MODE == 2 && inside) {
+    const float4 a = im.acc[pix_g];
+    const uint32_t cb = im.contrib[pix_g];
+    C0 = a.x; C1 = a.y; C2 = a.z; T = a.w;
+    contributor = cb & 0x7fffffffu;
+    done = (cb >> 31) != 0;
+    last = im.n_contrib[pix_g];
+  }
   int todo = (int)(range.y - range.x);
   for (uint32_t start = range.x; start < range.y; start += TILE_PIX, todo -= TILE_PIX) {
     if (__syncthreads_count(done) == TILE_PIX) break;
@@ -591,6 +640,15 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, Geo
       last = contributor;
     }
   }
+  if (MODE == 1) {
+    // a pixel that ran out of phase-A entries without saturating must continue in phase B
+    if (inside) {
+      im.acc[pix_g] = make_float4(C0, C1, C2, T);
+      im.contrib[pix_g] = contributor | (done ? 0x80000000u : 0u);
+    }
+    const int unfinished = __syncthreads_or(!done);
+    if (threadIdx.x == 0 && unfinished) atomicAdd(gs.totals + 2, 1u);
+  }
   if (inside) {
     const size_t pid = (size_t)y * pb.W + x;
     const size_t ibase = (size_t)view * pb.W * pb.H;
@@ -621,6 +679,7 @@ constexpr int BWD_CHUNK = 64;  // Gaussians staged per round in the backward
 
 __global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(Problem pb, GeomState gs, ImgState im,
                                                                   const uint32_t* __restrict__ point_list,
+                                                                  const uint32_t* __restrict__ point_list_b,
                                                                   const float* __restrict__ dL_dpix,
                                                                   float* __restrict__ dmean2D /*[N,3]*/,
                                                                   float* __restrict__ dconic /*[N,4]*/,
@@ -665,6 +724,8 @@ __global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(Problem pb, Ge
   __syncthreads();
   const uint32_t deepest = s_max;  // entries [0, deepest) of this tile's list matter
   if (deepest == 0) return;
+  const uint32_t len_a = range.y - range.x;
+  const uint2 range_b = point_list_b ? im.ranges_b[tile_g] : make_uint2(0u, 0u);
 
   float T = T_final;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
@@ -676,7 +737,9 @@ __global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(Problem pb, Ge
     const int nb = min(BWD_CHUNK, top + 1);
     __syncthreads();  // previous chunk's s_acc fully flushed, staging buffers free
     if (threadIdx.x < nb) {
-      const uint32_t id = point_list[range.x + (uint32_t)(top - (int)threadIdx.x)];
+      // position in the tile's full depth-ordered list = phase-A entries followed by phase-B entries
+      const uint32_t pos_t = (uint32_t)(top - (int)threadIdx.x);
+      const uint32_t id = (pos_t < len_a) ? point_list[range.x + pos_t] : point_list_b[range_b.x + (pos_t - len_a)];
       const size_t g = gbase + id;
       s_id[threadIdx.x] = id;
       const float4 a0 = gs.g0[g];
@@ -1024,8 +1087,8 @@ struct ForwardPlan {
 static int run_forward(Problem pb, bool build_cams, const float* c2w, const float* fxfycxcy, const float* view,
                        const float* proj, const float* campos, float tanx, float tany, dgs_alloc_fn geom_alloc,
                        void* geom_user, dgs_alloc_fn bin_alloc, void* bin_user, dgs_alloc_fn img_alloc,
-                       void* img_user, float* out_color, int* radii, long long* R_out, cudaStream_t st,
-                       int debug) {
+                       void* img_user, float* out_color, int* radii, long long* R_out, long long chunk_R[2],
+                       cudaStream_t st, int debug) {
   const size_t N = (size_t)pb.NV * pb.P;
   DGS_REQUIRE(N < (size_t)INT32_MAX, "n_views * P = %zu does not fit the 32-bit scan", N);
   size_t gbytes = 0, ibytes = 0;
@@ -1058,42 +1121,89 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
     DGS_LAUNCH_OK(st, debug);
     DGS_CUDA_OK(cub::DeviceScan::InclusiveSum(gs.scan_temp, gs.scan_bytes, gs.tiles_sorted, gs.offsets, (int)N, st));
   }
-  uint32_t R32 = 0;
-  DGS_CUDA_OK(cudaMemcpyAsync(&R32, gs.offsets + N - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  DGS_CUDA_OK(cudaStreamSynchronize(st));  // the one host sync per batch
-  const long long R = (long long)R32;
+  // two-phase binning candidates need the near/far split of the instance counts; it rides on the same single sync
+  const int Pn = (pb.near_log2 > 0) ? (pb.P >> pb.near_log2) : 0;
+  const bool may_split = Pn >= 1024;
+  uint32_t tot[2] = {0, 0};
+  if (may_split) {
+    chunk_meta_kernel<<<1, 32, 0, st>>>(pb.NV, pb.P, Pn, gs.offsets, gs.view_meta, gs.totals);
+    DGS_LAUNCH_OK(st, debug);
+    DGS_CUDA_OK(cudaMemcpyAsync(tot, gs.totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  } else {
+    DGS_CUDA_OK(cudaMemcpyAsync(tot, gs.offsets + N - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  }
+  DGS_CUDA_OK(cudaStreamSynchronize(st));  // the one host sync per batch (two-phase: a second, after phase A)
+  const long long R = (long long)tot[0];
   if (R >= (long long)INT32_MAX) { set_error("instance count %lld exceeds 2^31-1", R); return DGS_ERR_OVERFLOW; }
   *R_out = R;
-
-  size_t bbytes = 0;
-  BinState::carve(nullptr, R, &bbytes);
-  void* bbuf = bin_alloc(bbytes, bin_user);
-  if (!bbuf) { set_error("binning allocator returned NULL"); return DGS_ERR_ALLOC; }
-  BinState bs = BinState::carve(bbuf, R, nullptr);
+  // phase A must be a real saving: at most half of the instances
+  const bool split = may_split && R >= (1ll << 21) && 2ll * tot[1] <= R && tot[1] > 0;
+  const long long RA = split ? (long long)tot[1] : R;
+  const long long RB = split ? R - RA : 0;
+  chunk_R[0] = RA;
+  chunk_R[1] = 0;
 
   const size_t ntiles = (size_t)pb.NV * pb.tiles;
-  DGS_CUDA_OK(cudaMemsetAsync(im.ranges, 0, ntiles * sizeof(uint2), st));
-  if (R > 0) {
-    {
-      ProfScope ps(st, PROF_RASTER_EMIT);
-      emit_keys_kernel<<<pgrid, 256, 0, st>>>(pb, gs, bs.keys_in, bs.vals_in);
-      DGS_LAUNCH_OK(st, debug);
+  const int end_bit = bits_for((uint32_t)ntiles);  // tile ids only: depth order is already in the emission order
+  // one binning pass over a rank range into its own arena: emit -> stable tile sort -> tile ranges
+  auto bin_pass = [&](long long Rp, int phase, int rank_lo, int rank_hi, uint2* ranges, BinState* out_bs) -> int {
+    size_t bbytes = 0;
+    BinState::carve(nullptr, Rp, &bbytes);
+    void* bbuf = bin_alloc(bbytes, bin_user);
+    if (!bbuf) { set_error("binning allocator returned NULL"); return DGS_ERR_ALLOC; }
+    BinState bs = BinState::carve(bbuf, Rp, nullptr);
+    *out_bs = bs;
+    DGS_CUDA_OK(cudaMemsetAsync(ranges, 0, ntiles * sizeof(uint2), st));
+    if (Rp > 0) {
+      {
+        ProfScope ps(st, PROF_RASTER_EMIT);
+        dim3 egrid(ceil_div(rank_hi - rank_lo, 256), pb.NV);
+        emit_keys_kernel<<<egrid, 256, 0, st>>>(pb, gs, bs.keys_in, bs.vals_in, phase, rank_lo, rank_hi);
+        DGS_LAUNCH_OK(st, debug);
+      }
+      {
+        ProfScope ps(st, PROF_RASTER_SORT);
+        DGS_CUDA_OK(cub::DeviceRadixSort::SortPairs(bs.sort_temp, bs.sort_bytes, bs.keys_in, bs.keys, bs.vals_in,
+                                                    bs.point_list, (int)Rp, 0, end_bit, st));
+      }
+      {
+        ProfScope ps(st, PROF_RASTER_RANGES);
+        tile_ranges_kernel<<<(unsigned)((Rp + 255) / 256), 256, 0, st>>>(Rp, bs.keys, ranges);
+        DGS_LAUNCH_OK(st, debug);
+      }
     }
-    const int end_bit = bits_for((uint32_t)ntiles);  // tile ids only: depth order is already in the emission order
-    {
-      ProfScope ps(st, PROF_RASTER_SORT);
-      DGS_CUDA_OK(cub::DeviceRadixSort::SortPairs(bs.sort_temp, bs.sort_bytes, bs.keys_in, bs.keys, bs.vals_in,
-                                                  bs.point_list, (int)R, 0, end_bit, st));
-    }
-    {
-      ProfScope ps(st, PROF_RASTER_RANGES);
-      tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, bs.keys, im.ranges);
-      DGS_LAUNCH_OK(st, debug);
-    }
-  }
-  {
+    return DGS_OK;
+  };
+
+  BinState bsa, bsb;
+  if (!split) {
+    int rc = bin_pass(R, 0, 0, pb.P, im.ranges, &bsa);
+    if (rc) return rc;
     ProfScope ps(st, PROF_RASTER_BLEND_FWD);
-    blend_forward_kernel<<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bs.point_list, out_color);
+    blend_forward_kernel<0><<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bsa.point_list, out_color);
+    DGS_LAUNCH_OK(st, debug);
+    return DGS_OK;
+  }
+  // ---- phase A: the nearest Pn Gaussians of every view.  In dense scenes every pixel saturates here and the
+  // remaining (1 - 2^-near_log2) of the instances are never emitted, sorted or read.
+  {
+    int rc = bin_pass(RA, 1, 0, Pn, im.ranges, &bsa);
+    if (rc) return rc;
+    ProfScope ps(st, PROF_RASTER_BLEND_FWD);
+    blend_forward_kernel<1><<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bsa.point_list, out_color);
+    DGS_LAUNCH_OK(st, debug);
+  }
+  uint32_t unfinished = 0;
+  DGS_CUDA_OK(cudaMemcpyAsync(&unfinished, gs.totals + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  DGS_CUDA_OK(cudaStreamSynchronize(st));
+  if (unfinished == 0) return DGS_OK;
+  // ---- phase B: everything behind, continuing from the saved per-pixel state
+  {
+    int rc = bin_pass(RB, 2, Pn, pb.P, im.ranges_b, &bsb);
+    if (rc) return rc;
+    chunk_R[1] = RB;
+    ProfScope ps(st, PROF_RASTER_BLEND_FWD);
+    blend_forward_kernel<2><<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bsb.point_list, out_color);
     DGS_LAUNCH_OK(st, debug);
   }
   return DGS_OK;
@@ -1104,7 +1214,7 @@ static Problem make_problem(int NV, int V, int P, int D, int M, int W, int H, in
   memset(&pb, 0, sizeof(pb));
   pb.NV = NV; pb.V = V; pb.P = P; pb.D = D; pb.M = M; pb.W = W; pb.H = H;
   pb.gx = ceil_div(W, TILE); pb.gy = ceil_div(H, TILE); pb.tiles = pb.gx * pb.gy;
-  pb.raw = raw; pb.mod = mod;
+  pb.raw = raw; pb.mod = mod; pb.near_log2 = 0;
   return pb;
 }
 
@@ -1167,9 +1277,9 @@ int dgs_raster_forward(const dgs_raster_args* a, dgs_alloc_fn geom_alloc, void* 
   DGS_CUDA_OK(cudaMemcpyAsync(bg, a->background, sizeof(bg), cudaMemcpyDeviceToHost, st));
   DGS_CUDA_OK(cudaStreamSynchronize(st));
   Problem pb = single_problem(a, bg);
-  long long R = 0;
+  long long R = 0, chunk_R[2] = {0, 0};
   rc = run_forward(pb, false, nullptr, nullptr, a->viewmatrix, a->projmatrix, a->campos, a->tan_fovx, a->tan_fovy,
-                   geom_alloc, geom_user, bin_alloc, bin_user, img_alloc, img_user, out_color, radii, &R, st,
+                   geom_alloc, geom_user, bin_alloc, bin_user, img_alloc, img_user, out_color, radii, &R, chunk_R, st,
                    a->debug);
   *num_rendered = (int)R;
   return rc;
@@ -1194,8 +1304,8 @@ int dgs_raster_backward(const dgs_raster_args* a, int R, const int* radii, const
   ImgState im = ImgState::carve(const_cast<void*>(image_buffer), 1, a->W, a->H, nullptr);
   BinState bs = BinState::carve(const_cast<void*>(binning_buffer), R, nullptr);
   if (R > 0) {
-    blend_backward_kernel<<<pb.tiles, TILE_PIX, 0, st>>>(pb, gs, im, bs.point_list, dL_dpix, dL_dmean2D, dL_dconic,
-                                                          dL_dopacity, dL_dcolor);
+    blend_backward_kernel<<<pb.tiles, TILE_PIX, 0, st>>>(pb, gs, im, bs.point_list, nullptr, dL_dpix, dL_dmean2D,
+                                                          dL_dconic, dL_dopacity, dL_dcolor);
     DGS_LAUNCH_OK(st, a->debug);
   }
   GeomGradOut out;
@@ -1230,34 +1340,43 @@ static Problem batch_problem(const dgs_render_batch_args* a) {
   Problem pb = make_problem(a->B * a->V, a->V, a->P, a->D, a->M, a->W, a->H, 1, a->scale_modifier);
   pb.means = a->xyz; pb.shs = a->features; pb.opac = a->opacity; pb.scales = a->scaling; pb.rots = a->rotation;
   pb.bg[0] = a->bg[0]; pb.bg[1] = a->bg[1]; pb.bg[2] = a->bg[2];
+  pb.near_log2 = a->near_log2 > 0 ? a->near_log2 : 0;
   return pb;
 }
 
 int dgs_render_batch_forward(const dgs_render_batch_args* a, dgs_alloc_fn geom_alloc, void* geom_user,
                              dgs_alloc_fn bin_alloc, void* bin_user, dgs_alloc_fn img_alloc, void* img_user,
-                             float* out_images, long long* num_rendered, void* stream) {
+                             float* out_images, long long* num_rendered, long long* chunk_instances,
+                             void* stream) {
   int rc = check_batch_args(a);
   if (rc) return rc;
-  DGS_REQUIRE(geom_alloc && bin_alloc && img_alloc && out_images && num_rendered, "NULL output/allocator");
+  DGS_REQUIRE(geom_alloc && bin_alloc && img_alloc && out_images && num_rendered && chunk_instances,
+              "NULL output/allocator");
   Problem pb = batch_problem(a);
   return run_forward(pb, true, a->c2w, a->fxfycxcy, nullptr, nullptr, nullptr, 0.f, 0.f, geom_alloc, geom_user,
-                     bin_alloc, bin_user, img_alloc, img_user, out_images, nullptr, num_rendered,
+                     bin_alloc, bin_user, img_alloc, img_user, out_images, nullptr, num_rendered, chunk_instances,
                      (cudaStream_t)stream, a->debug);
 }
 
-int dgs_render_batch_backward(const dgs_render_batch_args* a, long long R, const void* geom_buffer,
-                              const void* binning_buffer, const void* image_buffer, const float* dL_dimages,
+int dgs_render_batch_backward(const dgs_render_batch_args* a, long long R, const long long* chunk_instances,
+                              const void* geom_buffer, const void* binning_buffer, const void* binning_buffer_b,
+                              const void* image_buffer, const float* dL_dimages,
                               float* d_xyz, float* d_features, float* d_scaling, float* d_rotation,
                               float* d_opacity, dgs_alloc_fn scratch_alloc, void* scratch_user, void* stream) {
   int rc = check_batch_args(a);
   if (rc) return rc;
-  DGS_REQUIRE(geom_buffer && binning_buffer && image_buffer && dL_dimages && scratch_alloc, "NULL state buffer");
+  DGS_REQUIRE(geom_buffer && binning_buffer && image_buffer && dL_dimages && scratch_alloc && chunk_instances,
+              "NULL state buffer");
+  DGS_REQUIRE(chunk_instances[1] == 0 || binning_buffer_b, "phase-B binning buffer missing");
   DGS_REQUIRE(d_xyz && d_features && d_scaling && d_rotation && d_opacity, "NULL gradient buffer");
   cudaStream_t st = (cudaStream_t)stream;
   Problem pb = batch_problem(a);
   GeomState gs = GeomState::carve(const_cast<void*>(geom_buffer), pb.NV, pb.P, nullptr);
   ImgState im = ImgState::carve(const_cast<void*>(image_buffer), pb.NV, pb.W, pb.H, nullptr);
-  BinState bs = BinState::carve(const_cast<void*>(binning_buffer), R, nullptr);
+  BinState bs = BinState::carve(const_cast<void*>(binning_buffer), chunk_instances[0], nullptr);
+  const uint32_t* list_b = nullptr;
+  if (chunk_instances[1] > 0)
+    list_b = BinState::carve(const_cast<void*>(binning_buffer_b), chunk_instances[1], nullptr).point_list;
   // per-(view, Gaussian) screen-space gradient records: mean2D[3] conic[4] opacity[1] colour[3]
   const size_t N = (size_t)pb.NV * pb.P;
   Carver c(nullptr);
@@ -1274,7 +1393,7 @@ int dgs_render_batch_backward(const dgs_render_batch_args* a, long long R, const
   if (R > 0) {
     ProfScope ps(st, PROF_RASTER_BLEND_BWD);
     blend_backward_kernel<<<(unsigned)((size_t)pb.NV * pb.tiles), TILE_PIX, 0, st>>>(
-        pb, gs, im, bs.point_list, dL_dimages, dmean2D, dconic, dopac, dcolor);
+        pb, gs, im, bs.point_list, list_b, dL_dimages, dmean2D, dconic, dopac, dcolor);
     DGS_LAUNCH_OK(st, a->debug);
   }
   GeomGradOut out;

@@ -24,7 +24,7 @@ class RenderBatchArgs(C.Structure):
                 ("W", C.c_int), ("H", C.c_int), ("xyz", C.c_void_p), ("features", C.c_void_p),
                 ("scaling", C.c_void_p), ("rotation", C.c_void_p), ("opacity", C.c_void_p),
                 ("c2w", C.c_void_p), ("fxfycxcy", C.c_void_p), ("scale_modifier", C.c_float),
-                ("bg", C.c_float * 3), ("debug", C.c_int)]
+                ("bg", C.c_float * 3), ("debug", C.c_int), ("near_log2", C.c_int)]
 
 
 class DitWeights(C.Structure):
@@ -72,8 +72,9 @@ def lib():
         L.dgs_raster_backward.argtypes = [C.POINTER(RasterArgs), C.c_int] + [vp] * 15
         L.dgs_mark_visible.argtypes = [C.c_int, vp, vp, vp, vp, vp]
         L.dgs_render_batch_forward.argtypes = [C.POINTER(RenderBatchArgs), ALLOC_FN, vp, ALLOC_FN, vp,
-                                               ALLOC_FN, vp, vp, C.POINTER(C.c_longlong), vp]
-        L.dgs_render_batch_backward.argtypes = [C.POINTER(RenderBatchArgs), C.c_longlong] + [vp] * 9 + [ALLOC_FN, vp, vp]
+                                               ALLOC_FN, vp, vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), vp]
+        L.dgs_render_batch_backward.argtypes = [C.POINTER(RenderBatchArgs), C.c_longlong, C.POINTER(C.c_longlong)] + \
+            [vp] * 11 + [ALLOC_FN, vp, vp]
         L.dgs_raster_export_state.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong] + [vp] * 13
         L.dgs_dit_workspace_bytes.restype = C.c_size_t
         L.dgs_dit_workspace_bytes.argtypes = [C.POINTER(DitWeights), C.c_int, C.c_int, C.c_int, C.c_int]

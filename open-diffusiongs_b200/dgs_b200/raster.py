@@ -21,21 +21,24 @@ class _Arena:
 
     def __init__(self, device, cache=None, key=None):
         self.device = device
-        self.cache, self.key = cache, key   # optional grow-only buffer re-used across calls (inference path)
+        self.cache, self.key = cache, key   # optional grow-only buffers re-used across calls (inference path)
         self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.tensors = []                   # every buffer handed out (the binning arena is requested once per phase)
         self.cb = ALLOC_FN(self._alloc)
 
     def _alloc(self, nbytes, _user):
         try:
             if self.cache is not None:
-                t = self.cache.get(self.key)
+                k = f"{self.key}{len(self.tensors)}"
+                t = self.cache.get(k)
                 if t is None or t.numel() < nbytes or t.device != self.device:
                     t = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
-                    self.cache[self.key] = t
-                self.tensor = t
-                return t.data_ptr()
-            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-            return self.tensor.data_ptr()
+                    self.cache[k] = t
+            else:
+                t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self.tensor = t
+            self.tensors.append(t)
+            return t.data_ptr()
         except Exception:  # noqa: BLE001  (propagated as DGS_ERR_ALLOC by the C side)
             return None
 
@@ -143,7 +146,11 @@ def mark_visible(means3D, viewmatrix, projmatrix):
 # ------------------------------------------------------------------------------------------------
 # batched renderer
 # ------------------------------------------------------------------------------------------------
-def _batch_args(xyz, features, scaling, rotation, opacity, C2W, fxfycxcy, H, W, scale_modifier, debug=False):
+DEFAULT_NEAR_LOG2 = 3  # two-phase binning: phase A = the nearest 1/8 of every view's Gaussians (0 = single pass)
+
+
+def _batch_args(xyz, features, scaling, rotation, opacity, C2W, fxfycxcy, H, W, scale_modifier, debug=False,
+                near_log2=0):
     B, P = xyz.shape[0], xyz.shape[1]
     V = C2W.shape[1]
     M = features.shape[2]
@@ -151,13 +158,14 @@ def _batch_args(xyz, features, scaling, rotation, opacity, C2W, fxfycxcy, H, W, 
     a = RenderBatchArgs(B=B, V=V, P=P, M=M, D=D, W=int(W), H=int(H), xyz=xyz.data_ptr(), features=features.data_ptr(),
                         scaling=scaling.data_ptr(), rotation=rotation.data_ptr(), opacity=opacity.data_ptr(),
                         c2w=C2W.data_ptr(), fxfycxcy=fxfycxcy.data_ptr(),
-                        scale_modifier=1.0 if scale_modifier is None else float(scale_modifier), debug=int(debug))
+                        scale_modifier=1.0 if scale_modifier is None else float(scale_modifier), debug=int(debug),
+                        near_log2=int(near_log2))
     a.bg[0] = a.bg[1] = a.bg[2] = 1.0  # render_opencv_cam's default bg_color, gs_core.py:880
     return a
 
 
 def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, fxfycxcy, scale_modifier=None,
-                         arena_cache=None):
+                         arena_cache=None, near_log2=None):
     """All (sample, view) pairs in one launch set -> (images [B,V,3,H,W] fp32, state).
     `arena_cache` (a dict): re-use grow-only arenas across calls -- only valid when no backward will follow (the
     inference / denoise-step path); stream order makes the re-use safe."""
@@ -168,14 +176,18 @@ def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, f
     with torch.cuda.device(dev):
         out = torch.empty(B, V, 3, int(H), int(W), dtype=torch.float32, device=dev)
         geom, binning, img = (_Arena(dev, arena_cache, k) for k in ("geom", "binning", "img"))
-        a = _batch_args(*tens, H, W, scale_modifier)
+        near_log2 = DEFAULT_NEAR_LOG2 if near_log2 is None else near_log2
+        a = _batch_args(*tens, H, W, scale_modifier, near_log2=near_log2)
         R = C.c_longlong(0)
+        chunks = (C.c_longlong * 2)(0, 0)
         check(_lib.lib().dgs_render_batch_forward(C.byref(a), geom.cb, None, binning.cb, None, img.cb, None,
-                                                  out.data_ptr(), C.byref(R), _stream(dev)))
+                                                  out.data_ptr(), C.byref(R), chunks, _stream(dev)))
     global LAST_NUM_RENDERED
     LAST_NUM_RENDERED = R.value
-    state = dict(tensors=tens, geom=geom.tensor, binning=binning.tensor, img=img.tensor, R=R.value, H=int(H),
-                 W=int(W), scale_modifier=scale_modifier)
+    state = dict(tensors=tens, geom=geom.tensor, binning=binning.tensors[0],
+                 binning_b=binning.tensors[1] if len(binning.tensors) > 1 else None, img=img.tensor, R=R.value,
+                 chunks=(int(chunks[0]), int(chunks[1])), H=int(H), W=int(W), scale_modifier=scale_modifier,
+                 near_log2=near_log2)
     return out, state
 
 
@@ -187,9 +199,11 @@ def render_batch_backward(state, grad_images):
     with torch.cuda.device(dev):
         outs = [torch.empty_like(t) for t in tens[:5]]
         scratch = _Arena(dev)
-        a = _batch_args(*tens, state["H"], state["W"], state["scale_modifier"])
+        a = _batch_args(*tens, state["H"], state["W"], state["scale_modifier"], near_log2=state["near_log2"])
+        chunks = (C.c_longlong * 2)(*state["chunks"])
         check(_lib.lib().dgs_render_batch_backward(
-            C.byref(a), state["R"], _ptr(state["geom"]), _ptr(state["binning"]), _ptr(state["img"]), g.data_ptr(),
+            C.byref(a), state["R"], chunks, _ptr(state["geom"]), _ptr(state["binning"]), _ptr(state["binning_b"]),
+            _ptr(state["img"]), g.data_ptr(),
             outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), outs[4].data_ptr(),
             scratch.cb, None, _stream(dev)))
     return tuple(outs)

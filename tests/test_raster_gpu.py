@@ -295,7 +295,7 @@ def test_full_size_properties_obj256():
     raw, c2w, fx = _batch_inputs(B, V, P, W, H, dist="init")
     raw["features"] = np.full_like(raw["features"], (1.0 - 0.5) / 0.28209479177387814)  # rgb == 1 exactly
     t = [T(raw[k]) for k in ("xyz", "features", "scaling", "rotation", "opacity")]
-    img, state = raster.render_batch_forward(*t, H, W, T(c2w), T(fx))
+    img, state = raster.render_batch_forward(*t, H, W, T(c2w), T(fx), near_log2=0)  # single pass: lists exportable
     assert float((img - 1.0).abs().max()) < 5e-5  # sum_i w_i + T_final == 1
     R = state["R"]
     ex = raster.export_state(B * V, P, W, H, R, state["geom"], state["binning"], state["img"])
@@ -318,3 +318,28 @@ def test_full_size_properties_obj256():
     for a_, b_ in zip(d1, d2):
         assert rel_l2((2.0 * a_).cpu().numpy(), b_.cpu().numpy()) < 1e-5
     print(f"obj-256 init-like: R={R} ({R / (B * V):.0f} instances/view)")
+
+
+@pytest.mark.parametrize("dist,P,expect_phase_b", [("init", 2 + 4 * 256 * 256, False), ("fine", 400000, True)])
+def test_two_phase_binning_is_exact(dist, P, expect_phase_b):
+    """near_log2 = 3: phase A bins/blends only the nearest 1/8 of each view's Gaussians; dense scenes stop there, sparse
+    ones continue with phase B from the saved per-pixel state.  Images, final_T and n_contrib must be BIT-identical to
+    the single-pass result (same blend order), gradients equal up to atomics-order noise."""
+    from dgs_b200 import raster
+    B, V, W, H = 1, 4, 256, 256
+    raw, c2w, fx = _batch_inputs(B, V, P, W, H, dist=dist)
+    t = [T(raw[k]) for k in ("xyz", "features", "scaling", "rotation", "opacity")]
+    img1, st1 = raster.render_batch_forward(*t, H, W, T(c2w), T(fx), near_log2=0)
+    img2, st2 = raster.render_batch_forward(*t, H, W, T(c2w), T(fx), near_log2=3)
+    print(f"[{dist}] R={st1['R']} single-pass chunks={st1['chunks']} two-phase chunks={st2['chunks']}")
+    assert st1["R"] == st2["R"] and st1["chunks"] == (st1["R"], 0)
+    assert st2["chunks"][0] < st1["R"] // 2 and (st2["chunks"][1] > 0) == expect_phase_b
+    assert torch.equal(img1, img2)
+    e1 = raster.export_state(B * V, P, W, H, 0, st1["geom"], st1["binning"], st1["img"])
+    e2 = raster.export_state(B * V, P, W, H, 0, st2["geom"], st2["binning"], st2["img"])
+    assert torch.equal(e1["final_T"], e2["final_T"]) and torch.equal(e1["n_contrib"], e2["n_contrib"])
+    g = torch.randn(img1.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(3))
+    d1 = raster.render_batch_backward(st1, g)
+    d2 = raster.render_batch_backward(st2, g)
+    for a_, b_ in zip(d1, d2):
+        assert rel_l2(b_.cpu().numpy(), a_.cpu().numpy()) < 2e-5
