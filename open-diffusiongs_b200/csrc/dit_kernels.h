@@ -24,6 +24,9 @@ int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const 
 // CTA-pair (cta_group::2) variant, 256 x 256 tiles, needs N % 256 == 0 (gemm2_sm100.cu); gemm_bf16 dispatches to it
 int gemm_bf16_2cta(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st);
 
+// single-CTA 256 x 256 tile variant (gemm3_sm100.cu), needs N % 256 == 0
+int gemm_bf16_m256(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st);
+
 // softmax(Q K^T / sqrt(64)) V over qkv [B, N, 3, H, 64] (bf16) -> out [B, N, H*64] (bf16) (attention_sm100.cu)
 int attention_fwd(const void* qkv, void* out, int B, int N, int H, cudaStream_t st);
 

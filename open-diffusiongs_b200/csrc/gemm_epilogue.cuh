@@ -24,25 +24,28 @@ __device__ __forceinline__ uint32_t epi_pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NT>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 // Stage bias[n0 .. n0+BN) and (gate epilogue) gate[sample(row0)][n0 .. n0+BN) into shared memory.
 // `s_vec` = this accumulator buffer's [2][BN] floats.  All 128 epilogue threads call it.
 // NOTE gate: a 128-row tile may straddle two samples; rows then read their own sample's gate directly from global
 // memory (rare: one tile per sample boundary), signalled by *uniform_gate == false.
-template <int EPI, int BN>
-__device__ __forceinline__ void epilogue_stage_vectors(const GemmEpilogue& ep, float* s_vec, int et /*0..127*/, int m0,
+// NT = number of epilogue threads sharing s_vec (128, or 256 when two 128-row halves are drained side by side: then
+// ROWS = 256 and the sample-uniformity check spans both halves).
+template <int EPI, int BN, int NT = 128, int ROWS = 128>
+__device__ __forceinline__ void epilogue_stage_vectors(const GemmEpilogue& ep, float* s_vec, int et /*0..NT-1*/, int m0,
                                                        int n0, int M, int N, bool* uniform_gate) {
-  const int last_row = min(m0 + 127, M - 1);
+  const int last_row = min(m0 + ROWS - 1, M - 1);
   const bool uni = (EPI != EPI_GATE_RESID_F32) || (m0 / ep.rows_per_sample == last_row / ep.rows_per_sample);
   *uniform_gate = uni;
-  for (int i = et; i < BN; i += 128) {
+  for (int i = et; i < BN; i += NT) {
     const int n = n0 + i;
     s_vec[i] = (ep.bias && n < N) ? __ldg(ep.bias + n) : 0.f;
     if (EPI == EPI_GATE_RESID_F32)
       s_vec[BN + i] = (uni && n < N) ? __ldg(ep.gate + (size_t)(m0 / ep.rows_per_sample) * ep.gate_stride + n) : 0.f;
   }
-  epi_bar_sync();
+  epi_bar_sync<NT>();
 }
 
 // Drain one accumulator row (this thread's) of BN columns.

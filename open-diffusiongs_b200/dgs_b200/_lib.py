@@ -74,7 +74,7 @@ def lib():
         L.dgs_render_batch_forward.argtypes = [C.POINTER(RenderBatchArgs), ALLOC_FN, vp, ALLOC_FN, vp,
                                                ALLOC_FN, vp, vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), vp]
         L.dgs_render_batch_backward.argtypes = [C.POINTER(RenderBatchArgs), C.c_longlong, C.POINTER(C.c_longlong)] + \
-            [vp] * 11 + [ALLOC_FN, vp, vp]
+            [vp] * 10 + [ALLOC_FN, vp, vp]
         L.dgs_raster_export_state.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong] + [vp] * 13
         L.dgs_dit_workspace_bytes.restype = C.c_size_t
         L.dgs_dit_workspace_bytes.argtypes = [C.POINTER(DitWeights), C.c_int, C.c_int, C.c_int, C.c_int]
