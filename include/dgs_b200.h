@@ -210,11 +210,62 @@ typedef struct {
   float* opacity;            /* out [B,P,1]                                                           */
   float* img_aligned_xyz;    /* out [B,V,3,H,W] or NULL                                               */
   float* tokens_out;         /* optional debug out: final residual stream [B,N,width] fp32, or NULL   */
+  void* train_state;         /* NULL: inference.  Else a caller buffer of dgs_dit_train_state_bytes(): the forward
+                                keeps every activation the backward needs there (no recompute: 4 GB per sample at
+                                N=4098 -- the reference instead checkpoints each block, denoiser.py:348-354, and pays a
+                                second forward); it must stay untouched, together with `workspace`, until
+                                dgs_dit_backward has run.                                               */
 } dgs_dit_io;
 
 size_t dgs_dit_workspace_bytes(const dgs_dit_weights* w, int B, int V, int H, int W);
 int dgs_dit_forward(const dgs_dit_weights* w, const dgs_dit_io* io, void* workspace, size_t workspace_bytes,
                     void* stream);
+
+/* ---- training: backward of dgs_dit_forward (what torch autograd derives for denoiser.py:306-416 in the reference) ----
+ * dgrad GEMMs read TRANSPOSED bf16 copies of the block weights (W^T, [in, out] row-major) so that every GEMM of the
+ * backward runs on the same K-major tcgen05 kernel as the forward; the caller refreshes them after each optimizer step
+ * (dgs_transpose_bf16).  Gradients are fp32, in the state_dict layout of the fp32 master parameters. */
+typedef struct {
+  const void* qkv_wT;   /* bf16 [L, w, 3w]   */
+  const void* proj_wT;  /* bf16 [L, w, w]    */
+  const void* fc1_wT;   /* bf16 [L, w, 4w]   */
+  const void* fc2_wT;   /* bf16 [L, 4w, w]   */
+  const void* dec_wT;   /* bf16 [w, patch*patch*14]  (image_token_decoder.linear.weight^T)             */
+  const float* ups_w;   /* fp32 [14, w]      (upsampler.linear.weight, master copy)                    */
+} dgs_dit_weights_t;
+
+typedef struct {  /* all fp32, OVERWRITTEN by dgs_dit_backward */
+  float* tokenizer_w;  /* [w, patch*patch*9] */
+  float* pos_embed;    /* [n_gaussians, w]   */
+  float* in_ln_w;      /* [w]                */
+  float* t0_w; float* t0_b; float* t2_w; float* t2_b;
+  /* per-block tensors: the pointer addresses block 0; block l lives layer_stride floats further.  This is the layout
+     of a flat gradient arena in module.parameters() order (dgs_b200/dist.py GradArena: one contiguous bucket per
+     block, all-reduced in reverse order as the backward finishes them); a stacked [L, ...] layout is not expressible */
+  long long layer_stride;
+  float* qkv_w; float* qkv_b; float* proj_w; float* proj_b; float* fc1_w; float* fc1_b; float* fc2_w; float* fc2_b;
+  float* adaln_w; float* adaln_b;          /* block 0: [6w, w], [6w] */
+  float* ups_ln_w; float* ups_w;           /* [w], [14, w]               */
+  float* ups_adaln_w; float* ups_adaln_b;  /* [2w, w], [2w]              */
+  float* dec_ln_w; float* dec_w;           /* [w], [patch*patch*14, w]   */
+  float* dec_adaln_w; float* dec_adaln_b;  /* [2w, w], [2w]              */
+} dgs_dit_grads;
+
+typedef struct {  /* gradients w.r.t. the outputs of dgs_dit_forward (what dgs_render_batch_backward returns) */
+  const float* d_xyz; const float* d_features; const float* d_scaling; const float* d_rotation; const float* d_opacity;
+} dgs_dit_out_grads;
+
+size_t dgs_dit_train_state_bytes(const dgs_dit_weights* w, int B, int V, int H, int W);
+/* io / workspace / io->train_state: exactly what the matching dgs_dit_forward call was given. */
+int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, const dgs_dit_io* io,
+                     const dgs_dit_out_grads* dout, const dgs_dit_grads* grads, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* out[c, m] = bf16(in[m, c]) for in [M, C] (fp32 if in_is_f32 else bf16), out [C, round_up(M, 64)] zero padded;
+ * colsum (optional, fp32 [C]) += column sums.  Used for the transposed weight copies and inside the backward. */
+int dgs_transpose_bf16(const void* in, int in_is_f32, int M, int C, void* out, float* colsum, void* stream);
+/* fused AdamW on fp32 master parameters (torch.optim.AdamW semantics; diffusionGS_rel.yaml:57-62), step >= 1 */
+int dgs_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
 /* Building blocks, exported for the unit parity tests (same kernels dgs_dit_forward launches).
  * epi: 0 = bias -> bf16, 1 = bias + GELU(tanh) -> bf16, 2 = out(fp32) += gate[row / rows_per_sample] * (acc + bias),
@@ -223,6 +274,23 @@ int dgs_gemm_bf16(const void* A, const void* W, const float* bias, const float* 
                   int K, int epi, int ldc, int gate_stride, int rows_per_sample, void* stream);
 /* qkv [B,N,3,heads,64] bf16 -> out [B,N,heads*64] bf16 = softmax(q k^T / 8) v */
 int dgs_attention_fwd(const void* qkv, void* out, int B, int N, int heads, void* stream);
+/* training pair: the forward also writes lse2 [B, heads, round_up(N,128)] fp32; the backward turns (qkv, out, lse2,
+ * dout [B,N,heads*64] bf16) into dqkv [B,N,3,heads,64] bf16; dsum = scratch of the lse2 size. */
+int dgs_attention_fwd_train(const void* qkv, void* out, float* lse2, int B, int N, int heads, void* stream);
+int dgs_attention_bwd(const void* qkv, const void* out, const void* dout, float* lse2, float* dsum, void* dqkv, int B,
+                      int N, int heads, void* stream);
+/* extended GEMM entry (training epilogues): epi 4 = out(bf16) = acc * gelu'(aux);  aux (bf16 [M,ldc]): epi 1/2 also
+ * store acc + bias there;  resid: residual source of epi 2 (NULL = in place);  lda/ldb: operand row strides (0 = K) */
+int dgs_gemm_bf16_ex(const void* A, const void* W, const float* bias, const float* gate, void* out, void* aux,
+                     const float* resid, int M, int N, int K, int lda, int ldb, int epi, int ldc, int gate_stride,
+                     int rows_per_sample, void* stream);
+/* backward of dgs_ln_modulate: dx (+)= ..., dshift/dscale [B, mod_stride] += ..., dln_w += ... (NULL where absent) */
+int dgs_ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* ln_w, const float* scale,
+                        int mod_stride, int B, int rows, int width, float eps, float* dx, int accumulate, float* dshift,
+                        float* dscale, float* dln_w, void* stream);
+/* backward of x_out = x_in + gate[b] * y: dy (bf16 [M,C]), dyT (bf16 [C, round_up(M,64)]), dgate += , dbias += */
+int dgs_gate_bwd(const float* dx, const void* y, const float* gate, int gate_stride, int rows_per_sample, int M, int C,
+                 void* dy, void* dyT, float* dgate, float* dbias, void* stream);
 /* h = (LN(x; eps) [* ln_w]) * (1 + scale[b]) + shift[b] -> bf16 ; x fp32 [B, rows, width] */
 int dgs_ln_modulate(const float* x, const float* ln_w, const float* shift, const float* scale, int mod_stride,
                     void* h, int B, int rows, int width, float eps, void* stream);

@@ -1,0 +1,496 @@
+// attention_bwd_sm100.cu -- backward of the non-causal multi-head attention on tcgen05 (sm_100a), head_dim 64.
+//
+// Backward of  O = softmax(Q K^T / 8) V  (timm Attention.forward -> F.scaled_dot_product_attention, instantiated at
+// utils_transformer.py:254-256; the reference differentiates it through torch autograd / the SDPA backward).
+// With P = exp2(S * c - lse2) (c = log2(e)/8, lse2 saved by the forward), Dsum = rowsum(dO * O):
+//     dV = P^T dO          dP = dO V^T          dS = P * (dP - Dsum) / 8          dQ = dS K          dK = dS^T Q
+// Two kernels, no atomics, every operand read straight from the [B, N, 3, H, 64] qkv tensor / the [B, N, H*64] dO
+// tensor through 3-D TMA maps and written straight into the [B, N, 3, H, 64] dqkv tensor:
+//   attn_bwd_dq_kernel   one CTA per (128 queries, head, sample), loops over 64-key blocks:
+//                        S = Q K_j^T, dP = dO V_j^T (TMEM) -> dS_j (bf16, smem) -> dQ += dS_j K_j (TMEM accumulator;
+//                        K_j consumed MN-major from the same smem tile that fed S)
+//   attn_bwd_dkv_kernel  one CTA per (128 keys, head, sample), loops over 64-query blocks, works on the TRANSPOSED
+//                        scores so that the key is the TMEM lane / the thread:  S^T = K Q_i^T, dP^T = V dO_i^T ->
+//                        P^T, dS^T (bf16, smem, K-major A operands) -> dV += P^T dO_i, dK += dS^T Q_i (dO_i, Q_i
+//                        consumed MN-major from the tiles that fed S^T / dP^T)
+// Both: 192 threads (TMA warp, MMA warp, 4 softmax warps), 2 CTAs per SM, 256 TMEM columns.  No row reductions are
+// needed in the backward (lse2 and Dsum are inputs), so a thread only does exp2 + 3 FMA-pipe ops + packing per element.
+#include "dgs_internal.h"
+#include "dit_kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace dgs {
+
+using namespace ptx;
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+namespace {
+
+constexpr int AB_THREADS = 192, AB_HD = 64;
+constexpr int AB_T128 = 128 * AB_HD * 2;  // [128 x 64] bf16 tile, 16 KB
+constexpr int AB_T64 = 64 * AB_HD * 2;    // [64 x 64] bf16 tile, 8 KB
+constexpr int AB_STAGES = 2;
+constexpr float AB_SL2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+constexpr float AB_SCALE = 0.125f;
+
+__device__ __forceinline__ uint32_t ab_pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Dsum[b, h, n] = sum_d O[b, n, h, d] * dO[b, n, h, d];  pads n in [N, Np): lse2 = +inf (=> P = 0), Dsum = 0
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
+                                     float* __restrict__ lse2, float* __restrict__ dsum, int N, int Np, int H) {
+  const int n = blockIdx.x, b = blockIdx.y, t = threadIdx.x;  // blockDim.x = H * 16
+  const int D = H * AB_HD;
+  if (n >= N) {
+    if (t < H) {
+      lse2[((size_t)b * H + t) * Np + n] = INFINITY;
+      dsum[((size_t)b * H + t) * Np + n] = 0.f;
+    }
+    return;
+  }
+  float s = 0.f;
+  if (t < H * 16) {  // (blockDim.x is padded to a full warp when H == 1)
+    const size_t off = ((size_t)b * N + n) * D + (size_t)t * 4;
+    const uint2 a = *reinterpret_cast<const uint2*>(O + off);
+    const uint2 g = *reinterpret_cast<const uint2*>(dO + off);
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const float2 x = __bfloat1622float2(a2[i]), y = __bfloat1622float2(g2[i]);
+      s = fmaf(x.x, y.x, s);
+      s = fmaf(x.y, y.y, s);
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((t & 15) == 0 && t < H * 16) dsum[((size_t)b * H + (t >> 4)) * Np + n] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dQ
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DQ_SMEM = 2 * AB_T128 /*Q, dO*/ + 2 * AB_T128 /*dS x2*/ + 2 * AB_STAGES * AB_T64 /*K, V*/ + 1024 + 256;
+constexpr uint32_t DQ_TM_S = 0, DQ_TM_DP = 64, DQ_TM_DQ = 128, DQ_TMEM_COLS = 256;
+
+__global__ void __launch_bounds__(AB_THREADS, 2)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_kv64,
+                   const __grid_constant__ CUtensorMap tm_do128, const float* __restrict__ lse2,
+                   const float* __restrict__ dsum, __nv_bfloat16* __restrict__ dqkv, int N, int Np, int H) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + AB_T128;
+  uint8_t* sdS = sdO + AB_T128;  // 2 buffers
+  uint8_t* sK = sdS + 2 * AB_T128;
+  uint8_t* sV = sK + AB_STAGES * AB_T64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AB_STAGES * AB_T64);
+  uint64_t* q_full = bars;                    // Q + dO landed
+  uint64_t* kv_full = bars + 1;               // [AB_STAGES]
+  uint64_t* kv_empty = kv_full + AB_STAGES;   // [AB_STAGES]
+  uint64_t* sdp_full = kv_empty + AB_STAGES;  // S and dP of block j in TMEM
+  uint64_t* ds_full = sdp_full + 1;           // [2] dS_j written (and S/dP read out of TMEM)
+  uint64_t* dq_done = ds_full + 2;            // [2] dQ MMA of block j retired (dS buffer free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int n_blocks = (N + 63) / 64;
+  const int D = H * AB_HD;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_q128);
+    prefetch_tmap(&tm_kv64);
+    prefetch_tmap(&tm_do128);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < AB_STAGES; s++) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
+    mbar_init(sdp_full, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(ds_full + s, 128); mbar_init(dq_done + s, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, DQ_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * AB_T128);
+      tma_load_3d(sQ, &tm_q128, q_full, h * AB_HD, q0, b);
+      tma_load_3d(sdO, &tm_do128, q_full, h * AB_HD, q0, b);
+      for (int j = 0; j < n_blocks; j++) {
+        const int s = j % AB_STAGES;
+        mbar_wait(kv_empty + s, ((uint32_t)(j / AB_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(kv_full + s, 2 * AB_T64);
+        tma_load_3d(sK + s * AB_T64, &tm_kv64, kv_full + s, D + h * AB_HD, j * 64, b);
+        tma_load_3d(sV + s * AB_T64, &tm_kv64, kv_full + s, 2 * D + h * AB_HD, j * 64, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_kk = make_idesc_bf16(128, 64, false, false);  // A K-major x B K-major
+      constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 64, false, true);  // A K-major x B MN-major
+      const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t dodesc = make_smem_desc_sw128(smem_u32(sdO), 16, 1024);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_blocks; j++) {
+        const int s = j % AB_STAGES;
+        mbar_wait(kv_full + s, (uint32_t)(j / AB_STAGES) & 1);
+        tc_fence_after();
+        // S and dP are single-buffered: block j-1's softmax has read them (ds_full(j-1) was waited below)
+        const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s * AB_T64), 16, 1024);
+        const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + s * AB_T64), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          umma_bf16(tmem_base + DQ_TM_S, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          umma_bf16(tmem_base + DQ_TM_DP, dodesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+        umma_commit(sdp_full);
+        mbar_wait(ds_full + (j & 1), (uint32_t)(j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t dsbase = smem_u32(sdS + (j & 1) * AB_T128);
+        const uint32_t kbase = smem_u32(sK + s * AB_T64);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          // A = dS_j: K-major [128 q x 64 keys], 16 keys = 32 B inside the swizzled row;
+          // B = K_j: MN-major ([key][64 dims] rows of 128 B), 16 keys = 2 groups of 8 rows = 2048 B
+          const uint64_t adesc = make_smem_desc_sw128(dsbase + (uint32_t)(k * 32), 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(kbase + (uint32_t)(k * 2048), AB_T64, 1024);
+          umma_bf16(tmem_base + DQ_TM_DQ, adesc, bdesc, idesc_kmn, (j | k) ? 1u : 0u);
+        }
+        umma_commit(dq_done + (j & 1));
+        umma_commit(kv_empty + s);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const size_t stat = ((size_t)b * H + h) * Np + q0 + row;  // q0 + row < Np always
+    const float lse = lse2[stat];                             // +inf on pad rows -> P = 0
+    const float dsc = dsum[stat] * AB_SCALE;
+    for (int j = 0; j < n_blocks; j++) {
+      const int buf = j & 1;
+      mbar_wait(sdp_full, (uint32_t)j & 1);
+      tc_fence_after();
+      if (j >= 2) mbar_wait(dq_done + buf, (uint32_t)((j - 2) >> 1) & 1);  // dS buffer consumed
+      const int kv_valid = N - j * 64;
+      uint8_t* ds_row = sdS + buf * AB_T128 + row * 128;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        uint32_t rs[32], rp[32];
+        tmem_ld_32x32(t_lane + DQ_TM_S + (uint32_t)(half * 32), rs);
+        tmem_ld_32x32(t_lane + DQ_TM_DP + (uint32_t)(half * 32), rp);
+        tmem_ld_wait();
+        float ds[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          float p = ex2_approx(fmaf(__uint_as_float(rs[i]), AB_SL2, -lse));
+          if (half * 32 + i >= kv_valid) p = 0.f;  // zero-filled tail keys (last block only)
+          ds[i] = p * fmaf(__uint_as_float(rp[i]), AB_SCALE, -dsc);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          uint4 pk;
+          pk.x = ab_pack2(ds[8 * q], ds[8 * q + 1]); pk.y = ab_pack2(ds[8 * q + 2], ds[8 * q + 3]);
+          pk.z = ab_pack2(ds[8 * q + 4], ds[8 * q + 5]); pk.w = ab_pack2(ds[8 * q + 6], ds[8 * q + 7]);
+          *reinterpret_cast<uint4*>(ds_row + (((half * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(ds_full + buf);
+    }
+    const int last = n_blocks - 1;
+    mbar_wait(dq_done + (last & 1), (uint32_t)(last >> 1) & 1);
+    tc_fence_after();
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32(t_lane + DQ_TM_DQ, r0);
+    tmem_ld_32x32(t_lane + DQ_TM_DQ + 32u, r1);
+    tmem_ld_wait();
+    if (q0 + row < N) {
+      __nv_bfloat16* dst = dqkv + ((size_t)b * N + q0 + row) * 3 * D + h * AB_HD;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 pk;
+        pk.x = ab_pack2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+        pk.y = ab_pack2(__uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3]));
+        pk.z = ab_pack2(__uint_as_float(r0[i + 4]), __uint_as_float(r0[i + 5]));
+        pk.w = ab_pack2(__uint_as_float(r0[i + 6]), __uint_as_float(r0[i + 7]));
+        *reinterpret_cast<uint4*>(dst + i) = pk;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 pk;
+        pk.x = ab_pack2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
+        pk.y = ab_pack2(__uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3]));
+        pk.z = ab_pack2(__uint_as_float(r1[i + 4]), __uint_as_float(r1[i + 5]));
+        pk.w = ab_pack2(__uint_as_float(r1[i + 6]), __uint_as_float(r1[i + 7]));
+        *reinterpret_cast<uint4*>(dst + 32 + i) = pk;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, DQ_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dK, dV
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DKV_SMEM = 2 * AB_T128 /*K, V*/ + 2 * AB_T128 /*P^T, dS^T*/ + 2 * AB_STAGES * AB_T64 /*Q, dO*/ +
+                         2 * 128 * 4 /*lse2 | Dsum of a query block, x2*/ + 1024 + 256;
+constexpr uint32_t DKV_TM_ST = 0, DKV_TM_DPT = 64, DKV_TM_DV = 128, DKV_TM_DK = 192, DKV_TMEM_COLS = 256;
+
+__global__ void __launch_bounds__(AB_THREADS, 2)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_constant__ CUtensorMap tm_q64,
+                    const __grid_constant__ CUtensorMap tm_do64, const float* __restrict__ lse2,
+                    const float* __restrict__ dsum, __nv_bfloat16* __restrict__ dqkv, int N, int Np, int H) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + AB_T128;
+  uint8_t* sPt = sV + AB_T128;
+  uint8_t* sdSt = sPt + AB_T128;
+  uint8_t* sQ = sdSt + AB_T128;
+  uint8_t* sdO = sQ + AB_STAGES * AB_T64;
+  float* s_stat = reinterpret_cast<float*>(sdO + AB_STAGES * AB_T64);  // [2][128]: lse2[64] | Dsum/8 [64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 2 * 128);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;              // [AB_STAGES]
+  uint64_t* q_empty = q_full + AB_STAGES;   // [AB_STAGES]
+  uint64_t* stp_full = q_empty + AB_STAGES; // S^T and dP^T of block i in TMEM
+  uint64_t* pt_full = stp_full + 1;         // P^T, dS^T written (and S^T/dP^T read out of TMEM)
+  uint64_t* acc_done = pt_full + 1;         // dV/dK MMAs of block i retired (P^T/dS^T buffers free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int n_blocks = (N + 63) / 64;  // query blocks
+  const int D = H * AB_HD;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_kv128);
+    prefetch_tmap(&tm_q64);
+    prefetch_tmap(&tm_do64);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < AB_STAGES; s++) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, 1); }
+    mbar_init(stp_full, 1);
+    mbar_init(pt_full, 128);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, DKV_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * AB_T128);
+      tma_load_3d(sK, &tm_kv128, kv_full, D + h * AB_HD, k0, b);
+      tma_load_3d(sV, &tm_kv128, kv_full, 2 * D + h * AB_HD, k0, b);
+      for (int i = 0; i < n_blocks; i++) {
+        const int s = i % AB_STAGES;
+        mbar_wait(q_empty + s, ((uint32_t)(i / AB_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full + s, 2 * AB_T64);
+        tma_load_3d(sQ + s * AB_T64, &tm_q64, q_full + s, h * AB_HD, i * 64, b);
+        tma_load_3d(sdO + s * AB_T64, &tm_do64, q_full + s, h * AB_HD, i * 64, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_kk = make_idesc_bf16(128, 64, false, false);
+      constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 64, false, true);
+      const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+      const uint32_t ptbase = smem_u32(sPt), dstbase = smem_u32(sdSt);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < n_blocks; i++) {
+        const int s = i % AB_STAGES;
+        mbar_wait(q_full + s, (uint32_t)(i / AB_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t qbase = smem_u32(sQ + s * AB_T64), dobase = smem_u32(sdO + s * AB_T64);
+        const uint64_t qdesc = make_smem_desc_sw128(qbase, 16, 1024);
+        const uint64_t dodesc = make_smem_desc_sw128(dobase, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; k++)  // S^T = K Q_i^T : [128 keys x 64 queries]
+          umma_bf16(tmem_base + DKV_TM_ST, kdesc + (uint64_t)(2 * k), qdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; k++)  // dP^T = V dO_i^T
+          umma_bf16(tmem_base + DKV_TM_DPT, vdesc + (uint64_t)(2 * k), dodesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+        umma_commit(stp_full);
+        mbar_wait(pt_full, (uint32_t)i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {  // reduction over the 64 queries of the block, 16 per instruction
+          const uint64_t pdesc = make_smem_desc_sw128(ptbase + (uint32_t)(k * 32), 16, 1024);
+          const uint64_t dsdesc = make_smem_desc_sw128(dstbase + (uint32_t)(k * 32), 16, 1024);
+          const uint64_t dob = make_smem_desc_sw128(dobase + (uint32_t)(k * 2048), AB_T64, 1024);  // MN-major
+          const uint64_t qb = make_smem_desc_sw128(qbase + (uint32_t)(k * 2048), AB_T64, 1024);    // MN-major
+          umma_bf16(tmem_base + DKV_TM_DV, pdesc, dob, idesc_kmn, (i | k) ? 1u : 0u);   // dV += P^T dO_i
+          umma_bf16(tmem_base + DKV_TM_DK, dsdesc, qb, idesc_kmn, (i | k) ? 1u : 0u);   // dK += dS^T Q_i
+        }
+        umma_commit(acc_done);
+        umma_commit(q_empty + s);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;  // key row of this thread
+    const bool key_valid = k0 + row < N;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const size_t stat_base = ((size_t)b * H + h) * Np;
+    // per query block the 128 softmax threads stage lse2[64] | Dsum[64]/8 in smem (prefetched one block ahead)
+    const float* stat_src = (row < 64 ? lse2 : dsum) + stat_base + (row & 63);
+    const float stat_mul = row < 64 ? 1.0f : AB_SCALE;
+    float pre = stat_src[0] * stat_mul;  // block 0 (Np >= 128: in bounds)
+    for (int i = 0; i < n_blocks; i++) {
+      float* st = s_stat + (i & 1) * 128;
+      st[row] = pre;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (i + 1 < n_blocks) pre = stat_src[(i + 1) * 64] * stat_mul;  // (i+1)*64 + 63 < Np
+      mbar_wait(stp_full, (uint32_t)i & 1);
+      tc_fence_after();
+      if (i >= 1) mbar_wait(acc_done, (uint32_t)(i - 1) & 1);  // P^T / dS^T buffers consumed
+      uint8_t* pt_row = sPt + row * 128;
+      uint8_t* dst_row = sdSt + row * 128;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        uint32_t rs[32], rp[32];
+        tmem_ld_32x32(t_lane + DKV_TM_ST + (uint32_t)(half * 32), rs);
+        tmem_ld_32x32(t_lane + DKV_TM_DPT + (uint32_t)(half * 32), rp);
+        tmem_ld_wait();
+        float p[32], ds[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(st + half * 32 + c);        // smem broadcast
+          const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + half * 32 + c);
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            float pe = ex2_approx(fmaf(__uint_as_float(rs[c + e]), AB_SL2, -lv[e]));  // pad queries: lse2 = +inf -> 0
+            if (!key_valid) pe = 0.f;
+            p[c + e] = pe;
+            ds[c + e] = pe * fmaf(__uint_as_float(rp[c + e]), AB_SCALE, -dv[e]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          uint4 pk, dk;
+          pk.x = ab_pack2(p[8 * q], p[8 * q + 1]); pk.y = ab_pack2(p[8 * q + 2], p[8 * q + 3]);
+          pk.z = ab_pack2(p[8 * q + 4], p[8 * q + 5]); pk.w = ab_pack2(p[8 * q + 6], p[8 * q + 7]);
+          dk.x = ab_pack2(ds[8 * q], ds[8 * q + 1]); dk.y = ab_pack2(ds[8 * q + 2], ds[8 * q + 3]);
+          dk.z = ab_pack2(ds[8 * q + 4], ds[8 * q + 5]); dk.w = ab_pack2(ds[8 * q + 6], ds[8 * q + 7]);
+          const int chunk = ((half * 4 + q) ^ (row & 7)) << 4;  // 128B swizzle
+          *reinterpret_cast<uint4*>(pt_row + chunk) = pk;
+          *reinterpret_cast<uint4*>(dst_row + chunk) = dk;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(pt_full);
+    }
+    mbar_wait(acc_done, (uint32_t)(n_blocks - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int which = 0; which < 2; which++) {  // 0: dK (qkv section 1), 1: dV (section 2)
+      uint32_t r0[32], r1[32];
+      const uint32_t col = which ? DKV_TM_DV : DKV_TM_DK;
+      tmem_ld_32x32(t_lane + col, r0);
+      tmem_ld_32x32(t_lane + col + 32u, r1);
+      tmem_ld_wait();
+      if (key_valid) {
+        __nv_bfloat16* dst = dqkv + ((size_t)b * N + k0 + row) * 3 * D + (size_t)(1 + which) * D + h * AB_HD;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk;
+          pk.x = ab_pack2(__uint_as_float(r0[i]), __uint_as_float(r0[i + 1]));
+          pk.y = ab_pack2(__uint_as_float(r0[i + 2]), __uint_as_float(r0[i + 3]));
+          pk.z = ab_pack2(__uint_as_float(r0[i + 4]), __uint_as_float(r0[i + 5]));
+          pk.w = ab_pack2(__uint_as_float(r0[i + 6]), __uint_as_float(r0[i + 7]));
+          *reinterpret_cast<uint4*>(dst + i) = pk;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk;
+          pk.x = ab_pack2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
+          pk.y = ab_pack2(__uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3]));
+          pk.z = ab_pack2(__uint_as_float(r1[i + 4]), __uint_as_float(r1[i + 5]));
+          pk.w = ab_pack2(__uint_as_float(r1[i + 6]), __uint_as_float(r1[i + 7]));
+          *reinterpret_cast<uint4*>(dst + 32 + i) = pk;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, DKV_TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+int attention_bwd(const void* qkv, const void* out, const void* dout, float* lse2, float* dsum, void* dqkv, int B, int N,
+                  int H, cudaStream_t st) {
+  DGS_REQUIRE(B > 0 && N > 0 && H > 0 && H <= 64, "attention_bwd: bad shape B=%d N=%d H=%d", B, N, H);
+  const int D = H * AB_HD, Np = attention_lse_stride(N);
+  CUtensorMap tm_qkv128, tm_qkv64, tm_do128, tm_do64;
+  {
+    uint64_t dims[3] = {(uint64_t)(3 * D), (uint64_t)N, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)(3 * D) * 2, (uint64_t)N * 3 * D * 2};
+    uint32_t b128[3] = {AB_HD, 128, 1}, b64[3] = {AB_HD, 64, 1};
+    int rc = make_tmap_bf16(&tm_qkv128, qkv, 3, dims, str, b128);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tm_qkv64, qkv, 3, dims, str, b64);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)D, (uint64_t)N, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)D * 2, (uint64_t)N * D * 2};
+    uint32_t b128[3] = {AB_HD, 128, 1}, b64[3] = {AB_HD, 64, 1};
+    int rc = make_tmap_bf16(&tm_do128, dout, 3, dims, str, b128);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tm_do64, dout, 3, dims, str, b64);
+    if (rc) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    configured = true;
+  }
+  attn_bwd_prep_kernel<<<dim3(Np, B), H * 16 < 32 ? 32 : H * 16, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse2, dsum,
+                                                       N, Np, H);
+  DGS_POST_LAUNCH();
+  dim3 grid(ceil_div(N, 128), H, B);
+  attn_bwd_dq_kernel<<<grid, AB_THREADS, DQ_SMEM, st>>>(tm_qkv128, tm_qkv64, tm_do128, lse2, dsum,
+                                                        (__nv_bfloat16*)dqkv, N, Np, H);
+  DGS_POST_LAUNCH();
+  attn_bwd_dkv_kernel<<<grid, AB_THREADS, DKV_SMEM, st>>>(tm_qkv128, tm_qkv64, tm_do64, lse2, dsum,
+                                                          (__nv_bfloat16*)dqkv, N, Np, H);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+}  // namespace dgs

@@ -47,7 +47,7 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 template <int ATT_POLY_OF_8>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                     __nv_bfloat16* __restrict__ out, int N, int H) {
+                     __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int Np, int N, int H) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -241,6 +241,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const uint32_t lsum = tmem_ld_32x1(t_l);
       tmem_ld_wait();
       if (q0 + row < N) {
+        // training: log2-domain log-sum-exp of the scaled scores (the stale max is exact here: l was accumulated
+        // against the same m_run), consumed by attention_bwd_sm100.cu
+        if (lse2) lse2[((size_t)b * H + h) * Np + q0 + row] = fmaf(m_run, sl2, log2f(__uint_as_float(lsum)));
         const float inv = 1.0f / __uint_as_float(lsum);
         __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * D + h * ATT_HD;
 #pragma unroll
@@ -272,9 +275,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   }
 }
 
-int attention_fwd(const void* qkv, void* out, int B, int N, int H, cudaStream_t st) {
+int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st) {
   DGS_REQUIRE(B > 0 && N > 0 && H > 0, "attention: bad shape B=%d N=%d H=%d", B, N, H);
   const int D = H * ATT_HD;
+  const int Np = attention_lse_stride(N);
   CUtensorMap tm_q, tm_kv;
   uint64_t dims[3] = {(uint64_t)(3 * D), (uint64_t)N, (uint64_t)B};
   uint64_t str[2] = {(uint64_t)(3 * D) * 2, (uint64_t)N * 3 * D * 2};
@@ -293,9 +297,9 @@ int attention_fwd(const void* qkv, void* out, int B, int N, int H, cudaStream_t 
   }
   dim3 grid(ceil_div(N, ATT_BM), H, B);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (poly >= 4) attention_fwd_kernel<4><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, N, H);
-  else if (poly >= 2) attention_fwd_kernel<2><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, N, H);
-  else attention_fwd_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, N, H);
+  if (poly >= 4) attention_fwd_kernel<4><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, lse2, Np, N, H);
+  else if (poly >= 2) attention_fwd_kernel<2><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, lse2, Np, N, H);
+  else attention_fwd_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, lse2, Np, N, H);
   DGS_POST_LAUNCH();
   return DGS_OK;
 }

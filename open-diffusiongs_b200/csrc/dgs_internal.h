@@ -43,7 +43,8 @@ enum ProfFamily {
   PROF_RASTER_PROJECT = 0, PROF_RASTER_SCAN, PROF_RASTER_EMIT, PROF_RASTER_SORT, PROF_RASTER_RANGES,
   PROF_RASTER_BLEND_FWD, PROF_RASTER_BLEND_BWD, PROF_RASTER_GEOM_BWD,
   PROF_DIT_INPUT, PROF_DIT_COND, PROF_DIT_LN, PROF_DIT_GEMM_QKV, PROF_DIT_ATTN, PROF_DIT_GEMM_PROJ,
-  PROF_DIT_GEMM_FC1, PROF_DIT_GEMM_FC2, PROF_DIT_HEADS, PROF_N
+  PROF_DIT_GEMM_FC1, PROF_DIT_GEMM_FC2, PROF_DIT_HEADS,
+  PROF_DIT_BWD_ELEM, PROF_DIT_BWD_WGRAD, PROF_DIT_BWD_DGRAD, PROF_DIT_BWD_ATTN, PROF_N
 };
 extern bool g_prof_on;
 void prof_begin(cudaStream_t st, int family);

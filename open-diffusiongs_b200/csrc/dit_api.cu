@@ -45,6 +45,72 @@ struct DitWorkspace {
   }
 };
 
+// Everything the backward needs from the forward (training mode), plus the backward's own scratch.  Per-layer tensors
+// are stacked along a leading L axis.  M = B*N rows, Mp = round_up(M, 64), Mt = B*T image-token rows.
+struct SkinnyBwdSeg { size_t row0; int rows; float* dW; float* db; };
+
+struct TrainState {
+  float* x_pre;             // [M, w]      assembled tokens before the input LayerNorm
+  float* x_all;             // [L+1][M, w] residual stream entering block l (x_all[L] = final)
+  float* x_mid;             // [L][M, w]   after the attention branch
+  __nv_bfloat16* h1;        // [L][M, w]   LN1+modulate output (A of qkv)
+  __nv_bfloat16* h2;        // [L][M, w]   LN2+modulate output (A of fc1)
+  __nv_bfloat16* qkv;       // [L][M, 3w]
+  __nv_bfloat16* attn;      // [L][M, w]
+  float* lse;               // [L][B, heads, Np]
+  __nv_bfloat16* proj_out;  // [L][M, w]   attention branch output before the gate
+  __nv_bfloat16* fc2_out;   // [L][M, w]   MLP branch output before the gate
+  __nv_bfloat16* u_pre;     // [L][M, 4w]  fc1 + bias (pre-GELU)
+  __nv_bfloat16* u;         // [L][M, 4w]  GELU output (A of fc2)
+  __nv_bfloat16* hdec;      // [Mt, 3w]    decoder-head operand (split-bf16)
+  // ---- backward scratch ----
+  float* dx;                // [M, w]      gradient of the residual stream
+  float* dx_pre;            // [M, w]
+  float* dmod;              // [B, mod_stride]
+  float* dsum;              // [B, heads, Np]
+  float* dcond;             // [3][B, w]   dsilu(c) / dtemb1 / pre1
+  float* d_gs_tok;          // [B*G, 14]
+  __nv_bfloat16* dyb;       // [M, w]      gated branch gradient / generic [M, w] bf16
+  __nv_bfloat16* dh;        // [M, w]
+  __nv_bfloat16* big0;      // [M, 4w]     du / dqkv / d_img_gs
+  __nv_bfloat16* bigT0;     // [4w, Mp]    transposed gradient operand
+  __nv_bfloat16* bigT1;     // [4w, Mp]    transposed activation operand
+  size_t bytes;
+  TrainState(void* base, const dgs_dit_weights* w, int B, int V, int H, int W) {
+    const size_t T = (size_t)V * (H / w->patch) * (W / w->patch), N = T + w->n_gaussians, D = w->width, L = w->layers;
+    const size_t M = (size_t)B * N, Mp = (M + 63) / 64 * 64, U = w->mlp_hidden;
+    const size_t Np = (size_t)attention_lse_stride((int)N);
+    const size_t mod_stride = L * 6 * D + 4 * D;
+    const size_t wide = U > 3 * D ? U : 3 * D;
+    Carver c(base);
+    x_pre = c.take<float>(M * D);
+    x_all = c.take<float>((L + 1) * M * D);
+    x_mid = c.take<float>(L * M * D);
+    h1 = c.take<__nv_bfloat16>(L * M * D);
+    h2 = c.take<__nv_bfloat16>(L * M * D);
+    qkv = c.take<__nv_bfloat16>(L * M * 3 * D);
+    attn = c.take<__nv_bfloat16>(L * M * D);
+    lse = c.take<float>(L * B * w->heads * Np);
+    proj_out = c.take<__nv_bfloat16>(L * M * D);
+    fc2_out = c.take<__nv_bfloat16>(L * M * D);
+    u_pre = c.take<__nv_bfloat16>(L * M * U);
+    u = c.take<__nv_bfloat16>(L * M * U);
+    hdec = c.take<__nv_bfloat16>((size_t)B * T * 3 * D);
+    dx = c.take<float>(M * D);
+    dx_pre = c.take<float>(M * D);
+    dmod = c.take<float>((size_t)B * mod_stride);
+    dsum = c.take<float>((size_t)B * w->heads * Np);
+    dcond = c.take<float>((size_t)3 * B * D);
+    d_gs_tok = c.take<float>((size_t)B * w->n_gaussians * 14 + 16);
+    dyb = c.take<__nv_bfloat16>(M * D);
+    dh = c.take<__nv_bfloat16>(M * D);
+    big0 = c.take<__nv_bfloat16>(M * wide);
+    bigT0 = c.take<__nv_bfloat16>(wide * Mp);
+    bigT1 = c.take<__nv_bfloat16>(wide * Mp);
+    bytes = c.bytes();
+  }
+};
+
 int check_dit(const dgs_dit_weights* w, int B, int V, int H, int W) {
   DGS_REQUIRE(w != nullptr, "weights is NULL");
   DGS_REQUIRE(w->width == 1024 && w->heads * 64 == w->width, "unsupported width/heads %d/%d (1024/16 only)", w->width, w->heads);
@@ -82,8 +148,10 @@ int dgs_dit_forward(const dgs_dit_weights* w, const dgs_dit_io* io, void* worksp
   DitWorkspace ws(workspace, w, B, V, H, W);
   DGS_REQUIRE(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
   const int mod_stride = L * 6 * D + 4 * D;
-  const __nv_bfloat16* bf = nullptr;
-  (void)bf;
+  const bool train = io->train_state != nullptr;
+  TrainState ts(io->train_state, w, B, V, H, W);
+  const size_t MD = (size_t)B * N * D, MU = (size_t)B * N * w->mlp_hidden;
+  float* x0 = train ? ts.x_all : ws.x;  // residual stream entering block 0
 
   // ---- input stage: posed image -> tokens -> tokenizer GEMM -> [pos tokens | image tokens] -> LayerNorm(weight) ----
   if (g_prof_on) prof_begin(st, PROF_DIT_INPUT);
@@ -93,8 +161,9 @@ int dgs_dit_forward(const dgs_dit_weights* w, const dgs_dit_io* io, void* worksp
     ep.out = ws.tok; ep.ldc = D;
     DGS_TRY(gemm_bf16(ws.tokens, w->tokenizer_w, B * T, D, 3 * Kin, EPI_F32, ep, st));  // split-bf16: K = 3*576
   }
-  DGS_TRY(assemble_tokens(ws.tok, w->pos_embed, ws.x, B, G, T, D, st));
-  DGS_TRY(ln_weight_inplace(ws.x, w->in_ln_w, B * N, D, 1e-5f, st));  // nn.LayerNorm default eps (denoiser.py:234-236)
+  DGS_TRY(assemble_tokens(ws.tok, w->pos_embed, x0, B, G, T, D, st));
+  if (train) DGS_CUDA_OK(cudaMemcpyAsync(ts.x_pre, x0, MD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  DGS_TRY(ln_weight_inplace(x0, w->in_ln_w, B * N, D, 1e-5f, st));  // nn.LayerNorm default eps (denoiser.py:234-236)
   if (g_prof_on) { prof_end(st, PROF_DIT_INPUT); prof_begin(st, PROF_DIT_COND); }
 
   // ---- conditioning: timestep MLP, then the adaLN modulation of ALL blocks and both heads in one launch ----
@@ -107,62 +176,76 @@ int dgs_dit_forward(const dgs_dit_weights* w, const dgs_dit_io* io, void* worksp
   // ---- L x DiTBlock (utils_transformer.py:270-290) ----
   for (int l = 0; l < L; l++) {
     const float* m = ws.mod + (size_t)l * 6 * D;  // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
+    // inference: one set of buffers, residual stream updated in place; training: per-layer slices of the train state
+    float* x_in = train ? ts.x_all + (size_t)l * MD : ws.x;
+    float* x_mid = train ? ts.x_mid + (size_t)l * MD : ws.x;
+    float* x_out = train ? ts.x_all + (size_t)(l + 1) * MD : ws.x;
+    __nv_bfloat16* h1 = train ? ts.h1 + (size_t)l * MD : ws.h;
+    __nv_bfloat16* h2 = train ? ts.h2 + (size_t)l * MD : ws.h;
+    __nv_bfloat16* qkv = train ? ts.qkv + (size_t)l * 3 * MD : ws.qkv;
+    __nv_bfloat16* attn = train ? ts.attn + (size_t)l * MD : ws.attn;
+    __nv_bfloat16* u = train ? ts.u + (size_t)l * MU : ws.u;
+    float* lse = train ? ts.lse + (size_t)l * B * w->heads * attention_lse_stride(N) : nullptr;
     {
       ProfScope ps(st, PROF_DIT_LN);
-      DGS_TRY(ln_modulate(ws.x, nullptr, m, m + D, mod_stride, ws.h, B, N, 0, N, D, 1e-6f, 0, st));
+      DGS_TRY(ln_modulate(x_in, nullptr, m, m + D, mod_stride, h1, B, N, 0, N, D, 1e-6f, 0, st));
     }
     {
       ProfScope ps(st, PROF_DIT_GEMM_QKV);
       GemmEpilogue ep;
-      ep.out = ws.qkv; ep.ldc = 3 * D; ep.bias = w->qkv_b + (size_t)l * 3 * D;
-      DGS_TRY(gemm_bf16(ws.h, (const __nv_bfloat16*)w->qkv_w + (size_t)l * 3 * D * D, B * N, 3 * D, D, EPI_BIAS_BF16, ep, st));
+      ep.out = qkv; ep.ldc = 3 * D; ep.bias = w->qkv_b + (size_t)l * 3 * D;
+      DGS_TRY(gemm_bf16(h1, (const __nv_bfloat16*)w->qkv_w + (size_t)l * 3 * D * D, B * N, 3 * D, D, EPI_BIAS_BF16, ep, st));
     }
     {
       ProfScope ps(st, PROF_DIT_ATTN);
-      DGS_TRY(attention_fwd(ws.qkv, ws.attn, B, N, w->heads, st));
+      DGS_TRY(attention_fwd(qkv, attn, lse, B, N, w->heads, st));
     }
     {
       ProfScope ps(st, PROF_DIT_GEMM_PROJ);
       GemmEpilogue ep;
-      ep.out = ws.x; ep.ldc = D; ep.bias = w->proj_b + (size_t)l * D;
+      ep.out = x_mid; ep.ldc = D; ep.bias = w->proj_b + (size_t)l * D;
       ep.gate = m + 2 * D; ep.gate_stride = mod_stride; ep.rows_per_sample = N;
-      DGS_TRY(gemm_bf16(ws.attn, (const __nv_bfloat16*)w->proj_w + (size_t)l * D * D, B * N, D, D, EPI_GATE_RESID_F32, ep, st));
+      if (train) { ep.resid = x_in; ep.aux = ts.proj_out + (size_t)l * MD; }
+      DGS_TRY(gemm_bf16(attn, (const __nv_bfloat16*)w->proj_w + (size_t)l * D * D, B * N, D, D, EPI_GATE_RESID_F32, ep, st));
     }
     {
       ProfScope ps(st, PROF_DIT_LN);
-      DGS_TRY(ln_modulate(ws.x, nullptr, m + 3 * D, m + 4 * D, mod_stride, ws.h, B, N, 0, N, D, 1e-6f, 0, st));
+      DGS_TRY(ln_modulate(x_mid, nullptr, m + 3 * D, m + 4 * D, mod_stride, h2, B, N, 0, N, D, 1e-6f, 0, st));
     }
     {
       ProfScope ps(st, PROF_DIT_GEMM_FC1);
       GemmEpilogue ep;
-      ep.out = ws.u; ep.ldc = w->mlp_hidden; ep.bias = w->fc1_b + (size_t)l * w->mlp_hidden;
-      DGS_TRY(gemm_bf16(ws.h, (const __nv_bfloat16*)w->fc1_w + (size_t)l * w->mlp_hidden * D, B * N, w->mlp_hidden, D,
+      ep.out = u; ep.ldc = w->mlp_hidden; ep.bias = w->fc1_b + (size_t)l * w->mlp_hidden;
+      if (train) ep.aux = ts.u_pre + (size_t)l * MU;
+      DGS_TRY(gemm_bf16(h2, (const __nv_bfloat16*)w->fc1_w + (size_t)l * w->mlp_hidden * D, B * N, w->mlp_hidden, D,
                         EPI_BIAS_GELU_BF16, ep, st));
     }
     {
       ProfScope ps(st, PROF_DIT_GEMM_FC2);
       GemmEpilogue ep;
-      ep.out = ws.x; ep.ldc = D; ep.bias = w->fc2_b + (size_t)l * D;
+      ep.out = x_out; ep.ldc = D; ep.bias = w->fc2_b + (size_t)l * D;
       ep.gate = m + 5 * D; ep.gate_stride = mod_stride; ep.rows_per_sample = N;
-      DGS_TRY(gemm_bf16(ws.u, (const __nv_bfloat16*)w->fc2_w + (size_t)l * D * w->mlp_hidden, B * N, D, w->mlp_hidden,
+      if (train) { ep.resid = x_mid; ep.aux = ts.fc2_out + (size_t)l * MD; }
+      DGS_TRY(gemm_bf16(u, (const __nv_bfloat16*)w->fc2_w + (size_t)l * D * w->mlp_hidden, B * N, D, w->mlp_hidden,
                         EPI_GATE_RESID_F32, ep, st));
     }
   }
+  float* x_fin = train ? ts.x_all + (size_t)L * MD : ws.x;
   if (io->tokens_out)
-    DGS_CUDA_OK(cudaMemcpyAsync(io->tokens_out, ws.x, (size_t)B * N * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DGS_CUDA_OK(cudaMemcpyAsync(io->tokens_out, x_fin, (size_t)B * N * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
   // ---- heads (denoiser.py:76-164): LN(weight) + modulate + Linear ----
   ProfScope ps_heads(st, PROF_DIT_HEADS);
   const float* mu = ws.mod + (size_t)L * 6 * D;  // upsampler: shift | scale
   const float* md = mu + 2 * D;                  // image_token_decoder: shift | scale
   if (G > 0) {
-    DGS_TRY(ln_modulate(ws.x, w->ups_ln_w, mu, mu + D, mod_stride, ws.hg, B, N, 0, G, D, 1e-5f, 1, st));
+    DGS_TRY(ln_modulate(x_fin, w->ups_ln_w, mu, mu + D, mod_stride, ws.hg, B, N, 0, G, D, 1e-5f, 1, st));
     DGS_TRY(tiny_linear_bf16(ws.hg, (const __nv_bfloat16*)w->ups_w, ws.gs_tok, B * G, 14, 3 * D, st));
   }
   // the decoder head runs split-bf16 (K = 3*width) so the Gaussian parameters are fp32-accurate functions of the
   // residual stream; its A operand re-uses the (now free) MLP hidden buffer
-  __nv_bfloat16* hdec = ws.u;
-  DGS_TRY(ln_modulate(ws.x, w->dec_ln_w, md, md + D, mod_stride, hdec, B, N, G, T, D, 1e-5f, 1, st));
+  __nv_bfloat16* hdec = train ? ts.hdec : ws.u;
+  DGS_TRY(ln_modulate(x_fin, w->dec_ln_w, md, md + D, mod_stride, hdec, B, N, G, T, D, 1e-5f, 1, st));
   {
     GemmEpilogue ep;
     ep.out = ws.img_gs; ep.ldc = Ndec;
@@ -174,6 +257,244 @@ int dgs_dit_forward(const dgs_dit_weights* w, const dgs_dit_io* io, void* worksp
   DGS_TRY(gaussians_epilogue(ws.gs_tok, ws.img_gs, io->ray_o, io->ray_d, go, B, G, V, H, W, p, io->scene_depth,
                              io->range_near, io->range_far, st));
   return DGS_OK;
+}
+
+size_t dgs_dit_train_state_bytes(const dgs_dit_weights* w, int B, int V, int H, int W) {
+  if (check_dit(w, B, V, H, W)) return 0;
+  return TrainState(nullptr, w, B, V, H, W).bytes;
+}
+
+int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, const dgs_dit_io* io,
+                     const dgs_dit_out_grads* dout, const dgs_dit_grads* g, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  DGS_REQUIRE(io != nullptr && wT != nullptr && dout != nullptr && g != nullptr, "NULL argument");
+  DGS_TRY(check_dit(w, io->B, io->V, io->H, io->W));
+  DGS_REQUIRE(io->train_state, "dgs_dit_backward: io->train_state is NULL (the forward must run in training mode)");
+  DGS_REQUIRE(dout->d_xyz && dout->d_features && dout->d_scaling && dout->d_rotation && dout->d_opacity, "NULL output gradient");
+  DGS_REQUIRE(wT->qkv_wT && wT->proj_wT && wT->fc1_wT && wT->fc2_wT && wT->dec_wT && wT->ups_w, "NULL transposed weight");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = io->B, V = io->V, H = io->H, W = io->W, D = w->width, L = w->layers, G = w->n_gaussians, p = w->patch;
+  const int T = V * (H / p) * (W / p), N = T + G, Kin = p * p * 9, Ndec = p * p * 14, U = w->mlp_hidden;
+  const int M = B * N, Mp = (M + 63) / 64 * 64, Mt = B * T, Mtp = (Mt + 63) / 64 * 64;
+  DGS_REQUIRE(B <= 8, "dgs_dit_backward: per-call batch %d > 8 (split the batch)", B);
+  DGS_REQUIRE(N >= 64, "dgs_dit_backward: needs at least 64 tokens per sample");
+  DitWorkspace ws(workspace, w, B, V, H, W);
+  DGS_REQUIRE(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
+  TrainState ts(io->train_state, w, B, V, H, W);
+  const int mod_stride = L * 6 * D + 4 * D;
+  const size_t MD = (size_t)M * D, MU = (size_t)M * U;
+  const int Np = attention_lse_stride(N);
+
+  // gradients accumulated by atomics start from zero; GEMM-produced ones are overwritten
+  DGS_CUDA_OK(cudaMemsetAsync(ts.dmod, 0, (size_t)B * mod_stride * sizeof(float), st));
+  DGS_CUDA_OK(cudaMemsetAsync(ts.dcond, 0, (size_t)3 * B * D * sizeof(float), st));
+  const size_t LS = (size_t)g->layer_stride;
+  for (int l = 0; l < L; l++) {
+    DGS_CUDA_OK(cudaMemsetAsync(g->qkv_b + l * LS, 0, (size_t)3 * D * sizeof(float), st));
+    DGS_CUDA_OK(cudaMemsetAsync(g->proj_b + l * LS, 0, (size_t)D * sizeof(float), st));
+    DGS_CUDA_OK(cudaMemsetAsync(g->fc1_b + l * LS, 0, (size_t)U * sizeof(float), st));
+    DGS_CUDA_OK(cudaMemsetAsync(g->fc2_b + l * LS, 0, (size_t)D * sizeof(float), st));
+  }
+  DGS_CUDA_OK(cudaMemsetAsync(g->in_ln_w, 0, D * sizeof(float), st));
+  DGS_CUDA_OK(cudaMemsetAsync(g->ups_ln_w, 0, D * sizeof(float), st));
+  DGS_CUDA_OK(cudaMemsetAsync(g->dec_ln_w, 0, D * sizeof(float), st));
+
+  auto wgrad = [&](const __nv_bfloat16* dyT, const __nv_bfloat16* xT, float* dW, int n_out, int n_in, int kp) -> int {
+    GemmEpilogue ep;  // dW[n_out, n_in] = dY^T [n_out, kp] x (X^T [n_in, kp])^T   (K = padded row count, pads are zero)
+    ep.out = dW; ep.ldc = n_in;
+    return gemm_bf16(dyT, xT, n_out, n_in, kp, EPI_F32, ep, st);
+  };
+  auto dgrad = [&](const __nv_bfloat16* dy, const void* wt, __nv_bfloat16* dxo, int rows, int n_in, int n_out, int epi,
+                   void* aux) -> int {
+    GemmEpilogue ep;  // dX[rows, n_in] = dY [rows, n_out] x (W^T [n_in, n_out])^T
+    ep.out = dxo; ep.ldc = n_in; ep.aux = aux;
+    return gemm_bf16(dy, wt, rows, n_in, n_out, epi, ep, st);
+  };
+
+  const float* x_fin = ts.x_all + (size_t)L * MD;
+  const float* mu = ws.mod + (size_t)L * 6 * D;
+  const float* md = mu + 2 * D;
+  float* dmu = ts.dmod + (size_t)L * 6 * D;
+  float* dmd = dmu + 2 * D;
+  {  // ---- heads ----
+    ProfScope ps(st, PROF_DIT_BWD_ELEM);
+    __nv_bfloat16* d_img = ts.big0;  // [Mt, Ndec]
+    DGS_TRY(gaussians_epilogue_bwd(ws.gs_tok, ws.img_gs, io->ray_d, dout->d_xyz, dout->d_features, dout->d_scaling,
+                                   dout->d_rotation, dout->d_opacity, ts.d_gs_tok, d_img, B, G, V, H, W, p,
+                                   io->scene_depth, io->range_near, io->range_far, st));
+    // image_token_decoder: dh = d_img W, dW = d_img^T h
+    DGS_TRY(dgrad(d_img, wT->dec_wT, ts.dh, Mt, D, Ndec, EPI_BIAS_BF16, nullptr));
+    DGS_TRY(transpose_to_bf16(d_img, 0, Ndec, 1, Mt, 0, Mt, Ndec, ts.bigT0, nullptr, st));
+    DGS_TRY(transpose_to_bf16(ts.hdec, 0, 3 * D, 1, Mt, 0, Mt, D, ts.bigT1, nullptr, st));  // hi part of [hi|lo|hi]
+    DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->dec_w, Ndec, D, Mtp));
+    DGS_TRY(ln_modulate_bwd(x_fin, ts.dh, 0, w->dec_ln_w, md + D, mod_stride, B, N, G, T, D, 1e-5f, ts.dx, 0, dmd, dmd + D,
+                            g->dec_ln_w, st));
+    if (G > 0) {  // upsampler (the free Gaussian tokens, rows 0..G of every sample)
+      DGS_TRY(tiny_linear_bwd(ts.d_gs_tok, wT->ups_w, ws.hg, ts.dyb, g->ups_w, B * G, 14, D, st));
+      DGS_TRY(ln_modulate_bwd(x_fin, ts.dyb, 0, w->ups_ln_w, mu + D, mod_stride, B, N, 0, G, D, 1e-5f, ts.dx, 0, dmu, dmu + D,
+                              g->ups_ln_w, st));
+    }
+  }
+
+  // ---- L x DiTBlock, reversed ----
+  for (int l = L - 1; l >= 0; l--) {
+    const float* m = ws.mod + (size_t)l * 6 * D;
+    float* dm = ts.dmod + (size_t)l * 6 * D;
+    const float* x_in = ts.x_all + (size_t)l * MD;
+    const float* x_mid = ts.x_mid + (size_t)l * MD;
+    // -- MLP branch: x_out = x_mid + gate_mlp * (fc2(gelu(fc1(h2))) )
+    {
+      ProfScope ps(st, PROF_DIT_BWD_ELEM);
+      DGS_TRY(gate_bwd(ts.dx, ts.fc2_out + (size_t)l * MD, m + 5 * D, mod_stride, N, M, D, ts.dyb, ts.bigT0, dm + 5 * D,
+                       g->fc2_b + l * LS, st));
+      DGS_TRY(transpose_to_bf16(ts.u + (size_t)l * MU, 0, U, 1, M, 0, M, U, ts.bigT1, nullptr, st));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_WGRAD);
+      DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->fc2_w + l * LS, D, U, Mp));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_DGRAD);
+      DGS_TRY(dgrad(ts.dyb, (const __nv_bfloat16*)wT->fc2_wT + (size_t)l * D * U, ts.big0, M, U, D, EPI_DGELU_BF16,
+                    ts.u_pre + (size_t)l * MU));  // du_pre = (dy W2) * gelu'(u_pre)
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_ELEM);
+      DGS_TRY(transpose_to_bf16(ts.big0, 0, U, 1, M, 0, M, U, ts.bigT0, g->fc1_b + l * LS, st));
+      DGS_TRY(transpose_to_bf16(ts.h2 + (size_t)l * MD, 0, D, 1, M, 0, M, D, ts.bigT1, nullptr, st));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_WGRAD);
+      DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->fc1_w + l * LS, U, D, Mp));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_DGRAD);
+      DGS_TRY(dgrad(ts.big0, (const __nv_bfloat16*)wT->fc1_wT + (size_t)l * D * U, ts.dh, M, D, U, EPI_BIAS_BF16, nullptr));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_ELEM);
+      DGS_TRY(ln_modulate_bwd(x_mid, ts.dh, 0, nullptr, m + 4 * D, mod_stride, B, N, 0, N, D, 1e-6f, ts.dx, 1, dm + 3 * D,
+                              dm + 4 * D, nullptr, st));
+      // -- attention branch: x_mid = x_in + gate_msa * proj(attn(qkv(h1)))
+      DGS_TRY(gate_bwd(ts.dx, ts.proj_out + (size_t)l * MD, m + 2 * D, mod_stride, N, M, D, ts.dyb, ts.bigT0, dm + 2 * D,
+                       g->proj_b + l * LS, st));
+      DGS_TRY(transpose_to_bf16(ts.attn + (size_t)l * MD, 0, D, 1, M, 0, M, D, ts.bigT1, nullptr, st));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_WGRAD);
+      DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->proj_w + l * LS, D, D, Mp));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_DGRAD);
+      DGS_TRY(dgrad(ts.dyb, (const __nv_bfloat16*)wT->proj_wT + (size_t)l * D * D, ts.dh, M, D, D, EPI_BIAS_BF16, nullptr));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_ATTN);
+      DGS_TRY(attention_bwd(ts.qkv + (size_t)l * 3 * MD, ts.attn + (size_t)l * MD, ts.dh,
+                            ts.lse + (size_t)l * B * w->heads * Np, ts.dsum, ts.big0, B, N, w->heads, st));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_ELEM);
+      DGS_TRY(transpose_to_bf16(ts.big0, 0, 3 * D, 1, M, 0, M, 3 * D, ts.bigT0, g->qkv_b + l * LS, st));
+      DGS_TRY(transpose_to_bf16(ts.h1 + (size_t)l * MD, 0, D, 1, M, 0, M, D, ts.bigT1, nullptr, st));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_WGRAD);
+      DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->qkv_w + l * LS, 3 * D, D, Mp));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_DGRAD);
+      DGS_TRY(dgrad(ts.big0, (const __nv_bfloat16*)wT->qkv_wT + (size_t)l * 3 * D * D, ts.dh, M, D, 3 * D, EPI_BIAS_BF16, nullptr));
+    }
+    {
+      ProfScope ps(st, PROF_DIT_BWD_ELEM);
+      DGS_TRY(ln_modulate_bwd(x_in, ts.dh, 0, nullptr, m + D, mod_stride, B, N, 0, N, D, 1e-6f, ts.dx, 1, dm, dm + D, nullptr, st));
+    }
+  }
+
+  ProfScope ps_in(st, PROF_DIT_BWD_ELEM);
+  // ---- input stage: LayerNorm(weight) -> [pos tokens | tokenizer GEMM] ----
+  DGS_TRY(ln_modulate_bwd(ts.x_pre, ts.dx, 1, w->in_ln_w, nullptr, 0, B, N, 0, N, D, 1e-5f, ts.dx_pre, 0, nullptr, nullptr,
+                          g->in_ln_w, st));
+  DGS_TRY(pos_embed_bwd(ts.dx_pre, g->pos_embed, B, G, N, D, st));
+  DGS_TRY(transpose_to_bf16(ts.dx_pre, 1, D, B, N, G, T, D, ts.bigT0, nullptr, st));          // d tok^T [D, Mtp]
+  DGS_TRY(transpose_to_bf16(ws.tokens, 0, 3 * Kin, 1, Mt, 0, Mt, Kin, ts.bigT1, nullptr, st));  // hi part of the patches
+  DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->tokenizer_w, D, Kin, Mtp));
+
+  // ---- conditioning: adaLN modulation of all blocks + heads, then the timestep MLP ----
+  float* dsc = ts.dcond;                       // d silu(c), then dc
+  float* dt1 = ts.dcond + (size_t)B * D;       // d temb1, then d pre1
+  float* pre1 = ts.dcond + (size_t)2 * B * D;  // t0 pre-activation (recomputed)
+  {  // one launch per adaLN linear (L blocks + 2 heads): their gradient tensors are separate parameters
+    SkinnyBwdSeg seg;
+    for (int l = 0; l < L; l++) {
+      seg = {(size_t)l * 6 * D, 6 * D, g->adaln_w + l * LS, g->adaln_b + l * LS};
+      DGS_TRY(skinny_linear_bwd(ws.c, w->adaln_w + seg.row0 * D, ts.dmod + seg.row0, mod_stride, B, seg.rows, D, 1, seg.dW,
+                                seg.db, dsc, st));
+    }
+    seg = {(size_t)L * 6 * D, 2 * D, g->ups_adaln_w, g->ups_adaln_b};
+    DGS_TRY(skinny_linear_bwd(ws.c, w->adaln_w + seg.row0 * D, ts.dmod + seg.row0, mod_stride, B, seg.rows, D, 1, seg.dW,
+                              seg.db, dsc, st));
+    seg = {(size_t)L * 6 * D + 2 * D, 2 * D, g->dec_adaln_w, g->dec_adaln_b};
+    DGS_TRY(skinny_linear_bwd(ws.c, w->adaln_w + seg.row0 * D, ts.dmod + seg.row0, mod_stride, B, seg.rows, D, 1, seg.dW,
+                              seg.db, dsc, st));
+  }
+  DGS_TRY(silu_bwd_inplace(dsc, ws.c, B * D, st));
+  DGS_TRY(skinny_linear_bwd(ws.temb1, w->t2_w, dsc, D, B, D, D, 0, g->t2_w, g->t2_b, dt1, st));
+  DGS_TRY(skinny_linear(ws.temb0, w->t0_w, w->t0_b, pre1, B, D, 256, 0, 0, st));
+  DGS_TRY(silu_bwd_inplace(dt1, pre1, B * D, st));
+  DGS_TRY(skinny_linear_bwd(ws.temb0, w->t0_w, dt1, D, B, D, 256, 0, g->t0_w, g->t0_b, nullptr, st));
+  return DGS_OK;
+}
+
+int dgs_transpose_bf16(const void* in, int in_is_f32, int M, int C, void* out, float* colsum, void* stream) {
+  DGS_REQUIRE(in && out && M > 0, "NULL pointer / bad shape");
+  return transpose_to_bf16(in, in_is_f32, C, 1, M, 0, M, C, (__nv_bfloat16*)out, colsum, (cudaStream_t)stream);
+}
+
+int dgs_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  DGS_REQUIRE(param && grad && exp_avg && exp_avg_sq && step >= 1, "bad AdamW arguments");
+  return adamw_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                    (cudaStream_t)stream);
+}
+
+int dgs_attention_fwd_train(const void* qkv, void* out, float* lse2, int B, int N, int heads, void* stream) {
+  DGS_REQUIRE(qkv && out && lse2, "NULL pointer");
+  return attention_fwd(qkv, out, lse2, B, N, heads, (cudaStream_t)stream);
+}
+
+int dgs_attention_bwd(const void* qkv, const void* out, const void* dout, float* lse2, float* dsum, void* dqkv, int B,
+                      int N, int heads, void* stream) {
+  DGS_REQUIRE(qkv && out && dout && lse2 && dsum && dqkv, "NULL pointer");
+  return attention_bwd(qkv, out, dout, lse2, dsum, dqkv, B, N, heads, (cudaStream_t)stream);
+}
+
+int dgs_gemm_bf16_ex(const void* A, const void* Wt, const float* bias, const float* gate, void* out, void* aux,
+                     const float* resid, int M, int N, int K, int lda, int ldb, int epi, int ldc, int gate_stride,
+                     int rows_per_sample, void* stream) {
+  DGS_REQUIRE(A && Wt && out, "NULL pointer");
+  DGS_REQUIRE(epi != EPI_GATE_RESID_F32 || (gate && rows_per_sample > 0), "gate epilogue needs gate and rows_per_sample");
+  GemmEpilogue ep;
+  ep.out = out; ep.ldc = ldc; ep.bias = bias; ep.gate = gate; ep.gate_stride = gate_stride;
+  ep.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
+  ep.aux = aux; ep.resid = resid; ep.lda = lda; ep.ldb = ldb;
+  return gemm_bf16(A, Wt, M, N, K, epi, ep, (cudaStream_t)stream);
+}
+
+int dgs_ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* ln_w, const float* scale,
+                        int mod_stride, int B, int rows, int width, float eps, float* dx, int accumulate, float* dshift,
+                        float* dscale, float* dln_w, void* stream) {
+  DGS_REQUIRE(x && dh && dx, "NULL pointer");
+  return ln_modulate_bwd(x, dh, dh_is_f32, ln_w, scale, mod_stride, B, rows, 0, rows, width, eps, dx, accumulate, dshift,
+                         dscale, dln_w, (cudaStream_t)stream);
+}
+
+int dgs_gate_bwd(const float* dx, const void* y, const float* gate, int gate_stride, int rows_per_sample, int M, int C,
+                 void* dy, void* dyT, float* dgate, float* dbias, void* stream) {
+  DGS_REQUIRE(dx && y && gate && dy && dyT && dgate, "NULL pointer");
+  return gate_bwd(dx, (const __nv_bfloat16*)y, gate, gate_stride, rows_per_sample, M, C, (__nv_bfloat16*)dy,
+                  (__nv_bfloat16*)dyT, dgate, dbias, (cudaStream_t)stream);
 }
 
 int dgs_gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gate, void* out, int M, int N, int K,
@@ -188,7 +509,7 @@ int dgs_gemm_bf16(const void* A, const void* Wt, const float* bias, const float*
 
 int dgs_attention_fwd(const void* qkv, void* out, int B, int N, int heads, void* stream) {
   DGS_REQUIRE(qkv && out, "NULL pointer");
-  return attention_fwd(qkv, out, B, N, heads, (cudaStream_t)stream);
+  return attention_fwd(qkv, out, nullptr, B, N, heads, (cudaStream_t)stream);
 }
 
 int dgs_ln_modulate(const float* x, const float* ln_w, const float* shift, const float* scale, int mod_stride, void* h,

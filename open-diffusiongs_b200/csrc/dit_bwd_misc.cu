@@ -1,0 +1,534 @@
+// dit_bwd_misc.cu -- the memory-bound kernels of the DiT denoiser BACKWARD (everything that is not a GEMM or the
+// attention backward): operand transposes for the weight-gradient GEMMs (+ bias gradients), the gate/residual
+// backward, LayerNorm+adaLN-modulate backward, the skinny conditioning linears' backward, the Gaussian heads'
+// epilogue backward, and the fused AdamW update.
+// The reference gets all of this from torch autograd over denoiser.py:306-416 / utils_transformer.py:246-290; the
+// formulas below are the derivatives of the forward kernels in dit_misc.cu / gemm_epilogue.cuh.
+#include "dgs_internal.h"
+#include "dit_kernels.h"
+
+namespace dgs {
+
+namespace {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+constexpr int TP = 72;  // smem tile pitch in bf16 elements (144 B: 16-byte aligned rows)
+
+// ---------------------------------------------------------------------------------------------------------------
+// out[c, m] = bf16(in[row(m), c]),  m = b * rows_out + j  ->  input row  b * rows_in + row_off + j;  out is [C, Mp]
+// (Mp = round_up(M, 64), pad columns zero-filled: they are the K tail of the weight-gradient GEMM).
+// colsum[c] += sum_m in[row(m), c]  (bias gradient), optional.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename TI>
+__global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ in, int ldi, int rows_in, int row_off,
+                                                        int rows_out, int M, int Mp, __nv_bfloat16* __restrict__ out,
+                                                        float* __restrict__ colsum) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64 * TP];
+  const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64, t = threadIdx.x;
+  {
+    const int lr = t >> 2, lc = (t & 3) * 16;
+    const int m = m0 + lr;
+    __nv_bfloat16 v[16];
+    if (m < M) {
+      const int b = m / rows_out, j = m - b * rows_out;
+      const TI* src = in + ((size_t)b * rows_in + row_off + j) * ldi + c0 + lc;
+#pragma unroll
+      for (int i = 0; i < 16; i++) v[i] = __float2bfloat16_rn(to_f(src[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i++) v[i] = __float2bfloat16_rn(0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) tile[lr * TP + lc + i] = v[i];
+  }
+  __syncthreads();
+  const int c = t >> 2, mc = (t & 3) * 16;
+  __align__(16) __nv_bfloat16 o[16];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    o[i] = tile[(mc + i) * TP + c];
+    s += __bfloat162float(o[i]);
+  }
+  __nv_bfloat16* dst = out + (size_t)(c0 + c) * Mp + m0 + mc;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+  *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<const uint4*>(o + 8);
+  if (colsum) {
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if ((t & 3) == 0) atomicAdd(colsum + c0 + c, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of  x_out = x_in + gate[b] * y   (y = branch output incl. bias, saved pre-gate in bf16):
+//   dy = gate[b] * dx  (bf16, row-major AND transposed [C, Mp]),  dgate[b, c] += sum_rows dx * y,  dbias[c] += sum dy
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ y,
+                                                       const float* __restrict__ gate, int gate_stride,
+                                                       int rows_per_sample, int M, int Mp, int C,
+                                                       __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dyT,
+                                                       float* __restrict__ dgate, float* __restrict__ dbias) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64 * TP];
+  __shared__ float prod[64 * 65];
+  const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64, t = threadIdx.x;
+  {
+    const int lr = t >> 2, lc = (t & 3) * 16;
+    const int m = m0 + lr;
+    if (m < M) {
+      const int b = m / rows_per_sample;
+      const float* g = gate + (size_t)b * gate_stride + c0 + lc;
+      const float* dxr = dx + (size_t)m * C + c0 + lc;
+      const __nv_bfloat16* yr = y + (size_t)m * C + c0 + lc;
+      __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const float d = dxr[i];
+        v[i] = __float2bfloat16_rn(d * __ldg(g + i));
+        prod[lr * 65 + lc + i] = d * __bfloat162float(yr[i]);
+        tile[lr * TP + lc + i] = v[i];
+      }
+      __nv_bfloat16* o = dy + (size_t)m * C + c0 + lc;
+      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(v);
+      *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(v + 8);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        prod[lr * 65 + lc + i] = 0.f;
+        tile[lr * TP + lc + i] = __float2bfloat16_rn(0.f);
+      }
+    }
+  }
+  __syncthreads();
+  const int c = t >> 2, mc = (t & 3) * 16;
+  __align__(16) __nv_bfloat16 o[16];
+  const int b_first = m0 / rows_per_sample;
+  const int split = (b_first + 1) * rows_per_sample - m0;  // tile rows >= split belong to sample b_first + 1
+  float s = 0.f, g0 = 0.f, g1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    o[i] = tile[(mc + i) * TP + c];
+    s += __bfloat162float(o[i]);
+    const float p = prod[(mc + i) * 65 + c];
+    if (mc + i < split) g0 += p; else g1 += p;
+  }
+  __nv_bfloat16* dst = dyT + (size_t)(c0 + c) * Mp + m0 + mc;
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+  *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<const uint4*>(o + 8);
+#pragma unroll
+  for (int sh = 1; sh <= 2; sh <<= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, sh);
+    g0 += __shfl_xor_sync(0xffffffffu, g0, sh);
+    g1 += __shfl_xor_sync(0xffffffffu, g1, sh);
+  }
+  if ((t & 3) == 0) {
+    if (dbias) atomicAdd(dbias + c0 + c, s);
+    atomicAdd(dgate + (size_t)b_first * gate_stride + c0 + c, g0);
+    if (split < 64 && m0 + split < M) atomicAdd(dgate + (size_t)(b_first + 1) * gate_stride + c0 + c, g1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of  h = (LN(x; eps) [* w]) * (1 + scale[b]) + shift[b]   (ln_modulate_kernel / ln_weight_kernel).
+// One warp per row, rows of a CTA all belong to one sample (grid.y = sample), 64 rows per CTA.
+//   dshift[b] += sum g ; dscale[b] += sum g * y ; dw += sum g (1+scale) xhat ; dx (+)= rstd (dxh - mean(dxh) - xhat mean(dxh xhat))
+// ---------------------------------------------------------------------------------------------------------------
+template <typename TG, bool HAS_MOD, bool HAS_W>
+__global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const float* __restrict__ x, const TG* __restrict__ dh,
+                                                              const float* __restrict__ lnw,
+                                                              const float* __restrict__ scale, int mod_stride,
+                                                              int rows_in, int row_off, int rows_out, float eps,
+                                                              float* __restrict__ dx, int accumulate,
+                                                              float* __restrict__ dshift, float* __restrict__ dscale,
+                                                              float* __restrict__ dlnw) {
+  constexpr int D = 1024, PER = 32;
+  __shared__ float s_acc[3 * D];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 3 * D; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  float a_sh[HAS_MOD ? PER : 1], a_sc[HAS_MOD ? PER : 1], a_w[HAS_W ? PER : 1];
+#pragma unroll
+  for (int i = 0; i < (HAS_MOD ? PER : 1); i++) { a_sh[i] = 0.f; a_sc[i] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < (HAS_W ? PER : 1); i++) a_w[i] = 0.f;
+  const int r_end = min(rows_out, (int)(blockIdx.x + 1) * 64);
+  for (int r = blockIdx.x * 64 + warp; r < r_end; r += 8) {
+    const size_t xrow = ((size_t)b * rows_in + row_off + r) * D;
+    const TG* gr = dh + ((size_t)b * rows_out + r) * D;
+    float v[PER], g[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER / 4; i++) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 t4 = *reinterpret_cast<const float4*>(x + xrow + c);
+      v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+      s += t4.x + t4.y + t4.z + t4.w;
+#pragma unroll
+      for (int e = 0; e < 4; e++) g[4 * i + e] = to_f(gr[c + e]);
+    }
+    const float mean = wsum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { v[i] -= mean; q += v[i] * v[i]; }
+    const float rstd = rsqrtf(wsum(q) * (1.0f / D) + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER / 4; i++) {
+      const int c = (i * 32 + lane) * 4;
+      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), w4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (HAS_MOD) s4 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride + c));
+      if (HAS_W) w4 = __ldg(reinterpret_cast<const float4*>(lnw + c));
+      const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int k = 4 * i + e;
+        const float xh = v[k] * rstd;
+        const float gg = g[k];
+        if (HAS_MOD) { a_sh[k] += gg; a_sc[k] += gg * xh * wv[e]; }
+        const float dyv = gg * (1.0f + sv[e]);
+        if (HAS_W) a_w[k] += dyv * xh;
+        const float dxh = dyv * wv[e];
+        v[k] = xh;   // keep xhat
+        g[k] = dxh;  // keep dxhat
+        m1 += dxh;
+        m2 += dxh * xh;
+      }
+    }
+    m1 = wsum(m1) * (1.0f / D);
+    m2 = wsum(m2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < PER / 4; i++) {
+      const int c = (i * 32 + lane) * 4;
+      float4 o;
+      o.x = rstd * (g[4 * i] - m1 - v[4 * i] * m2);
+      o.y = rstd * (g[4 * i + 1] - m1 - v[4 * i + 1] * m2);
+      o.z = rstd * (g[4 * i + 2] - m1 - v[4 * i + 2] * m2);
+      o.w = rstd * (g[4 * i + 3] - m1 - v[4 * i + 3] * m2);
+      float4* dst = reinterpret_cast<float4*>(dx + xrow + c);
+      if (accumulate) {
+        const float4 p = *dst;
+        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      }
+      *dst = o;
+    }
+  }
+  if (HAS_MOD || HAS_W) {
+#pragma unroll
+    for (int i = 0; i < PER / 4; i++) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int c = (i * 32 + lane) * 4 + e, k = 4 * i + e;
+        if (HAS_MOD) { atomicAdd(s_acc + c, a_sh[k]); atomicAdd(s_acc + D + c, a_sc[k]); }
+        if (HAS_W) atomicAdd(s_acc + 2 * D + c, a_w[k]);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += 256) {
+      if (HAS_MOD) {
+        atomicAdd(dshift + (size_t)b * mod_stride + c, s_acc[c]);
+        atomicAdd(dscale + (size_t)b * mod_stride + c, s_acc[D + c]);
+      }
+      if (HAS_W) atomicAdd(dlnw + c, s_acc[2 * D + c]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of the skinny linear  out[b, n] = a[b, :] . W[n, :] + bias[n],  a = act_in(in)  (skinny_linear_kernel):
+//   dW[n, k] = sum_b dout[b, n] a[b, k]     dbias[n] = sum_b dout[b, n]     da[b, k] += sum_n dout[b, n] W[n, k]
+// One CTA per 256 output rows n; a thread owns 4 consecutive k.  W is read once, dW written once.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SKB_MAXB = 8, SKB_ROWS = 256;
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+__global__ void __launch_bounds__(256) skinny_linear_bwd_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                                                const float* __restrict__ dout, int ldo, int B, int N,
+                                                                int K, int act_in, float* __restrict__ dW,
+                                                                float* __restrict__ dbias, float* __restrict__ da) {
+  extern __shared__ float sm[];
+  float* s_a = sm;               // [B, K]
+  float* s_do = sm + B * K;      // [B, SKB_ROWS]
+  const int n0 = blockIdx.x * SKB_ROWS, nrows = min(SKB_ROWS, N - n0);
+  for (int t = threadIdx.x; t < B * K; t += 256) {
+    const float v = in[t];
+    s_a[t] = act_in ? silu_f(v) : v;
+  }
+  for (int t = threadIdx.x; t < B * SKB_ROWS; t += 256) {
+    const int b = t / SKB_ROWS, r = t - b * SKB_ROWS;
+    s_do[t] = r < nrows ? dout[(size_t)b * ldo + n0 + r] : 0.f;
+  }
+  __syncthreads();
+  if (dbias && threadIdx.x < nrows) {
+    float s = 0.f;
+    for (int b = 0; b < B; b++) s += s_do[b * SKB_ROWS + threadIdx.x];
+    dbias[n0 + threadIdx.x] = s;
+  }
+  for (int k = threadIdx.x * 4; k < K; k += 1024) {
+    float acc[SKB_MAXB][4];
+    float a[SKB_MAXB][4];
+#pragma unroll
+    for (int b = 0; b < SKB_MAXB; b++) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) { acc[b][e] = 0.f; a[b][e] = b < B ? s_a[b * K + k + e] : 0.f; }
+    }
+    for (int r = 0; r < nrows; r++) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + r) * K + k));
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int b = 0; b < SKB_MAXB; b++) {
+        if (b < B) {
+          const float d = s_do[b * SKB_ROWS + r];
+          g4.x += d * a[b][0]; g4.y += d * a[b][1]; g4.z += d * a[b][2]; g4.w += d * a[b][3];
+          acc[b][0] += d * w4.x; acc[b][1] += d * w4.y; acc[b][2] += d * w4.z; acc[b][3] += d * w4.w;
+        }
+      }
+      *reinterpret_cast<float4*>(dW + (size_t)(n0 + r) * K + k) = g4;
+    }
+    if (da) {
+#pragma unroll
+      for (int b = 0; b < SKB_MAXB; b++) {
+        if (b < B) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) atomicAdd(da + (size_t)b * K + k + e, acc[b][e]);
+        }
+      }
+    }
+  }
+}
+
+// dpre = dpost * silu'(pre)  (elementwise, in place on dpost)
+__global__ void silu_bwd_kernel(float* __restrict__ d, const float* __restrict__ pre, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = pre[i];
+  const float sg = 1.0f / (1.0f + __expf(-x));
+  d[i] *= sg * (1.0f + x * (1.0f - sg));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of gaussians_epilogue_kernel (to_gs + pixel alignment, denoiser.py:103-120, 362-413): gradients w.r.t. the
+// renderer-ready tensors -> gradients of the raw 14-channel head outputs (free tokens fp32, image tokens bf16).
+// ---------------------------------------------------------------------------------------------------------------
+struct GsGrad { const float* xyz; const float* features; const float* scaling; const float* rotation; const float* opacity; };
+
+__global__ void __launch_bounds__(256) gaussians_epilogue_bwd_kernel(const float* __restrict__ gs_tok,
+                                                                     const float* __restrict__ img_gs,
+                                                                     const float* __restrict__ ray_d, GsGrad d,
+                                                                     float* __restrict__ d_gs_tok,
+                                                                     __nv_bfloat16* __restrict__ d_img_gs, int B, int G,
+                                                                     int V, int H, int W, int p, int scene, float near_,
+                                                                     float far_) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_b = (long long)G + (long long)V * H * W;
+  if (idx >= (long long)B * per_b) return;
+  const int b = (int)(idx / per_b);
+  const long long g = idx - (long long)b * per_b;
+  const size_t o = (size_t)idx;
+  float da[14];
+  const float* src = (g < G) ? gs_tok + ((size_t)b * G + g) * 14 : img_gs + ((size_t)b * V * H * W + (g - G)) * 14;
+  const float gx = d.xyz[3 * o], gy = d.xyz[3 * o + 1], gz = d.xyz[3 * o + 2];
+  if (g < G) {
+    da[0] = gx; da[1] = gy; da[2] = gz;
+  } else {
+    const long long q = g - G;
+    const int hh_n = H / p, ww_n = W / p;
+    int pw = (int)(q % p);
+    long long r = q / p;
+    int ph = (int)(r % p); r /= p;
+    int ww = (int)(r % ww_n); r /= ww_n;
+    int hh = (int)(r % hh_n);
+    int v = (int)(r / hh_n);
+    const int y = hh * p + ph, x = ww * p + pw;
+    const size_t plane = (size_t)H * W, pix = (size_t)y * W + x;
+    const size_t base = ((size_t)b * V + v) * 3 * plane + pix;
+    const float d0 = ray_d[base], d1 = ray_d[base + plane], d2 = ray_d[base + 2 * plane];
+    const float m = (src[0] + src[1] + src[2]) / 3.0f;
+    const float sg = 1.0f / (1.0f + expf(-m));
+    const float dt = gx * d0 + gy * d1 + gz * d2;  // xyz = o + t d
+    const float dtdm = (scene ? (far_ - near_) : 3.6f) * sg * (1.0f - sg);
+    da[0] = da[1] = da[2] = dt * dtdm * (1.0f / 3.0f);
+  }
+  da[3] = d.features[3 * o]; da[4] = d.features[3 * o + 1]; da[5] = d.features[3 * o + 2];
+#pragma unroll
+  for (int k = 0; k < 3; k++) da[6 + k] = (src[6 + k] - 2.3f <= -1.2f) ? d.scaling[3 * o + k] : 0.f;  // clamp(max=-1.2)
+  const float4 dr = *reinterpret_cast<const float4*>(d.rotation + 4 * o);
+  da[9] = dr.x; da[10] = dr.y; da[11] = dr.z; da[12] = dr.w;
+  da[13] = d.opacity[o];
+  if (g < G) {
+    float* dst = d_gs_tok + ((size_t)b * G + g) * 14;
+#pragma unroll
+    for (int k = 0; k < 14; k++) dst[k] = da[k];
+  } else {
+    __nv_bfloat16* dst = d_img_gs + ((size_t)b * V * H * W + (g - G)) * 14;
+#pragma unroll
+    for (int k = 0; k < 14; k += 2) {
+      __nv_bfloat162 pk = __floats2bfloat162_rn(da[k], da[k + 1]);
+      *reinterpret_cast<__nv_bfloat162*>(dst + k) = pk;
+    }
+  }
+}
+
+// Backward of the free-token head linear (rows = B*G, N = 14): dh[r, k] = sum_n dy[r, n] W[n, k] (bf16 out),
+// dW[n, k] = sum_r dy[r, n] h[r, k]  with h = hi + lo of the split-bf16 operand [rows, 3K].
+__global__ void tiny_linear_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ W,
+                                       const __nv_bfloat16* __restrict__ h3, __nv_bfloat16* __restrict__ dh,
+                                       float* __restrict__ dW, int rows, int N, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  for (int r = 0; r < rows; r++) {
+    float s = 0.f;
+    for (int n = 0; n < N; n++) s += dy[r * N + n] * W[(size_t)n * K + k];
+    dh[(size_t)r * K + k] = __float2bfloat16_rn(s);
+  }
+  for (int n = 0; n < N; n++) {
+    float s = 0.f;
+    for (int r = 0; r < rows; r++)
+      s += dy[r * N + n] * (__bfloat162float(h3[(size_t)r * 3 * K + k]) + __bfloat162float(h3[(size_t)r * 3 * K + K + k]));
+    dW[(size_t)n * K + k] = s;
+  }
+}
+
+// dpos[g, :] = sum_b dx[b, g, :]   (the learned Gaussian tokens sit at rows 0..G of every sample)
+__global__ void pos_embed_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int B, int G, int N, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * D) return;
+  const int g = i / D, c = i - g * D;
+  float s = 0.f;
+  for (int b = 0; b < B; b++) s += dx[((size_t)b * N + g) * D + c];
+  dpos[i] = s;
+}
+
+// AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments), fp32 master weights
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2_sqrt, float grad_scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  float pi = p[i] * (1.0f - lr * wd);
+  pi -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  p[i] = pi;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+int transpose_to_bf16(const void* in, int in_is_f32, int ldi, int B, int rows_in, int row_off, int rows_out, int C,
+                      __nv_bfloat16* out, float* colsum, cudaStream_t st) {
+  DGS_REQUIRE(C % 64 == 0 && ldi % 8 == 0, "transpose: need C %% 64 == 0 (C=%d ldi=%d)", C, ldi);
+  const int M = B * rows_out, Mp = (M + 63) / 64 * 64;
+  dim3 grid(Mp / 64, C / 64);
+  if (in_is_f32)
+    transpose_kernel<float><<<grid, 256, 0, st>>>((const float*)in, ldi, rows_in, row_off, rows_out, M, Mp, out, colsum);
+  else
+    transpose_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, ldi, rows_in, row_off, rows_out, M,
+                                                          Mp, out, colsum);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+int gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, int gate_stride, int rows_per_sample, int M,
+             int C, __nv_bfloat16* dy, __nv_bfloat16* dyT, float* dgate, float* dbias, cudaStream_t st) {
+  DGS_REQUIRE(C % 64 == 0 && rows_per_sample >= 64, "gate_bwd: need C %% 64 == 0 and >= 64 rows per sample");
+  const int Mp = (M + 63) / 64 * 64;
+  gate_bwd_kernel<<<dim3(Mp / 64, C / 64), 256, 0, st>>>(dx, y, gate, gate_stride, rows_per_sample, M, Mp, C, dy, dyT,
+                                                         dgate, dbias);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+int ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* lnw, const float* scale, int mod_stride,
+                    int B, int rows_in, int row_off, int rows_out, int D, float eps, float* dx, int accumulate,
+                    float* dshift, float* dscale, float* dlnw, cudaStream_t st) {
+  DGS_REQUIRE(D == 1024, "ln_modulate_bwd: width %d not supported (1024 only)", D);
+  DGS_REQUIRE((scale != nullptr) == (dshift != nullptr && dscale != nullptr), "ln_modulate_bwd: scale/dshift/dscale mismatch");
+  DGS_REQUIRE((lnw != nullptr) == (dlnw != nullptr), "ln_modulate_bwd: lnw/dlnw mismatch");
+  dim3 grid((rows_out + 63) / 64, B);
+#define LNB(TG, MOD, HW)                                                                                              \
+  ln_modulate_bwd_kernel<TG, MOD, HW><<<grid, 256, 0, st>>>(x, (const TG*)dh, lnw, scale, mod_stride, rows_in, row_off, \
+                                                            rows_out, eps, dx, accumulate, dshift, dscale, dlnw)
+  const bool mod = scale != nullptr, hw = lnw != nullptr;
+  if (dh_is_f32) {
+    if (mod && hw) LNB(float, true, true); else if (mod) LNB(float, true, false);
+    else if (hw) LNB(float, false, true); else LNB(float, false, false);
+  } else {
+    if (mod && hw) LNB(__nv_bfloat16, true, true); else if (mod) LNB(__nv_bfloat16, true, false);
+    else if (hw) LNB(__nv_bfloat16, false, true); else LNB(__nv_bfloat16, false, false);
+  }
+#undef LNB
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+int skinny_linear_bwd(const float* in, const float* W, const float* dout, int ldo, int B, int N, int K, int act_in,
+                      float* dW, float* dbias, float* da, cudaStream_t st) {
+  DGS_REQUIRE(B >= 1 && B <= SKB_MAXB && K % 4 == 0, "skinny_linear_bwd: bad shape B=%d K=%d (B <= 8)", B, K);
+  const size_t smem = ((size_t)B * K + (size_t)B * SKB_ROWS) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    DGS_CUDA_OK(cudaFuncSetAttribute(skinny_linear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  DGS_REQUIRE(smem <= 96 * 1024, "skinny_linear_bwd: B*K too large");
+  skinny_linear_bwd_kernel<<<ceil_div(N, SKB_ROWS), 256, smem, st>>>(in, W, dout, ldo, B, N, K, act_in, dW, dbias, da);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+int silu_bwd_inplace(float* d, const float* pre, int n, cudaStream_t st) {
+  silu_bwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(d, pre, n);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+int gaussians_epilogue_bwd(const float* gs_tok, const float* img_gs, const float* ray_d, const float* dxyz,
+                           const float* dfeatures, const float* dscaling, const float* drotation, const float* dopacity,
+                           float* d_gs_tok, __nv_bfloat16* d_img_gs, int B, int G, int V, int H, int W, int patch,
+                           int scene_mode, float near_, float far_, cudaStream_t st) {
+  GsGrad d{dxyz, dfeatures, dscaling, drotation, dopacity};
+  const long long total = (long long)B * ((long long)G + (long long)V * H * W);
+  gaussians_epilogue_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gs_tok, img_gs, ray_d, d, d_gs_tok,
+                                                                                  d_img_gs, B, G, V, H, W, patch,
+                                                                                  scene_mode, near_, far_);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+int tiny_linear_bwd(const float* dy, const float* W, const __nv_bfloat16* h3, __nv_bfloat16* dh, float* dW, int rows,
+                    int N, int K, cudaStream_t st) {
+  tiny_linear_bwd_kernel<<<ceil_div(K, 128), 128, 0, st>>>(dy, W, h3, dh, dW, rows, N, K);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+int pos_embed_bwd(const float* dx, float* dpos, int B, int G, int N, int D, cudaStream_t st) {
+  if (G == 0) return DGS_OK;
+  pos_embed_bwd_kernel<<<ceil_div(G * D, 256), 256, 0, st>>>(dx, dpos, B, G, N, D);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+int adamw_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
+               int step, float grad_scale, cudaStream_t st) {
+  if (n == 0) return DGS_OK;
+  const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
+  adamw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2),
+                                                            grad_scale);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+}  // namespace dgs

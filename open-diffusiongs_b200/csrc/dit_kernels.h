@@ -7,7 +7,7 @@
 
 namespace dgs {
 
-enum GemmEpi { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_GATE_RESID_F32 = 2, EPI_F32 = 3 };
+enum GemmEpi { EPI_BIAS_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_GATE_RESID_F32 = 2, EPI_F32 = 3, EPI_DGELU_BF16 = 4 };
 
 struct GemmEpilogue {
   void* out = nullptr;          // bf16 or fp32 [M, ldc]
@@ -16,6 +16,12 @@ struct GemmEpilogue {
   const float* gate = nullptr;  // EPI_GATE_RESID_F32: gate vector of sample b at gate + b * gate_stride
   int gate_stride = 0;
   int rows_per_sample = 1;      // sample index of a row = row / rows_per_sample
+  // training-mode extras (all optional):
+  void* aux = nullptr;          // bf16 [M, ldc]: EPI_BIAS_GELU_BF16 -> also store the pre-activation (acc + b);
+                                //                EPI_GATE_RESID_F32 -> also store the pre-gate branch output (acc + b);
+                                //                EPI_DGELU_BF16     -> INPUT: the saved pre-activation u (out = acc * gelu'(u))
+  const float* resid = nullptr; // EPI_GATE_RESID_F32: residual source [M, ldc] (null: in place, = out)
+  int lda = 0, ldb = 0;         // row strides of A / W in elements (0 = K): lets K-padded (transposed) operands be used
 };
 
 // C = epi(A[M,K] * W[N,K]^T), bf16 operands, fp32 accumulate (gemm_sm100.cu)
@@ -28,7 +34,13 @@ int gemm_bf16_2cta(const void* A, const void* W, int M, int N, int K, int epi, c
 int gemm_bf16_m256(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st);
 
 // softmax(Q K^T / sqrt(64)) V over qkv [B, N, 3, H, 64] (bf16) -> out [B, N, H*64] (bf16) (attention_sm100.cu)
-int attention_fwd(const void* qkv, void* out, int B, int N, int H, cudaStream_t st);
+// lse2 (optional, training): [B, H, attention_lse_stride(N)] fp32, log2-domain log-sum-exp of the scaled scores
+int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st);
+inline int attention_lse_stride(int N) { return (N + 127) / 128 * 128; }
+// backward (attention_bwd_sm100.cu): dqkv [B, N, 3, H, 64] (bf16) from qkv, out (= O), lse2 and dout [B, N, H*64] (bf16);
+// dsum = scratch [B, H, attention_lse_stride(N)] fp32.  Fills the pad entries of lse2 (+inf) as a side effect.
+int attention_bwd(const void* qkv, const void* out, const void* dout, float* lse2, float* dsum, void* dqkv, int B, int N,
+                  int H, cudaStream_t st);
 
 // ---- dit_misc.cu -------------------------------------------------------------------------------
 // h[r,:] = (LN(x[r,:]; eps) [* w]) * (1 + scale[b,:]) + shift[b,:]   -> bf16
@@ -59,5 +71,28 @@ int gaussians_epilogue(const float* gs_tokens /*[B,G,14]*/, const float* img_gs 
                        const float* ray_o, const float* ray_d, GsOut out, int B, int G, int V, int H, int W, int patch,
                        int scene_mode, float near_, float far_, cudaStream_t st);
 int f32_to_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
+
+// ---- dit_bwd_misc.cu (backward glue) -------------------------------------------------------------
+// out[c, m] = bf16(in[row(m), c]); m = b*rows_out + j -> input row b*rows_in + row_off + j; out [C, round_up(M,64)]
+int transpose_to_bf16(const void* in, int in_is_f32, int ldi, int B, int rows_in, int row_off, int rows_out, int C,
+                      __nv_bfloat16* out, float* colsum, cudaStream_t st);
+int gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, int gate_stride, int rows_per_sample, int M,
+             int C, __nv_bfloat16* dy, __nv_bfloat16* dyT, float* dgate, float* dbias, cudaStream_t st);
+int ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* lnw, const float* scale, int mod_stride,
+                    int B, int rows_in, int row_off, int rows_out, int D, float eps, float* dx, int accumulate,
+                    float* dshift, float* dscale, float* dlnw, cudaStream_t st);
+// dout [B, ldo] (row stride ldo >= N): rows n of this linear are columns [0, N) of dout
+int skinny_linear_bwd(const float* in, const float* W, const float* dout, int ldo, int B, int N, int K, int act_in,
+                      float* dW, float* dbias, float* da, cudaStream_t st);
+int silu_bwd_inplace(float* d, const float* pre, int n, cudaStream_t st);
+int gaussians_epilogue_bwd(const float* gs_tok, const float* img_gs, const float* ray_d, const float* dxyz,
+                           const float* dfeatures, const float* dscaling, const float* drotation, const float* dopacity,
+                           float* d_gs_tok, __nv_bfloat16* d_img_gs, int B, int G, int V, int H, int W, int patch,
+                           int scene_mode, float near_, float far_, cudaStream_t st);
+int tiny_linear_bwd(const float* dy, const float* W, const __nv_bfloat16* h3, __nv_bfloat16* dh, float* dW, int rows,
+                    int N, int K, cudaStream_t st);
+int pos_embed_bwd(const float* dx, float* dpos, int B, int G, int N, int D, cudaStream_t st);
+int adamw_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
+               int step, float grad_scale, cudaStream_t st);
 
 }  // namespace dgs

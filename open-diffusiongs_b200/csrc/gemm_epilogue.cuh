@@ -20,6 +20,15 @@ __device__ __forceinline__ float epi_gelu_tanh(float x) {  // nn.GELU(approximat
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   return 0.5f * x * (1.0f + t);
 }
+__device__ __forceinline__ float epi_dgelu_tanh(float x) {  // d/dx of the above
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float u = k0 * (x + k1 * x * x2);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float du = k0 * (1.0f + 3.0f * k1 * x2);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+}
 __device__ __forceinline__ uint32_t epi_pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -59,9 +68,11 @@ __device__ __forceinline__ void epilogue_drain_row(const GemmEpilogue& ep, const
     gate_row = ep.gate + (size_t)(row / ep.rows_per_sample) * ep.gate_stride;
   float4 xn[8];  // residual prefetch (gate epilogue only)
   float* xrow = (EPI == EPI_GATE_RESID_F32 && valid) ? reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldc : nullptr;
+  const float* rrow = (EPI == EPI_GATE_RESID_F32 && valid) ? (ep.resid ? ep.resid + (size_t)row * ep.ldc : xrow) : nullptr;
+  __nv_bfloat16* arow = (ep.aux && valid) ? reinterpret_cast<__nv_bfloat16*>(ep.aux) + (size_t)row * ep.ldc : nullptr;
   if (EPI == EPI_GATE_RESID_F32 && valid && n0 < N) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) xn[j] = *reinterpret_cast<const float4*>(xrow + n0 + 4 * j);
+    for (int j = 0; j < 8; j++) xn[j] = *reinterpret_cast<const float4*>(rrow + n0 + 4 * j);
   }
 #pragma unroll 1
   for (int c = 0; c < BN / 32; c++) {
@@ -75,8 +86,13 @@ __device__ __forceinline__ void epilogue_drain_row(const GemmEpilogue& ep, const
       for (int j = 0; j < 8; j++) xc[j] = xn[j];
       if (n + 32 < N && c + 1 < BN / 32) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) xn[j] = *reinterpret_cast<const float4*>(xrow + n + 32 + 4 * j);
+        for (int j = 0; j < 8; j++) xn[j] = *reinterpret_cast<const float4*>(rrow + n + 32 + 4 * j);
       }
+    }
+    uint4 ua[4];  // EPI_DGELU_BF16: the saved pre-activation of this chunk
+    if (EPI == EPI_DGELU_BF16 && valid) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) ua[j] = *reinterpret_cast<const uint4*>(arow + n + 8 * j);
     }
     tmem_ld_wait();
     if (!valid) continue;
@@ -84,10 +100,24 @@ __device__ __forceinline__ void epilogue_drain_row(const GemmEpilogue& ep, const
     const float* sb = s_vec + c * 32;
 #pragma unroll
     for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + sb[j];
-    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+    if ((EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_GATE_RESID_F32) && arow) {  // training: keep acc + b (bf16)
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        pk.x = epi_pack_bf16(v[j], v[j + 1]); pk.y = epi_pack_bf16(v[j + 2], v[j + 3]);
+        pk.z = epi_pack_bf16(v[j + 4], v[j + 5]); pk.w = epi_pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(arow + n + j) = pk;
+      }
+    }
+    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_DGELU_BF16) {
       if (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = epi_gelu_tanh(v[j]);
+      }
+      if (EPI == EPI_DGELU_BF16) {
+        const __nv_bfloat16* ub = reinterpret_cast<const __nv_bfloat16*>(ua);
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] *= epi_dgelu_tanh(__bfloat162float(ub[j]));
       }
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldc + n;
 #pragma unroll

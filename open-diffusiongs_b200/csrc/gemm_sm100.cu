@@ -13,7 +13,10 @@
 //   EPI_BIAS_BF16       y = acc + b                         (qkv)
 //   EPI_BIAS_GELU_BF16  y = gelu_tanh(acc + b)              (mlp.fc1 + act)
 //   EPI_GATE_RESID_F32  x += gate[sample] * (acc + b)       (attn.proj / mlp.fc2 + gate + residual, fp32 stream)
-//   EPI_F32             y = acc (+ b), fp32                 (tokenizer, decoder head)
+//   EPI_F32             y = acc (+ b), fp32                 (tokenizer, decoder head, weight gradients)
+//   EPI_DGELU_BF16      y = acc * gelu'(u)                  (backward of mlp.fc2 -> act: u = saved pre-activation)
+// Training mode (GemmEpilogue::aux / resid): fc1 also stores its pre-activation, the gate epilogues also store the
+// pre-gate branch output and may read the residual from a different buffer than they write.
 #include <cstdlib>
 #include <cstring>
 
@@ -216,7 +219,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st) {
   DGS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %dx%dx%d", M, N, K);
-  DGS_REQUIRE(K % 8 == 0 && N % 32 == 0, "gemm: need K %% 8 == 0 and N %% 32 == 0 (got K=%d N=%d)", K, N);
+  DGS_REQUIRE(N % 32 == 0, "gemm: need N %% 32 == 0 (got N=%d)", N);
+  DGS_REQUIRE((ep.lda ? ep.lda : K) % 8 == 0 && (ep.ldb ? ep.ldb : K) % 8 == 0,
+              "gemm: operand row strides must be multiples of 8 elements (K=%d lda=%d ldb=%d)", K, ep.lda, ep.ldb);
+  DGS_REQUIRE(epi != EPI_DGELU_BF16 || ep.aux, "gemm: EPI_DGELU_BF16 needs aux = saved pre-activation");
   DGS_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm: operands must be 16-byte aligned");
   // CTA-pair kernel (gemm2_sm100.cu: 256 x 256 tiles, 2/3 of the operand traffic per CTA).  It is CORRECT (all parity
   // tests pass with DGS_GEMM_2CTA=1) but on B200 it currently runs ~1.6x SLOWER than this single-CTA kernel
@@ -226,26 +232,26 @@ int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const 
     const char* e = getenv("DGS_GEMM_2CTA");
     use_2cta = (e && e[0] == '1') ? 1 : 0;
   }
-  if (use_2cta && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_2cta(A, W, M, N, K, epi, ep, st);
+  if (use_2cta && epi != EPI_DGELU_BF16 && !ep.lda && !ep.ldb && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_2cta(A, W, M, N, K, epi, ep, st);
   // 256 x 256 single-CTA tiles (gemm3_sm100.cu, 1.5x less operand traffic per FLOP): DGS_GEMM_M256=1
   static int use_m256 = -1;
   if (use_m256 < 0) {
     const char* e = getenv("DGS_GEMM_M256");
     use_m256 = (e && e[0] == '1') ? 1 : 0;
   }
-  if (use_m256 && N % 256 == 0 && M >= 256 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_m256(A, W, M, N, K, epi, ep, st);
+  if (use_m256 && epi != EPI_DGELU_BF16 && !ep.lda && !ep.ldb && N % 256 == 0 && M >= 256 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_m256(A, W, M, N, K, epi, ep, st);
   // wide tiles when they still fill the machine, else 128-wide tiles for more CTAs
   const bool wide = (N % 256 == 0) && (ceil_div(M, BM) * (N / 256) >= 120);
   const int BN = wide ? 256 : 128;
   CUtensorMap tmA, tmB;
   {
-    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)K * 2};
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)(ep.lda ? ep.lda : K) * 2};
     uint32_t box[2] = {BK, BM};
     int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K * 2};
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)(ep.ldb ? ep.ldb : K) * 2};
     uint32_t box[2] = {BK, (uint32_t)BN};
     int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
     if (rc) return rc;
@@ -258,6 +264,7 @@ int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const 
     DGS_GEMM_CASE(EPI_BIAS_GELU_BF16)
     DGS_GEMM_CASE(EPI_GATE_RESID_F32)
     DGS_GEMM_CASE(EPI_F32)
+    DGS_GEMM_CASE(EPI_DGELU_BF16)
     default:
       set_error("gemm: unknown epilogue %d", epi);
       return DGS_ERR_INVALID_ARGUMENT;

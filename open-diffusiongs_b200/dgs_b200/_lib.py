@@ -39,7 +39,25 @@ class DitIO(C.Structure):
     _fields_ = [("B", C.c_int), ("V", C.c_int), ("H", C.c_int), ("W", C.c_int), ("plucker_mode", C.c_int),
                 ("scene_depth", C.c_int), ("range_near", C.c_float), ("range_far", C.c_float)] + [
         (n, C.c_void_p) for n in ("images", "ray_o", "ray_d", "t", "xyz", "features", "scaling", "rotation",
-                                  "opacity", "img_aligned_xyz", "tokens_out")]
+                                  "opacity", "img_aligned_xyz", "tokens_out", "train_state")]
+
+
+GRAD_FIELDS_A = ("tokenizer_w", "pos_embed", "in_ln_w", "t0_w", "t0_b", "t2_w", "t2_b")
+GRAD_FIELDS_B = ("qkv_w", "qkv_b", "proj_w", "proj_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "adaln_w", "adaln_b", "ups_ln_w",
+                 "ups_w", "ups_adaln_w", "ups_adaln_b", "dec_ln_w", "dec_w", "dec_adaln_w", "dec_adaln_b")
+
+
+class DitWeightsT(C.Structure):  # dgs_dit_weights_t
+    _fields_ = [(n, C.c_void_p) for n in ("qkv_wT", "proj_wT", "fc1_wT", "fc2_wT", "dec_wT", "ups_w")]
+
+
+class DitGrads(C.Structure):  # dgs_dit_grads
+    _fields_ = [(n, C.c_void_p) for n in GRAD_FIELDS_A] + [("layer_stride", C.c_longlong)] + \
+        [(n, C.c_void_p) for n in GRAD_FIELDS_B]
+
+
+class DitOutGrads(C.Structure):  # dgs_dit_out_grads
+    _fields_ = [(n, C.c_void_p) for n in ("d_xyz", "d_features", "d_scaling", "d_rotation", "d_opacity")]
 
 
 _lib = None
@@ -83,6 +101,18 @@ def lib():
                                     C.c_int, vp]
         L.dgs_attention_fwd.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
         L.dgs_ln_modulate.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
+        L.dgs_dit_train_state_bytes.restype = C.c_size_t
+        L.dgs_dit_train_state_bytes.argtypes = [C.POINTER(DitWeights), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.dgs_dit_backward.argtypes = [C.POINTER(DitWeights), C.POINTER(DitWeightsT), C.POINTER(DitIO),
+                                       C.POINTER(DitOutGrads), C.POINTER(DitGrads), vp, C.c_size_t, vp]
+        L.dgs_transpose_bf16.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+        L.dgs_adamw_step.argtypes = [vp, vp, vp, vp, C.c_size_t] + [C.c_float] * 5 + [C.c_int, C.c_float, vp]
+        L.dgs_attention_fwd_train.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        L.dgs_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        L.dgs_gemm_bf16_ex.argtypes = [vp] * 7 + [C.c_int] * 9 + [vp]
+        L.dgs_ln_modulate_bwd.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp,
+                                          C.c_int, vp, vp, vp, vp]
+        L.dgs_gate_bwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
         L.dgs_rays_from_cameras.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
         L.dgs_q_sample.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_longlong, vp, vp]
         L.dgs_p_sample_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_longlong, vp, vp]
@@ -93,7 +123,7 @@ def lib():
 PROF_FAMILIES = ["raster.project", "raster.scan", "raster.emit_keys", "raster.sort", "raster.tile_ranges",
                  "raster.blend_fwd", "raster.blend_bwd", "raster.geometry_bwd", "dit.input", "dit.conditioning",
                  "dit.ln_modulate", "dit.gemm_qkv", "dit.attention", "dit.gemm_proj", "dit.gemm_fc1", "dit.gemm_fc2",
-                 "dit.heads"]
+                 "dit.heads", "dit.bwd_elementwise", "dit.bwd_gemm_wgrad", "dit.bwd_gemm_dgrad", "dit.bwd_attention"]
 
 
 def profile_read():
@@ -117,4 +147,6 @@ EXPORTED = [  # every symbol include/dgs_b200.h declares (checked by tests/test_
     "dgs_render_batch_forward", "dgs_render_batch_backward", "dgs_raster_export_state",
     "dgs_dit_workspace_bytes", "dgs_dit_forward", "dgs_gemm_bf16", "dgs_attention_fwd", "dgs_ln_modulate",
     "dgs_rays_from_cameras", "dgs_q_sample", "dgs_p_sample_step",
+    "dgs_dit_train_state_bytes", "dgs_dit_backward", "dgs_transpose_bf16", "dgs_adamw_step", "dgs_attention_fwd_train",
+    "dgs_attention_bwd", "dgs_gemm_bf16_ex", "dgs_ln_modulate_bwd", "dgs_gate_bwd",
 ]

@@ -7,7 +7,7 @@ denoiser_scene.py:172-457) on top of libdgs_b200.so.
   render_gaussians(params, c2w, fxfycxcy, H, W), prepare_to_save, `dtype`, `gs_renderer`;
 * the arithmetic is ONE C-ABI call (dgs_dit_forward: tcgen05 GEMMs + tcgen05 attention + fused glue);
   the nn.Linear / nn.LayerNorm objects below only HOLD parameters under the reference's names, their
-  forward() is never used.  Forward only in this round (no autograd through the DiT yet).
+  forward() is never used.  Training: dgs_b200/train.py (DitTrainer) attaches the backward.
 """
 import ctypes as C
 
@@ -189,14 +189,29 @@ class DGSDenoiser(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
-    @torch.no_grad()
     def image_to_gaussians(self, images, ray_o, ray_d, t, training: bool = False, return_tokens: bool = False):
+        """denoiser.py:306-416.  Inference: one dgs_dit_forward call under no_grad.  With autograd enabled on a module
+        in train() mode that has a DitTrainer attached (dgs_b200/train.py), the call is recorded as ONE autograd node
+        whose backward is dgs_dit_backward (activations stored, not recomputed)."""
+        if torch.is_grad_enabled() and self.training and getattr(self, "_trainer", None) is not None:
+            from .train import dit_train_forward
+            out, img_xyz = dit_train_forward(self, images, ray_o, ray_d, t)
+            return (out, img_xyz, None) if return_tokens else (out, img_xyz)
+        with torch.no_grad():
+            out, img_xyz, tokens, _ = self._run_dit(images, ray_o, ray_d, t, return_tokens=return_tokens)
+            if self.cfg.clip_xyz and training and not self.SCENE:  # denoiser.py:395-396 (never taken by the reference's callers)
+                n_img = images.shape[1] * images.shape[3] * images.shape[4]
+                out.xyz[:, -n_img:] = out.xyz[:, -n_img:].clamp(-1.0, 1.0)
+                img_xyz = img_xyz.clamp(-1.0, 1.0)
+        return (out, img_xyz, tokens) if return_tokens else (out, img_xyz)
+
+    def _run_dit(self, images, ray_o, ray_d, t, return_tokens=False, train_state=None):
         dev = self.device
         if dev.type != "cuda":
             raise _lib.DgsError("DGSDenoiser runs on a CUDA device only (no CPU / PyTorch fallback)")
         c = self.cfg
-        images = images[:, :, :3].float().contiguous()
-        ray_o, ray_d = ray_o.float().contiguous(), ray_d.float().contiguous()
+        images = images[:, :, :3].detach().float().contiguous()
+        ray_o, ray_d = ray_o.detach().float().contiguous(), ray_d.detach().float().contiguous()
         B, V, _, H, W = images.shape
         P = c.n_gaussians + V * H * W
         tf = t.to(device=dev, dtype=torch.float32).contiguous()
@@ -221,14 +236,12 @@ class DGSDenoiser(nn.Module):
                        ray_d=ray_d.data_ptr(), t=tf.data_ptr(), xyz=out.xyz.data_ptr(),
                        features=out.features.data_ptr(), scaling=out.scaling.data_ptr(),
                        rotation=out.rotation.data_ptr(), opacity=out.opacity.data_ptr(),
-                       img_aligned_xyz=img_xyz.data_ptr(), tokens_out=None if tokens is None else tokens.data_ptr())
+                       img_aligned_xyz=img_xyz.data_ptr(), tokens_out=None if tokens is None else tokens.data_ptr(),
+                       train_state=None if train_state is None else train_state.data_ptr())
             check(L.dgs_dit_forward(C.byref(w), C.byref(io), ws.data_ptr(), nbytes,
                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
-        if c.clip_xyz and training and not self.SCENE:  # denoiser.py:395-396 (never taken by the reference's callers)
-            n_img = V * H * W
-            out.xyz[:, -n_img:] = out.xyz[:, -n_img:].clamp(-1.0, 1.0)
-            img_xyz = img_xyz.clamp(-1.0, 1.0)
-        return (out, img_xyz, tokens) if return_tokens else (out, img_xyz)
+        keep = (io, ws, nbytes, images, ray_o, ray_d, tf, w, _keep)  # what a later dgs_dit_backward needs alive
+        return out, img_xyz, tokens, keep
 
     def render_gaussians(self, gaussian_params, c2w, fxfycxcy, height, width):
         g = gaussian_params
