@@ -213,6 +213,132 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def run_train(args, rank, local_rank, world):
+    """Training step of the obj-256 config (BASELINE configs[2], diffusionGS_rel.yaml: 4 input views, 10 rendered views,
+    AdamW lr 1e-5, clip 0.5; loss = MSE only -- the LPIPS weights are not available offline): one process per GPU,
+    per-GPU batch --batch, gradients all-reduced over NCCL every step.  Prints one JSON line (same keys as the default
+    workload; `value` = samples/s over all ranks)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dgs_b200 import _lib, synth
+    from dgs_b200.denoiser import DGSDenoiser
+    from dgs_b200.train import DitTrainer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("DGS_NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)  # identical initial weights on every rank (what DDP's broadcast establishes)
+    model = DGSDenoiser(dict(patch_size=PATCH)).to(dev)
+    trainer = DitTrainer(model, lr=1e-5, betas=(0.9, 0.99), eps=1e-8, clip=0.5)
+    model.train()
+    B, VR = args.batch, args.render_views
+    host = make_batch(B, seed=rank)
+    c2w_r, fx_r = synth.orbit_cameras(VR, W, H, radius=3.0, el_deg=20.0, az_step=36.0)
+    rng = np.random.default_rng(100 + rank)
+    host["c2w_r"] = torch.from_numpy(np.broadcast_to(c2w_r, (B, VR, 4, 4)).copy())
+    host["fx_r"] = torch.from_numpy(np.broadcast_to(fx_r, (B, VR, 4)).copy())
+    host["target"] = torch.from_numpy(rng.uniform(0, 1, (B, VR, 3, H, W)).astype(np.float32))
+    host = {k: v.pin_memory() for k, v in host.items()}
+    devb = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+
+    def step(b):
+        out, _ = model.image_to_gaussians(b["image"], b["ray_o"], b["ray_d"], b["t"])
+        renders = model.render_gaussians(out, b["c2w_r"], b["fx_r"], H, W)
+        loss = ((renders - b["target"]) ** 2).mean()
+        trainer.zero_grad()
+        loss.backward()
+        trainer.optimizer_step(allreduce=True)
+        return loss.detach()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step(devb)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = L.dgs_kernel_launch_count()
+    barrier()
+    t0 = time.time()
+    for a, b_ in ev:
+        flush.zero_()
+        a.record()
+        loss = step(devb)
+        b_.record()
+    barrier()
+    t1 = time.time()
+    launches = L.dgs_kernel_launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    step_ms = [a.elapsed_time(b_) for a, b_ in ev]
+    total_s = torch.tensor([sum(step_ms) / 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_s, op=dist.ReduceOp.MAX)
+    value = world * B * args.steps / float(total_s)
+    # per-family device time
+    L.dgs_profile_enable(1)
+    _lib.profile_read()
+    for _ in range(args.steps):
+        step(devb)
+    torch.cuda.synchronize(dev)
+    fam = _lib.profile_read()
+    L.dgs_profile_enable(0)
+    fam_ms = {k: v[0] / args.steps for k, v in fam.items() if v[1]}
+    # end to end: pinned host inputs -> device every step, loss read back
+    def e2e_step():
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        return step(b).to("cpu")
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        lh = e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peaks = load_peaks()
+        f_train = 3 * dit_forward_flops() * B  # fwd + 2 x bwd, activations stored (no recompute)
+        dit_ms = sum(v for k, v in fam_ms.items() if k.startswith("dit."))
+        bwd_att = fam_ms.get("dit.bwd_attention")
+        roof = None
+        if bwd_att:
+            ach = 2.5 * attention_flops() * B / (bwd_att / LAYERS * 1e-3) / 1e12  # 5 GEMMs of the algorithm vs 2 forward
+            roof = dict(kernel="dit.bwd_attention", bound="tensor", achieved=ach, peak=peaks["bf16_tflops_sustained"],
+                        unit="TFLOP/s", frac=ach / peaks["bf16_tflops_sustained"], traffic=None,
+                        peak_source=peaks["source"], launch_ms=bwd_att / LAYERS,
+                        note="algorithmic FLOPs = 2.5 x forward attention (dV, dP, dQ, dK + S); the kernel pair recomputes S and dP once more")
+        line = dict(metric="train-samples/sec @256^2 (DiT fwd+bwd + %d-view render fwd+bwd + grad all-reduce + AdamW)" % VR,
+                    value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=float(total_s) / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="bf16", data="synthetic",
+                    config=dict(workload="obj-256 train step: 4 input views, %d rendered views, MSE loss, AdamW" % VR,
+                                per_gpu_batch=B, parallelism=f"dp{world} (NCCL all-reduce of 460 M fp32 gradients)",
+                                l2="256 MB buffer written between timed steps"),
+                    e2e=dict(value=world * B * args.steps / float(e2e_s), unit="samples/s",
+                             h2d_bytes_per_step=sum(v.numel() * v.element_size() for v in host.values()),
+                             d2h_bytes_per_step=lh.numel() * lh.element_size()),
+                    gpu_launches=int(launches), roofline=roof, cpu_baseline=None, clocks=clocks,
+                    breakdown_ms=dict(dit=dit_ms, families={k: round(v, 4) for k, v in fam_ms.items()}),
+                    dit_train_tflops=f_train / (dit_ms * 1e-3) / 1e12 if dit_ms else None, loss=float(loss),
+                    step_ms=[round(v, 3) for v in step_ms], mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def workload_name(batch):
     return (f"obj-256 denoise step (BASELINE configs[1]): 1 DiT forward (24 layers, {N_TOK} tokens) + {V}-view "
             f"256x256 splat render of P={P_GAUSS} Gaussians, per-GPU batch {batch}, random-init weights")
@@ -229,6 +355,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="denoise", choices=["denoise", "train"],
+                    help="denoise = BASELINE configs[1] (the contract's default line); train = configs[2]-shaped training "
+                         "step (DiT fwd+bwd, V_render-view render fwd+bwd, gradient all-reduce, AdamW)")
+    ap.add_argument("--render-views", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -237,6 +367,9 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.workload == "train":
+        run_train(args, rank, local_rank, world)
         return
 
     import torch

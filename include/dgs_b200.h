@@ -263,9 +263,15 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
 /* out[c, m] = bf16(in[m, c]) for in [M, C] (fp32 if in_is_f32 else bf16), out [C, round_up(M, 64)] zero padded;
  * colsum (optional, fp32 [C]) += column sums.  Used for the transposed weight copies and inside the backward. */
 int dgs_transpose_bf16(const void* in, int in_is_f32, int M, int C, void* out, float* colsum, void* stream);
-/* fused AdamW on fp32 master parameters (torch.optim.AdamW semantics; diffusionGS_rel.yaml:57-62), step >= 1 */
+/* fused AdamW on fp32 master parameters (torch.optim.AdamW semantics; diffusionGS_rel.yaml:57-62), step >= 1.
+ * The gradient is multiplied by grad_scale * (grad_scale_dev ? *grad_scale_dev : 1): the clip factor stays on the device */
 int dgs_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, const float* grad_scale_dev,
+                   void* stream);
+/* weight refresh after an optimizer step: `batch` fp32 matrices [M, C] (matrix i at in + i*in_batch_stride floats) ->
+ * bf16 copies [batch, M, C] (optional) and transposed bf16 copies [batch, C, M]; M, C multiples of 64 */
+int dgs_cast_transpose_f32(const float* in, long long in_batch_stride, int batch, int M, int C, void* out_bf16,
+                           void* outT_bf16, void* stream);
 
 /* Building blocks, exported for the unit parity tests (same kernels dgs_dit_forward launches).
  * epi: 0 = bias -> bf16, 1 = bias + GELU(tanh) -> bf16, 2 = out(fp32) += gate[row / rows_per_sample] * (acc + bias),
@@ -284,10 +290,11 @@ int dgs_attention_bwd(const void* qkv, const void* out, const void* dout, float*
 int dgs_gemm_bf16_ex(const void* A, const void* W, const float* bias, const float* gate, void* out, void* aux,
                      const float* resid, int M, int N, int K, int lda, int ldb, int epi, int ldc, int gate_stride,
                      int rows_per_sample, void* stream);
-/* backward of dgs_ln_modulate: dx (+)= ..., dshift/dscale [B, mod_stride] += ..., dln_w += ... (NULL where absent) */
+/* backward of dgs_ln_modulate: dx (+)= ..., dshift/dscale [B, mod_stride] += ..., dln_w += ... (NULL where absent);
+ * stats = scratch of 2*B*rows floats (per-row mean / rstd handed from the row kernel to the column kernel) */
 int dgs_ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* ln_w, const float* scale,
                         int mod_stride, int B, int rows, int width, float eps, float* dx, int accumulate, float* dshift,
-                        float* dscale, float* dln_w, void* stream);
+                        float* dscale, float* dln_w, float* stats, void* stream);
 /* backward of x_out = x_in + gate[b] * y: dy (bf16 [M,C]), dyT (bf16 [C, round_up(M,64)]), dgate += , dbias += */
 int dgs_gate_bwd(const float* dx, const void* y, const float* gate, int gate_stride, int rows_per_sample, int M, int C,
                  void* dy, void* dyT, float* dgate, float* dbias, void* stream);

@@ -69,6 +69,7 @@ struct TrainState {
   float* dmod;              // [B, mod_stride]
   float* dsum;              // [B, heads, Np]
   float* dcond;             // [3][B, w]   dsilu(c) / dtemb1 / pre1
+  float* ln_stats;          // [M, 2]      (mean, rstd) of the LayerNorm being differentiated
   float* d_gs_tok;          // [B*G, 14]
   __nv_bfloat16* dyb;       // [M, w]      gated branch gradient / generic [M, w] bf16
   __nv_bfloat16* dh;        // [M, w]
@@ -101,6 +102,7 @@ struct TrainState {
     dmod = c.take<float>((size_t)B * mod_stride);
     dsum = c.take<float>((size_t)B * w->heads * Np);
     dcond = c.take<float>((size_t)3 * B * D);
+    ln_stats = c.take<float>(2 * M);
     d_gs_tok = c.take<float>((size_t)B * w->n_gaussians * 14 + 16);
     dyb = c.take<__nv_bfloat16>(M * D);
     dh = c.take<__nv_bfloat16>(M * D);
@@ -328,11 +330,11 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
     DGS_TRY(transpose_to_bf16(ts.hdec, 0, 3 * D, 1, Mt, 0, Mt, D, ts.bigT1, nullptr, st));  // hi part of [hi|lo|hi]
     DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->dec_w, Ndec, D, Mtp));
     DGS_TRY(ln_modulate_bwd(x_fin, ts.dh, 0, w->dec_ln_w, md + D, mod_stride, B, N, G, T, D, 1e-5f, ts.dx, 0, dmd, dmd + D,
-                            g->dec_ln_w, st));
+                            g->dec_ln_w, ts.ln_stats, st));
     if (G > 0) {  // upsampler (the free Gaussian tokens, rows 0..G of every sample)
       DGS_TRY(tiny_linear_bwd(ts.d_gs_tok, wT->ups_w, ws.hg, ts.dyb, g->ups_w, B * G, 14, D, st));
       DGS_TRY(ln_modulate_bwd(x_fin, ts.dyb, 0, w->ups_ln_w, mu + D, mod_stride, B, N, 0, G, D, 1e-5f, ts.dx, 0, dmu, dmu + D,
-                              g->ups_ln_w, st));
+                              g->ups_ln_w, ts.ln_stats, st));
     }
   }
 
@@ -374,7 +376,7 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
     {
       ProfScope ps(st, PROF_DIT_BWD_ELEM);
       DGS_TRY(ln_modulate_bwd(x_mid, ts.dh, 0, nullptr, m + 4 * D, mod_stride, B, N, 0, N, D, 1e-6f, ts.dx, 1, dm + 3 * D,
-                              dm + 4 * D, nullptr, st));
+                              dm + 4 * D, nullptr, ts.ln_stats, st));
       // -- attention branch: x_mid = x_in + gate_msa * proj(attn(qkv(h1)))
       DGS_TRY(gate_bwd(ts.dx, ts.proj_out + (size_t)l * MD, m + 2 * D, mod_stride, N, M, D, ts.dyb, ts.bigT0, dm + 2 * D,
                        g->proj_b + l * LS, st));
@@ -408,14 +410,14 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_ELEM);
-      DGS_TRY(ln_modulate_bwd(x_in, ts.dh, 0, nullptr, m + D, mod_stride, B, N, 0, N, D, 1e-6f, ts.dx, 1, dm, dm + D, nullptr, st));
+      DGS_TRY(ln_modulate_bwd(x_in, ts.dh, 0, nullptr, m + D, mod_stride, B, N, 0, N, D, 1e-6f, ts.dx, 1, dm, dm + D, nullptr, ts.ln_stats, st));
     }
   }
 
   ProfScope ps_in(st, PROF_DIT_BWD_ELEM);
   // ---- input stage: LayerNorm(weight) -> [pos tokens | tokenizer GEMM] ----
   DGS_TRY(ln_modulate_bwd(ts.x_pre, ts.dx, 1, w->in_ln_w, nullptr, 0, B, N, 0, N, D, 1e-5f, ts.dx_pre, 0, nullptr, nullptr,
-                          g->in_ln_w, st));
+                          g->in_ln_w, ts.ln_stats, st));
   DGS_TRY(pos_embed_bwd(ts.dx_pre, g->pos_embed, B, G, N, D, st));
   DGS_TRY(transpose_to_bf16(ts.dx_pre, 1, D, B, N, G, T, D, ts.bigT0, nullptr, st));          // d tok^T [D, Mtp]
   DGS_TRY(transpose_to_bf16(ws.tokens, 0, 3 * Kin, 1, Mt, 0, Mt, Kin, ts.bigT1, nullptr, st));  // hi part of the patches
@@ -453,10 +455,18 @@ int dgs_transpose_bf16(const void* in, int in_is_f32, int M, int C, void* out, f
 }
 
 int dgs_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, const float* grad_scale_dev,
+                   void* stream) {
   DGS_REQUIRE(param && grad && exp_avg && exp_avg_sq && step >= 1, "bad AdamW arguments");
   return adamw_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
-                    (cudaStream_t)stream);
+                    grad_scale_dev, (cudaStream_t)stream);
+}
+
+int dgs_cast_transpose_f32(const float* in, long long in_batch_stride, int batch, int M, int C, void* out_bf16,
+                           void* outT_bf16, void* stream) {
+  DGS_REQUIRE(in && outT_bf16 && batch > 0, "bad arguments");
+  return cast_transpose_f32(in, in_batch_stride, batch, M, C, (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)outT_bf16,
+                            (cudaStream_t)stream);
 }
 
 int dgs_attention_fwd_train(const void* qkv, void* out, float* lse2, int B, int N, int heads, void* stream) {
@@ -484,10 +494,10 @@ int dgs_gemm_bf16_ex(const void* A, const void* Wt, const float* bias, const flo
 
 int dgs_ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* ln_w, const float* scale,
                         int mod_stride, int B, int rows, int width, float eps, float* dx, int accumulate, float* dshift,
-                        float* dscale, float* dln_w, void* stream) {
-  DGS_REQUIRE(x && dh && dx, "NULL pointer");
+                        float* dscale, float* dln_w, float* stats, void* stream) {
+  DGS_REQUIRE(x && dh && dx && stats, "NULL pointer");
   return ln_modulate_bwd(x, dh, dh_is_f32, ln_w, scale, mod_stride, B, rows, 0, rows, width, eps, dx, accumulate, dshift,
-                         dscale, dln_w, (cudaStream_t)stream);
+                         dscale, dln_w, stats, (cudaStream_t)stream);
 }
 
 int dgs_gate_bwd(const float* dx, const void* y, const float* gate, int gate_stride, int rows_per_sample, int M, int C,

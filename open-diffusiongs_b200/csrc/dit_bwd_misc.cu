@@ -21,35 +21,57 @@ __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float
 
 constexpr int TP = 72;  // smem tile pitch in bf16 elements (144 B: 16-byte aligned rows)
 
+// 16 consecutive elements of a row -> bf16 (two 16-byte vectors)
+__device__ __forceinline__ void load16_bf16(const __nv_bfloat16* src, uint4& lo, uint4& hi) {
+  lo = *reinterpret_cast<const uint4*>(src);
+  hi = *reinterpret_cast<const uint4*>(src + 8);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void load16_bf16(const float* src, uint4& lo, uint4& hi) {
+  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+  const float4 c = *reinterpret_cast<const float4*>(src + 8), d = *reinterpret_cast<const float4*>(src + 12);
+  lo = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+  hi = make_uint4(pack_bf16x2(c.x, c.y), pack_bf16x2(c.z, c.w), pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // out[c, m] = bf16(in[row(m), c]),  m = b * rows_out + j  ->  input row  b * rows_in + row_off + j;  out is [C, Mp]
 // (Mp = round_up(M, 64), pad columns zero-filled: they are the K tail of the weight-gradient GEMM).
 // colsum[c] += sum_m in[row(m), c]  (bias gradient), optional.
+// 64 x 64 tile per CTA: 16-byte global loads -> smem -> column reads with the lanes along c (conflict-free) ->
+// 32-byte global stores.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename TI>
 __global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ in, int ldi, int rows_in, int row_off,
                                                         int rows_out, int M, int Mp, __nv_bfloat16* __restrict__ out,
-                                                        float* __restrict__ colsum) {
+                                                        float* __restrict__ colsum, __nv_bfloat16* __restrict__ out_rm,
+                                                        int C, size_t in_bstride, size_t out_bstride, size_t rm_bstride) {
   __shared__ __align__(16) __nv_bfloat16 tile[64 * TP];
+  __shared__ float red[4 * 64];
   const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64, t = threadIdx.x;
+  in += (size_t)blockIdx.z * in_bstride;   // batched use (weight refresh): one matrix per blockIdx.z
+  out += (size_t)blockIdx.z * out_bstride;
   {
     const int lr = t >> 2, lc = (t & 3) * 16;
     const int m = m0 + lr;
-    __nv_bfloat16 v[16];
+    uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
     if (m < M) {
       const int b = m / rows_out, j = m - b * rows_out;
-      const TI* src = in + ((size_t)b * rows_in + row_off + j) * ldi + c0 + lc;
-#pragma unroll
-      for (int i = 0; i < 16; i++) v[i] = __float2bfloat16_rn(to_f(src[i]));
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; i++) v[i] = __float2bfloat16_rn(0.f);
+      load16_bf16(in + ((size_t)b * rows_in + row_off + j) * ldi + c0 + lc, lo, hi);
+      if (out_rm) {  // optional plain (row-major) bf16 copy of the same tile
+        __nv_bfloat16* rm = out_rm + (size_t)blockIdx.z * rm_bstride + (size_t)m * C + c0 + lc;
+        *reinterpret_cast<uint4*>(rm) = lo;
+        *reinterpret_cast<uint4*>(rm + 8) = hi;
+      }
     }
-#pragma unroll
-    for (int i = 0; i < 16; i++) tile[lr * TP + lc + i] = v[i];
+    *reinterpret_cast<uint4*>(tile + lr * TP + lc) = lo;
+    *reinterpret_cast<uint4*>(tile + lr * TP + lc + 8) = hi;
   }
   __syncthreads();
-  const int c = t >> 2, mc = (t & 3) * 16;
+  const int c = t & 63, mq = t >> 6, mc = mq * 16;
   __align__(16) __nv_bfloat16 o[16];
   float s = 0.f;
 #pragma unroll
@@ -61,9 +83,9 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ i
   *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
   *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<const uint4*>(o + 8);
   if (colsum) {
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if ((t & 3) == 0) atomicAdd(colsum + c0 + c, s);
+    red[mq * 64 + c] = s;
+    __syncthreads();
+    if (t < 64) atomicAdd(colsum + c0 + t, red[t] + red[64 + t] + red[128 + t] + red[192 + t]);
   }
 }
 
@@ -78,6 +100,7 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__
                                                        float* __restrict__ dgate, float* __restrict__ dbias) {
   __shared__ __align__(16) __nv_bfloat16 tile[64 * TP];
   __shared__ float prod[64 * 65];
+  __shared__ float red[3 * 4 * 64];
   const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64, t = threadIdx.x;
   {
     const int lr = t >> 2, lc = (t & 3) * 16;
@@ -86,28 +109,36 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__
       const int b = m / rows_per_sample;
       const float* g = gate + (size_t)b * gate_stride + c0 + lc;
       const float* dxr = dx + (size_t)m * C + c0 + lc;
-      const __nv_bfloat16* yr = y + (size_t)m * C + c0 + lc;
-      __align__(16) __nv_bfloat16 v[16];
+      uint4 ylo, yhi;
+      load16_bf16(y + (size_t)m * C + c0 + lc, ylo, yhi);
+      const uint32_t yw[8] = {ylo.x, ylo.y, ylo.z, ylo.w, yhi.x, yhi.y, yhi.z, yhi.w};
+      uint32_t pk[8];
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const float d = dxr[i];
-        v[i] = __float2bfloat16_rn(d * __ldg(g + i));
-        prod[lr * 65 + lc + i] = d * __bfloat162float(yr[i]);
-        tile[lr * TP + lc + i] = v[i];
+      for (int q = 0; q < 4; q++) {
+        const float4 d4 = *reinterpret_cast<const float4*>(dxr + 4 * q);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + 4 * q));
+        const float2 y0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[2 * q]));
+        const float2 y1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[2 * q + 1]));
+        pk[2 * q] = pack_bf16x2(d4.x * g4.x, d4.y * g4.y);
+        pk[2 * q + 1] = pack_bf16x2(d4.z * g4.z, d4.w * g4.w);
+        float* pr = prod + lr * 65 + lc + 4 * q;
+        pr[0] = d4.x * y0.x; pr[1] = d4.y * y0.y; pr[2] = d4.z * y1.x; pr[3] = d4.w * y1.y;
       }
+      const uint4 lo = make_uint4(pk[0], pk[1], pk[2], pk[3]), hi = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      *reinterpret_cast<uint4*>(tile + lr * TP + lc) = lo;
+      *reinterpret_cast<uint4*>(tile + lr * TP + lc + 8) = hi;
       __nv_bfloat16* o = dy + (size_t)m * C + c0 + lc;
-      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(v);
-      *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(v + 8);
+      *reinterpret_cast<uint4*>(o) = lo;
+      *reinterpret_cast<uint4*>(o + 8) = hi;
     } else {
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        prod[lr * 65 + lc + i] = 0.f;
-        tile[lr * TP + lc + i] = __float2bfloat16_rn(0.f);
-      }
+      for (int i = 0; i < 16; i++) prod[lr * 65 + lc + i] = 0.f;
+      *reinterpret_cast<uint4*>(tile + lr * TP + lc) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(tile + lr * TP + lc + 8) = make_uint4(0, 0, 0, 0);
     }
   }
   __syncthreads();
-  const int c = t >> 2, mc = (t & 3) * 16;
+  const int c = t & 63, mq = t >> 6, mc = mq * 16;
   __align__(16) __nv_bfloat16 o[16];
   const int b_first = m0 / rows_per_sample;
   const int split = (b_first + 1) * rows_per_sample - m0;  // tile rows >= split belong to sample b_first + 1
@@ -122,121 +153,141 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__
   __nv_bfloat16* dst = dyT + (size_t)(c0 + c) * Mp + m0 + mc;
   *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
   *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<const uint4*>(o + 8);
-#pragma unroll
-  for (int sh = 1; sh <= 2; sh <<= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, sh);
-    g0 += __shfl_xor_sync(0xffffffffu, g0, sh);
-    g1 += __shfl_xor_sync(0xffffffffu, g1, sh);
-  }
-  if ((t & 3) == 0) {
-    if (dbias) atomicAdd(dbias + c0 + c, s);
-    atomicAdd(dgate + (size_t)b_first * gate_stride + c0 + c, g0);
-    if (split < 64 && m0 + split < M) atomicAdd(dgate + (size_t)(b_first + 1) * gate_stride + c0 + c, g1);
+  red[mq * 64 + c] = s;
+  red[256 + mq * 64 + c] = g0;
+  red[512 + mq * 64 + c] = g1;
+  __syncthreads();
+  if (t < 64) {
+    const float ss = red[t] + red[64 + t] + red[128 + t] + red[192 + t];
+    const float s0 = red[256 + t] + red[320 + t] + red[384 + t] + red[448 + t];
+    const float s1 = red[512 + t] + red[576 + t] + red[640 + t] + red[704 + t];
+    if (dbias) atomicAdd(dbias + c0 + t, ss);
+    atomicAdd(dgate + (size_t)b_first * gate_stride + c0 + t, s0);
+    if (split < 64 && m0 + split < M) atomicAdd(dgate + (size_t)(b_first + 1) * gate_stride + c0 + t, s1);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Backward of  h = (LN(x; eps) [* w]) * (1 + scale[b]) + shift[b]   (ln_modulate_kernel / ln_weight_kernel).
-// One warp per row, rows of a CTA all belong to one sample (grid.y = sample), 64 rows per CTA.
-//   dshift[b] += sum g ; dscale[b] += sum g * y ; dw += sum g (1+scale) xhat ; dx (+)= rstd (dxh - mean(dxh) - xhat mean(dxh xhat))
+// Backward of  h = (LN(x; eps) [* w]) * (1 + scale[b]) + shift[b]   (ln_modulate_kernel / ln_weight_kernel), two kernels:
+//  rows:  one warp per row:  dx (+)= rstd (dxh - mean(dxh) - xhat mean(dxh xhat)),  dxh = g (1+scale) w;  keeps (mean, rstd)
+//  cols:  64-column x 128-row tiles:  dshift[b] += sum g ; dscale[b] += sum g xhat w ; dw += sum g (1+scale) xhat
+// (the fused single-kernel version needed 96 accumulator registers per lane -> 255 registers, 8 warps per SM)
 // ---------------------------------------------------------------------------------------------------------------
-template <typename TG, bool HAS_MOD, bool HAS_W>
-__global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const float* __restrict__ x, const TG* __restrict__ dh,
-                                                              const float* __restrict__ lnw,
-                                                              const float* __restrict__ scale, int mod_stride,
-                                                              int rows_in, int row_off, int rows_out, float eps,
-                                                              float* __restrict__ dx, int accumulate,
-                                                              float* __restrict__ dshift, float* __restrict__ dscale,
-                                                              float* __restrict__ dlnw) {
+template <typename TG>
+__device__ __forceinline__ void load4_f32(const TG* p, float* o);
+template <>
+__device__ __forceinline__ void load4_f32<float>(const float* p, float* o) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void load4_f32<__nv_bfloat16>(const __nv_bfloat16* p, float* o) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+template <typename TG>
+__global__ void __launch_bounds__(256) ln_bwd_rows_kernel(const float* __restrict__ x, const TG* __restrict__ dh,
+                                                          const float* __restrict__ lnw, const float* __restrict__ scale,
+                                                          int mod_stride, int rows_in, int row_off, int rows_out, float eps,
+                                                          float* __restrict__ dx, int accumulate,
+                                                          float2* __restrict__ stats) {
   constexpr int D = 1024, PER = 32;
-  __shared__ float s_acc[3 * D];
-  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 3 * D; i += 256) s_acc[i] = 0.f;
-  __syncthreads();
-  float a_sh[HAS_MOD ? PER : 1], a_sc[HAS_MOD ? PER : 1], a_w[HAS_W ? PER : 1];
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows_out) return;
+  const size_t xrow = ((size_t)b * rows_in + row_off + r) * D;
+  const TG* gr = dh + ((size_t)b * rows_out + r) * D;
+  float v[PER], g[PER];
+  float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < (HAS_MOD ? PER : 1); i++) { a_sh[i] = 0.f; a_sc[i] = 0.f; }
+  for (int i = 0; i < PER / 4; i++) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 t4 = *reinterpret_cast<const float4*>(x + xrow + c);
+    v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+    s += t4.x + t4.y + t4.z + t4.w;
+    load4_f32<TG>(gr + c, g + 4 * i);
+  }
+  const float mean = wsum(s) * (1.0f / D);
+  float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < (HAS_W ? PER : 1); i++) a_w[i] = 0.f;
-  const int r_end = min(rows_out, (int)(blockIdx.x + 1) * 64);
-  for (int r = blockIdx.x * 64 + warp; r < r_end; r += 8) {
-    const size_t xrow = ((size_t)b * rows_in + row_off + r) * D;
-    const TG* gr = dh + ((size_t)b * rows_out + r) * D;
-    float v[PER], g[PER];
-    float s = 0.f;
+  for (int i = 0; i < PER; i++) { v[i] -= mean; q += v[i] * v[i]; }
+  const float rstd = rsqrtf(wsum(q) * (1.0f / D) + eps);
+  if (lane == 0) stats[(size_t)b * rows_out + r] = make_float2(mean, rstd);
+  float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER / 4; i++) {
-      const int c = (i * 32 + lane) * 4;
-      const float4 t4 = *reinterpret_cast<const float4*>(x + xrow + c);
-      v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
-      s += t4.x + t4.y + t4.z + t4.w;
+  for (int i = 0; i < PER / 4; i++) {
+    const int c = (i * 32 + lane) * 4;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), w4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (scale) s4 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride + c));
+    if (lnw) w4 = __ldg(reinterpret_cast<const float4*>(lnw + c));
+    const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-      for (int e = 0; e < 4; e++) g[4 * i + e] = to_f(gr[c + e]);
-    }
-    const float mean = wsum(s) * (1.0f / D);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; i++) { v[i] -= mean; q += v[i] * v[i]; }
-    const float rstd = rsqrtf(wsum(q) * (1.0f / D) + eps);
-    float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER / 4; i++) {
-      const int c = (i * 32 + lane) * 4;
-      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), w4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (HAS_MOD) s4 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride + c));
-      if (HAS_W) w4 = __ldg(reinterpret_cast<const float4*>(lnw + c));
-      const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int k = 4 * i + e;
-        const float xh = v[k] * rstd;
-        const float gg = g[k];
-        if (HAS_MOD) { a_sh[k] += gg; a_sc[k] += gg * xh * wv[e]; }
-        const float dyv = gg * (1.0f + sv[e]);
-        if (HAS_W) a_w[k] += dyv * xh;
-        const float dxh = dyv * wv[e];
-        v[k] = xh;   // keep xhat
-        g[k] = dxh;  // keep dxhat
-        m1 += dxh;
-        m2 += dxh * xh;
-      }
-    }
-    m1 = wsum(m1) * (1.0f / D);
-    m2 = wsum(m2) * (1.0f / D);
-#pragma unroll
-    for (int i = 0; i < PER / 4; i++) {
-      const int c = (i * 32 + lane) * 4;
-      float4 o;
-      o.x = rstd * (g[4 * i] - m1 - v[4 * i] * m2);
-      o.y = rstd * (g[4 * i + 1] - m1 - v[4 * i + 1] * m2);
-      o.z = rstd * (g[4 * i + 2] - m1 - v[4 * i + 2] * m2);
-      o.w = rstd * (g[4 * i + 3] - m1 - v[4 * i + 3] * m2);
-      float4* dst = reinterpret_cast<float4*>(dx + xrow + c);
-      if (accumulate) {
-        const float4 p = *dst;
-        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-      }
-      *dst = o;
+    for (int e = 0; e < 4; e++) {
+      const int k = 4 * i + e;
+      const float xh = v[k] * rstd;
+      const float dxh = g[k] * (1.0f + sv[e]) * wv[e];
+      v[k] = xh;
+      g[k] = dxh;
+      m1 += dxh;
+      m2 += dxh * xh;
     }
   }
-  if (HAS_MOD || HAS_W) {
+  m1 = wsum(m1) * (1.0f / D);
+  m2 = wsum(m2) * (1.0f / D);
 #pragma unroll
-    for (int i = 0; i < PER / 4; i++) {
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int c = (i * 32 + lane) * 4 + e, k = 4 * i + e;
-        if (HAS_MOD) { atomicAdd(s_acc + c, a_sh[k]); atomicAdd(s_acc + D + c, a_sc[k]); }
-        if (HAS_W) atomicAdd(s_acc + 2 * D + c, a_w[k]);
-      }
+  for (int i = 0; i < PER / 4; i++) {
+    const int c = (i * 32 + lane) * 4;
+    float4 o;
+    o.x = rstd * (g[4 * i] - m1 - v[4 * i] * m2);
+    o.y = rstd * (g[4 * i + 1] - m1 - v[4 * i + 1] * m2);
+    o.z = rstd * (g[4 * i + 2] - m1 - v[4 * i + 2] * m2);
+    o.w = rstd * (g[4 * i + 3] - m1 - v[4 * i + 3] * m2);
+    float4* dst = reinterpret_cast<float4*>(dx + xrow + c);
+    if (accumulate) {
+      const float4 p = *dst;
+      o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < D; c += 256) {
-      if (HAS_MOD) {
-        atomicAdd(dshift + (size_t)b * mod_stride + c, s_acc[c]);
-        atomicAdd(dscale + (size_t)b * mod_stride + c, s_acc[D + c]);
-      }
-      if (HAS_W) atomicAdd(dlnw + c, s_acc[2 * D + c]);
+    *dst = o;
+  }
+}
+
+template <typename TG>
+__global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const float* __restrict__ x, const TG* __restrict__ dh,
+                                                          const float* __restrict__ lnw, const float* __restrict__ scale,
+                                                          int mod_stride, int rows_in, int row_off, int rows_out,
+                                                          const float2* __restrict__ stats, float* __restrict__ dshift,
+                                                          float* __restrict__ dscale, float* __restrict__ dlnw) {
+  constexpr int D = 1024, ROWS = 128;
+  __shared__ float red[3 * 4 * 64];
+  const int b = blockIdx.z, c = blockIdx.x * 64 + (threadIdx.x & 63), rq = threadIdx.x >> 6;
+  const int r0 = blockIdx.y * ROWS;
+  const float w = lnw ? __ldg(lnw + c) : 1.0f;
+  const float sc1 = scale ? 1.0f + __ldg(scale + (size_t)b * mod_stride + c) : 1.0f;
+  float a0 = 0.f, a1 = 0.f;
+  const int r_end = min(rows_out, r0 + ROWS);
+#pragma unroll 4
+  for (int r = r0 + rq; r < r_end; r += 4) {
+    const float2 st = __ldg(stats + (size_t)b * rows_out + r);
+    const float g = to_f(dh[((size_t)b * rows_out + r) * D + c]);
+    const float xh = (x[((size_t)b * rows_in + row_off + r) * D + c] - st.x) * st.y;
+    a0 += g;
+    a1 += g * xh;
+  }
+  red[rq * 64 + (threadIdx.x & 63)] = a0;
+  red[256 + rq * 64 + (threadIdx.x & 63)] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int t = threadIdx.x;
+    const float sg = red[t] + red[64 + t] + red[128 + t] + red[192 + t];
+    const float sgx = red[256 + t] + red[320 + t] + red[384 + t] + red[448 + t];
+    if (dshift) {
+      atomicAdd(dshift + (size_t)b * mod_stride + c, sg);
+      atomicAdd(dscale + (size_t)b * mod_stride + c, sgx * w);  // sum g * y, y = xhat * w
     }
+    if (dlnw) atomicAdd(dlnw + c, sgx * sc1);                     // sum g (1 + scale) xhat
   }
 }
 
@@ -408,9 +459,10 @@ __global__ void pos_embed_bwd_kernel(const float* __restrict__ dx, float* __rest
 // AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments), fp32 master weights
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                             float bc1, float bc2_sqrt, float grad_scale) {
+                             float bc1, float bc2_sqrt, float grad_scale, const float* __restrict__ grad_scale_dev) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (grad_scale_dev) grad_scale *= __ldg(grad_scale_dev);  // e.g. the clip factor, computed on the device
   const float gi = g[i] * grad_scale;
   const float mi = b1 * m[i] + (1.0f - b1) * gi;
   const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
@@ -432,10 +484,22 @@ int transpose_to_bf16(const void* in, int in_is_f32, int ldi, int B, int rows_in
   const int M = B * rows_out, Mp = (M + 63) / 64 * 64;
   dim3 grid(Mp / 64, C / 64);
   if (in_is_f32)
-    transpose_kernel<float><<<grid, 256, 0, st>>>((const float*)in, ldi, rows_in, row_off, rows_out, M, Mp, out, colsum);
+    transpose_kernel<float><<<grid, 256, 0, st>>>((const float*)in, ldi, rows_in, row_off, rows_out, M, Mp, out, colsum,
+                                                  nullptr, C, 0, 0, 0);
   else
     transpose_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, ldi, rows_in, row_off, rows_out, M,
-                                                          Mp, out, colsum);
+                                                          Mp, out, colsum, nullptr, C, 0, 0, 0);
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+// batch x [M, C] fp32 (matrix i at in + i * in_bstride) -> bf16 copies [batch, M, C] and/or transposed [batch, C, M]
+int cast_transpose_f32(const float* in, long long in_bstride, int batch, int M, int C, __nv_bfloat16* out_rm,
+                       __nv_bfloat16* outT, cudaStream_t st) {
+  DGS_REQUIRE(M % 64 == 0 && C % 64 == 0 && outT != nullptr, "cast_transpose: need M, C multiples of 64 and outT");
+  dim3 grid(M / 64, C / 64, batch);
+  transpose_kernel<float><<<grid, 256, 0, st>>>(in, C, M, 0, M, M, M, outT, nullptr, out_rm, C, (size_t)in_bstride,
+                                                (size_t)M * C, (size_t)M * C);
   DGS_POST_LAUNCH();
   return DGS_OK;
 }
@@ -452,24 +516,34 @@ int gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, int gat
 
 int ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* lnw, const float* scale, int mod_stride,
                     int B, int rows_in, int row_off, int rows_out, int D, float eps, float* dx, int accumulate,
-                    float* dshift, float* dscale, float* dlnw, cudaStream_t st) {
+                    float* dshift, float* dscale, float* dlnw, float* stats /* scratch: 2 * B * rows_out floats */,
+                    cudaStream_t st) {
   DGS_REQUIRE(D == 1024, "ln_modulate_bwd: width %d not supported (1024 only)", D);
   DGS_REQUIRE((scale != nullptr) == (dshift != nullptr && dscale != nullptr), "ln_modulate_bwd: scale/dshift/dscale mismatch");
   DGS_REQUIRE((lnw != nullptr) == (dlnw != nullptr), "ln_modulate_bwd: lnw/dlnw mismatch");
-  dim3 grid((rows_out + 63) / 64, B);
-#define LNB(TG, MOD, HW)                                                                                              \
-  ln_modulate_bwd_kernel<TG, MOD, HW><<<grid, 256, 0, st>>>(x, (const TG*)dh, lnw, scale, mod_stride, rows_in, row_off, \
-                                                            rows_out, eps, dx, accumulate, dshift, dscale, dlnw)
-  const bool mod = scale != nullptr, hw = lnw != nullptr;
+  DGS_REQUIRE(stats != nullptr, "ln_modulate_bwd: stats scratch is NULL");
+  float2* s2 = reinterpret_cast<float2*>(stats);
+  const dim3 grid_r((rows_out + 7) / 8, B), grid_c(D / 64, (rows_out + 127) / 128, B);
+  const bool cols = dshift != nullptr || dlnw != nullptr;
   if (dh_is_f32) {
-    if (mod && hw) LNB(float, true, true); else if (mod) LNB(float, true, false);
-    else if (hw) LNB(float, false, true); else LNB(float, false, false);
+    ln_bwd_rows_kernel<float><<<grid_r, 256, 0, st>>>(x, (const float*)dh, lnw, scale, mod_stride, rows_in, row_off,
+                                                      rows_out, eps, dx, accumulate, s2);
+    DGS_POST_LAUNCH();
+    if (cols) {
+      ln_bwd_cols_kernel<float><<<grid_c, 256, 0, st>>>(x, (const float*)dh, lnw, scale, mod_stride, rows_in, row_off,
+                                                        rows_out, s2, dshift, dscale, dlnw);
+      DGS_POST_LAUNCH();
+    }
   } else {
-    if (mod && hw) LNB(__nv_bfloat16, true, true); else if (mod) LNB(__nv_bfloat16, true, false);
-    else if (hw) LNB(__nv_bfloat16, false, true); else LNB(__nv_bfloat16, false, false);
+    ln_bwd_rows_kernel<__nv_bfloat16><<<grid_r, 256, 0, st>>>(x, (const __nv_bfloat16*)dh, lnw, scale, mod_stride,
+                                                              rows_in, row_off, rows_out, eps, dx, accumulate, s2);
+    DGS_POST_LAUNCH();
+    if (cols) {
+      ln_bwd_cols_kernel<__nv_bfloat16><<<grid_c, 256, 0, st>>>(x, (const __nv_bfloat16*)dh, lnw, scale, mod_stride,
+                                                                rows_in, row_off, rows_out, s2, dshift, dscale, dlnw);
+      DGS_POST_LAUNCH();
+    }
   }
-#undef LNB
-  DGS_POST_LAUNCH();
   return DGS_OK;
 }
 
@@ -522,11 +596,11 @@ int pos_embed_bwd(const float* dx, float* dpos, int B, int G, int N, int D, cuda
 }
 
 int adamw_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
-               int step, float grad_scale, cudaStream_t st) {
+               int step, float grad_scale, const float* grad_scale_dev, cudaStream_t st) {
   if (n == 0) return DGS_OK;
   const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
   adamw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2),
-                                                            grad_scale);
+                                                            grad_scale, grad_scale_dev);
   DGS_POST_LAUNCH();
   return DGS_OK;
 }

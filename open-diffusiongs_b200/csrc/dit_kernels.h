@@ -80,7 +80,7 @@ int gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, int gat
              int C, __nv_bfloat16* dy, __nv_bfloat16* dyT, float* dgate, float* dbias, cudaStream_t st);
 int ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* lnw, const float* scale, int mod_stride,
                     int B, int rows_in, int row_off, int rows_out, int D, float eps, float* dx, int accumulate,
-                    float* dshift, float* dscale, float* dlnw, cudaStream_t st);
+                    float* dshift, float* dscale, float* dlnw, float* stats /* scratch [B*rows_out*2] */, cudaStream_t st);
 // dout [B, ldo] (row stride ldo >= N): rows n of this linear are columns [0, N) of dout
 int skinny_linear_bwd(const float* in, const float* W, const float* dout, int ldo, int B, int N, int K, int act_in,
                       float* dW, float* dbias, float* da, cudaStream_t st);
@@ -93,6 +93,8 @@ int tiny_linear_bwd(const float* dy, const float* W, const __nv_bfloat16* h3, __
                     int N, int K, cudaStream_t st);
 int pos_embed_bwd(const float* dx, float* dpos, int B, int G, int N, int D, cudaStream_t st);
 int adamw_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
-               int step, float grad_scale, cudaStream_t st);
+               int step, float grad_scale, const float* grad_scale_dev, cudaStream_t st);
+int cast_transpose_f32(const float* in, long long in_bstride, int batch, int M, int C, __nv_bfloat16* out_rm,
+                       __nv_bfloat16* outT, cudaStream_t st);
 
 }  // namespace dgs

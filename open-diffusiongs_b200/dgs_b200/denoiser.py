@@ -140,10 +140,8 @@ class DGSDenoiser(nn.Module):
     def _pack_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def packed_weights(self, force=False):
-        key = self._pack_key()
-        if self._packed is not None and self._packed_key == key and not force:
-            return self._packed
+    def _pack_dict(self, skip=()):
+        """fp32 master parameters -> {field of dgs_dit_weights: tensor}; `skip` = fields somebody else fills."""
         bf = lambda t: t.detach().to(torch.bfloat16).contiguous()  # noqa: E731
 
         def split(t):  # split-bf16 weight [n, 3k] = [hi | hi | lo]  (see include/dgs_b200.h)
@@ -156,22 +154,29 @@ class DGSDenoiser(nn.Module):
         T = self.transformer
         stack = lambda get: torch.stack([get(b).detach() for b in T])  # noqa: E731
         heads = (self.upsampler, self.image_token_decoder)
-        adaln_w = torch.cat([b.adaLN_modulation[1].weight.detach() for b in T] +
-                            [h.adaLN_modulation[1].weight.detach() for h in heads], dim=0)
-        adaln_b = torch.cat([b.adaLN_modulation[1].bias.detach() for b in T] +
-                            [h.adaLN_modulation[1].bias.detach() for h in heads], dim=0)
-        t = dict(
-            tokenizer_w=split(self.image_tokenizer[1].weight), pos_embed=f32(self.gaussians_pos_embedding),
-            in_ln_w=f32(self.transformer_input_layernorm.weight),
-            t0_w=f32(self.t_embedder.mlp[0].weight), t0_b=f32(self.t_embedder.mlp[0].bias),
-            t2_w=f32(self.t_embedder.mlp[2].weight), t2_b=f32(self.t_embedder.mlp[2].bias),
-            adaln_w=f32(adaln_w), adaln_b=f32(adaln_b),
-            qkv_w=bf(stack(lambda b: b.attn.qkv.weight)), qkv_b=f32(stack(lambda b: b.attn.qkv.bias)),
-            proj_w=bf(stack(lambda b: b.attn.proj.weight)), proj_b=f32(stack(lambda b: b.attn.proj.bias)),
-            fc1_w=bf(stack(lambda b: b.mlp.fc1.weight)), fc1_b=f32(stack(lambda b: b.mlp.fc1.bias)),
-            fc2_w=bf(stack(lambda b: b.mlp.fc2.weight)), fc2_b=f32(stack(lambda b: b.mlp.fc2.bias)),
-            ups_ln_w=f32(self.upsampler.layernorm.weight), ups_w=split(self.upsampler.linear.weight),
-            dec_ln_w=f32(self.image_token_decoder.layernorm.weight), dec_w=split(self.image_token_decoder.linear.weight))
+        make = dict(
+            tokenizer_w=lambda: split(self.image_tokenizer[1].weight), pos_embed=lambda: f32(self.gaussians_pos_embedding),
+            in_ln_w=lambda: f32(self.transformer_input_layernorm.weight),
+            t0_w=lambda: f32(self.t_embedder.mlp[0].weight), t0_b=lambda: f32(self.t_embedder.mlp[0].bias),
+            t2_w=lambda: f32(self.t_embedder.mlp[2].weight), t2_b=lambda: f32(self.t_embedder.mlp[2].bias),
+            adaln_w=lambda: f32(torch.cat([b.adaLN_modulation[1].weight.detach() for b in T] +
+                                          [h.adaLN_modulation[1].weight.detach() for h in heads], dim=0)),
+            adaln_b=lambda: f32(torch.cat([b.adaLN_modulation[1].bias.detach() for b in T] +
+                                          [h.adaLN_modulation[1].bias.detach() for h in heads], dim=0)),
+            qkv_w=lambda: bf(stack(lambda b: b.attn.qkv.weight)), qkv_b=lambda: f32(stack(lambda b: b.attn.qkv.bias)),
+            proj_w=lambda: bf(stack(lambda b: b.attn.proj.weight)), proj_b=lambda: f32(stack(lambda b: b.attn.proj.bias)),
+            fc1_w=lambda: bf(stack(lambda b: b.mlp.fc1.weight)), fc1_b=lambda: f32(stack(lambda b: b.mlp.fc1.bias)),
+            fc2_w=lambda: bf(stack(lambda b: b.mlp.fc2.weight)), fc2_b=lambda: f32(stack(lambda b: b.mlp.fc2.bias)),
+            ups_ln_w=lambda: f32(self.upsampler.layernorm.weight), ups_w=lambda: split(self.upsampler.linear.weight),
+            dec_ln_w=lambda: f32(self.image_token_decoder.layernorm.weight),
+            dec_w=lambda: split(self.image_token_decoder.linear.weight))
+        return {k: fn() for k, fn in make.items() if k not in skip}
+
+    def packed_weights(self, force=False):
+        key = self._pack_key()
+        if self._packed is not None and self._packed_key == key and not force:
+            return self._packed
+        t = self._pack_dict()
         c = self.cfg
         w = DitWeights(width=c.width, heads=c.width // c.dim_heads, layers=c.num_layers, patch=c.patch_size,
                        n_gaussians=c.n_gaussians, mlp_hidden=4 * c.width)

@@ -84,17 +84,36 @@ class DitTrainer:
         g.dec_adaln_w, g.dec_adaln_b = ptr(d.adaLN_modulation[1].weight), ptr(d.adaLN_modulation[1].bias)
         return g
 
+    _BIG = dict(qkv_w=lambda b: b.attn.qkv.weight, proj_w=lambda b: b.attn.proj.weight,
+                fc1_w=lambda b: b.mlp.fc1.weight, fc2_w=lambda b: b.mlp.fc2.weight)
+
     def refresh_weights(self):
-        """fp32 master -> the bf16 stacks the forward reads + the transposed bf16 stacks the dgrad GEMMs read."""
+        """fp32 master -> the bf16 stacks the forward reads + the transposed bf16 stacks the dgrad GEMMs read.
+        The packed tensors are allocated once and updated IN PLACE (the dgs_dit_weights struct keeps its pointers):
+        the four big per-block matrices by one fused cast+transpose launch each (dgs_cast_transpose_f32, batched over
+        the blocks through the master arena's block stride), the small vectors / split-bf16 end matrices by torch copies."""
         m = self.model
-        m.packed_weights(force=True)
         T = m.transformer
-        tr = lambda get: torch.stack([get(b).detach().t() for b in T]).to(torch.bfloat16).contiguous()  # noqa: E731
-        self._wT_keep = dict(
-            qkv_wT=tr(lambda b: b.attn.qkv.weight), proj_wT=tr(lambda b: b.attn.proj.weight),
-            fc1_wT=tr(lambda b: b.mlp.fc1.weight), fc2_wT=tr(lambda b: b.mlp.fc2.weight),
-            dec_wT=m.image_token_decoder.linear.weight.detach().t().to(torch.bfloat16).contiguous(),
-            ups_w=m.upsampler.linear.weight.detach().float().contiguous())
+        dev = self.master.device
+        first = m._packed is None or getattr(self, "_wT_keep", None) is None
+        if first:
+            m.packed_weights(force=True)
+            self._wT_keep = {k + "T": torch.empty(len(T), get(T[0]).shape[1], get(T[0]).shape[0], dtype=torch.bfloat16,
+                                                  device=dev) for k, get in self._BIG.items()}
+        w, t = m._packed
+        L = _lib.lib()
+        stride = int(self._grads.layer_stride)  # master and gradient arenas share one layout
+        with torch.cuda.device(dev):
+            for k, get in self._BIG.items():
+                p0 = get(T[0])
+                check(L.dgs_cast_transpose_f32(p0.data_ptr(), stride, len(T), p0.shape[0], p0.shape[1], t[k].data_ptr(),
+                                               self._wT_keep[k + "T"].data_ptr(), _stream(dev)))
+        if not first:
+            for k, v in m._pack_dict(skip=tuple(self._BIG)).items():
+                t[k].copy_(v)
+        m._packed_key = m._pack_key()
+        self._wT_keep["dec_wT"] = m.image_token_decoder.linear.weight.detach().t().to(torch.bfloat16).contiguous()
+        self._wT_keep["ups_w"] = m.upsampler.linear.weight.detach().float().contiguous()
         wT = DitWeightsT()
         for k, v in self._wT_keep.items():
             setattr(wT, k, v.data_ptr())
@@ -117,13 +136,17 @@ class DitTrainer:
         """all-reduce (mean) -> clip at `clip` (Lightning gradient_clip_val) -> fused AdamW -> refresh bf16 weights."""
         if allreduce:
             self.arena.allreduce_mean_()
-        norm = self.arena.clip_grad_norm_(self.clip) if self.clip else None
+        norm = scale = None
+        if self.clip:  # torch clip_grad_norm_ semantics; the factor stays on the device and is applied inside AdamW
+            norm = torch.linalg.vector_norm(self.arena.flat)
+            scale = torch.clamp(self.clip / (norm + 1e-6), max=1.0).reshape(1).float()
         self.steps += 1
         dev = self.master.device
         with torch.cuda.device(dev):
             check(_lib.lib().dgs_adamw_step(self.master.data_ptr(), self.arena.flat.data_ptr(), self.exp_avg.data_ptr(),
                                             self.exp_avg_sq.data_ptr(), self.master.numel(), self.lr, self.betas[0],
-                                            self.betas[1], self.eps, self.weight_decay, self.steps, 1.0, _stream(dev)))
+                                            self.betas[1], self.eps, self.weight_decay, self.steps, 1.0,
+                                            None if scale is None else scale.data_ptr(), _stream(dev)))
         self.refresh_weights()
         return norm
 

@@ -128,6 +128,7 @@ def test_ln_modulate_backward():
     mod = torch.randn(B, 6 * D, device=DEV, generator=g).requires_grad_(True)
     lnw = torch.randn(D, device=DEV, generator=g).requires_grad_(True)
     dh = torch.randn(B, R, D, device=DEV, generator=g).to(torch.bfloat16)
+    stats = torch.empty(B * R * 2, device=DEV)
     for w_, eps, f32 in ((None, 1e-6, False), (lnw, 1e-5, False), (lnw, 1e-5, True)):
         for t in (x, mod, lnw):
             t.grad = None
@@ -139,7 +140,7 @@ def test_ln_modulate_backward():
         dh_in = dh.float().contiguous() if f32 else dh
         _lib.check(_lib.lib().dgs_ln_modulate_bwd(ptr(x), ptr(dh_in), int(f32), ptr(w_), mod[:, D:].data_ptr(), 6 * D, B, R,
                                                   D, eps, ptr(dx), 1, ptr(dmod), dmod[:, D:].data_ptr(),
-                                                  ptr(dw) if w_ is not None else None, stream()))
+                                                  ptr(dw) if w_ is not None else None, ptr(stats), stream()))
         assert rel(dx - 1, x.grad) < 1e-4
         assert rel(dmod[:, :2 * D], mod.grad[:, :2 * D]) < 1e-4
         if w_ is not None:
@@ -151,7 +152,7 @@ def test_ln_modulate_backward():
     dx = torch.zeros(B, R, D, device=DEV)
     dw = torch.zeros(D, device=DEV)
     _lib.check(_lib.lib().dgs_ln_modulate_bwd(ptr(x), ptr(dh), 0, ptr(lnw), None, 0, B, R, D, 1e-5, ptr(dx), 0, None, None,
-                                              ptr(dw), stream()))
+                                              ptr(dw), ptr(stats), stream()))
     assert rel(dx, x.grad) < 1e-4 and rel(dw, lnw.grad) < 1e-4
 
 
@@ -187,12 +188,13 @@ def test_adamw_matches_torch():
     ref_p = torch.nn.Parameter(p.clone())
     opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.01)
     m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    two = torch.full((1,), 2.0, device=DEV)  # host scale 0.5 x device scale 2.0 = 1
     for step in range(1, 4):
         grad = torch.randn(n, device=DEV, generator=g)
         ref_p.grad = grad.clone()
         opt.step()
-        _lib.check(_lib.lib().dgs_adamw_step(ptr(p), ptr(grad), ptr(m), ptr(v), n, 1e-3, 0.9, 0.99, 1e-8, 0.01, step, 1.0,
-                                             stream()))
+        _lib.check(_lib.lib().dgs_adamw_step(ptr(p), ptr(grad), ptr(m), ptr(v), n, 1e-3, 0.9, 0.99, 1e-8, 0.01, step, 0.5,
+                                             ptr(two), stream()))
     assert rel(p, ref_p.data) < 1e-6
 
 
