@@ -47,8 +47,6 @@ struct DitWorkspace {
 
 // Everything the backward needs from the forward (training mode), plus the backward's own scratch.  Per-layer tensors
 // are stacked along a leading L axis.  M = B*N rows, Mp = round_up(M, 64), Mt = B*T image-token rows.
-struct SkinnyBwdSeg { size_t row0; int rows; float* dW; float* db; };
-
 struct TrainState {
   float* x_pre;             // [M, w]      assembled tokens before the input LayerNorm
   float* x_all;             // [L+1][M, w] residual stream entering block l (x_all[L] = final)
@@ -427,19 +425,12 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
   float* dsc = ts.dcond;                       // d silu(c), then dc
   float* dt1 = ts.dcond + (size_t)B * D;       // d temb1, then d pre1
   float* pre1 = ts.dcond + (size_t)2 * B * D;  // t0 pre-activation (recomputed)
-  {  // one launch per adaLN linear (L blocks + 2 heads): their gradient tensors are separate parameters
-    SkinnyBwdSeg seg;
-    for (int l = 0; l < L; l++) {
-      seg = {(size_t)l * 6 * D, 6 * D, g->adaln_w + l * LS, g->adaln_b + l * LS};
-      DGS_TRY(skinny_linear_bwd(ws.c, w->adaln_w + seg.row0 * D, ts.dmod + seg.row0, mod_stride, B, seg.rows, D, 1, seg.dW,
-                                seg.db, dsc, st));
-    }
-    seg = {(size_t)L * 6 * D, 2 * D, g->ups_adaln_w, g->ups_adaln_b};
-    DGS_TRY(skinny_linear_bwd(ws.c, w->adaln_w + seg.row0 * D, ts.dmod + seg.row0, mod_stride, B, seg.rows, D, 1, seg.dW,
-                              seg.db, dsc, st));
-    seg = {(size_t)L * 6 * D + 2 * D, 2 * D, g->dec_adaln_w, g->dec_adaln_b};
-    DGS_TRY(skinny_linear_bwd(ws.c, w->adaln_w + seg.row0 * D, ts.dmod + seg.row0, mod_stride, B, seg.rows, D, 1, seg.dW,
-                              seg.db, dsc, st));
+  {  // ONE launch over the stacked adaLN linears (L blocks + 2 heads); their gradients are separate parameters
+    SkinnySegs segs;
+    segs.seg_rows = 6 * D; segs.n_seg = L; segs.seg_stride = (long long)LS; segs.dW0 = g->adaln_w; segs.db0 = g->adaln_b;
+    segs.tail_rows[0] = 2 * D; segs.tail_dW[0] = g->ups_adaln_w; segs.tail_db[0] = g->ups_adaln_b;
+    segs.tail_rows[1] = 2 * D; segs.tail_dW[1] = g->dec_adaln_w; segs.tail_db[1] = g->dec_adaln_b;
+    DGS_TRY(skinny_linear_bwd_segs(ws.c, w->adaln_w, ts.dmod, mod_stride, B, mod_stride, D, 1, segs, dsc, st));
   }
   DGS_TRY(silu_bwd_inplace(dsc, ws.c, B * D, st));
   DGS_TRY(skinny_linear_bwd(ws.temb1, w->t2_w, dsc, D, B, D, D, 0, g->t2_w, g->t2_b, dt1, st));

@@ -296,17 +296,33 @@ __global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const float* __restric
 //   dW[n, k] = sum_b dout[b, n] a[b, k]     dbias[n] = sum_b dout[b, n]     da[b, k] += sum_n dout[b, n] W[n, k]
 // One CTA per 256 output rows n; a thread owns 4 consecutive k.  W is read once, dW written once.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SKB_MAXB = 8, SKB_ROWS = 256;
+constexpr int SKB_MAXB = 8, SKB_ROWS = 128;
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
 __global__ void __launch_bounds__(256) skinny_linear_bwd_kernel(const float* __restrict__ in, const float* __restrict__ W,
                                                                 const float* __restrict__ dout, int ldo, int B, int N,
-                                                                int K, int act_in, float* __restrict__ dW,
-                                                                float* __restrict__ dbias, float* __restrict__ da) {
+                                                                int K, int act_in, SkinnySegs segs,
+                                                                float* __restrict__ da) {
   extern __shared__ float sm[];
   float* s_a = sm;               // [B, K]
   float* s_do = sm + B * K;      // [B, SKB_ROWS]
   const int n0 = blockIdx.x * SKB_ROWS, nrows = min(SKB_ROWS, N - n0);
+  // destination of this CTA's rows: regular segments (one per DiT block) then up to two tail segments (the heads)
+  float* dW;
+  float* dbias;
+  {
+    const int reg_rows = segs.seg_rows * segs.n_seg;
+    if (n0 < reg_rows) {
+      const int sg = n0 / segs.seg_rows, r0 = n0 - sg * segs.seg_rows;
+      dW = segs.dW0 + (size_t)sg * segs.seg_stride + (size_t)r0 * K;
+      dbias = segs.db0 ? segs.db0 + (size_t)sg * segs.seg_stride + r0 : nullptr;
+    } else {
+      int r0 = n0 - reg_rows, t = 0;
+      if (r0 >= segs.tail_rows[0]) { r0 -= segs.tail_rows[0]; t = 1; }
+      dW = segs.tail_dW[t] + (size_t)r0 * K;
+      dbias = segs.tail_db[t] ? segs.tail_db[t] + r0 : nullptr;
+    }
+  }
   for (int t = threadIdx.x; t < B * K; t += 256) {
     const float v = in[t];
     s_a[t] = act_in ? silu_f(v) : v;
@@ -319,7 +335,7 @@ __global__ void __launch_bounds__(256) skinny_linear_bwd_kernel(const float* __r
   if (dbias && threadIdx.x < nrows) {
     float s = 0.f;
     for (int b = 0; b < B; b++) s += s_do[b * SKB_ROWS + threadIdx.x];
-    dbias[n0 + threadIdx.x] = s;
+    dbias[threadIdx.x] = s;
   }
   for (int k = threadIdx.x * 4; k < K; k += 1024) {
     float acc[SKB_MAXB][4];
@@ -340,7 +356,7 @@ __global__ void __launch_bounds__(256) skinny_linear_bwd_kernel(const float* __r
           acc[b][0] += d * w4.x; acc[b][1] += d * w4.y; acc[b][2] += d * w4.z; acc[b][3] += d * w4.w;
         }
       }
-      *reinterpret_cast<float4*>(dW + (size_t)(n0 + r) * K + k) = g4;
+      *reinterpret_cast<float4*>(dW + (size_t)r * K + k) = g4;
     }
     if (da) {
 #pragma unroll
@@ -547,9 +563,12 @@ int ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* 
   return DGS_OK;
 }
 
-int skinny_linear_bwd(const float* in, const float* W, const float* dout, int ldo, int B, int N, int K, int act_in,
-                      float* dW, float* dbias, float* da, cudaStream_t st) {
+int skinny_linear_bwd_segs(const float* in, const float* W, const float* dout, int ldo, int B, int N, int K, int act_in,
+                           const SkinnySegs& segs, float* da, cudaStream_t st) {
   DGS_REQUIRE(B >= 1 && B <= SKB_MAXB && K % 4 == 0, "skinny_linear_bwd: bad shape B=%d K=%d (B <= 8)", B, K);
+  DGS_REQUIRE(segs.seg_rows % SKB_ROWS == 0 && segs.tail_rows[0] % SKB_ROWS == 0 &&
+                  segs.seg_rows * segs.n_seg + segs.tail_rows[0] + segs.tail_rows[1] == N,
+              "skinny_linear_bwd: segments must be multiples of %d rows and cover N", SKB_ROWS);
   const size_t smem = ((size_t)B * K + (size_t)B * SKB_ROWS) * sizeof(float);
   static bool configured = false;
   if (!configured) {
@@ -557,9 +576,19 @@ int skinny_linear_bwd(const float* in, const float* W, const float* dout, int ld
     configured = true;
   }
   DGS_REQUIRE(smem <= 96 * 1024, "skinny_linear_bwd: B*K too large");
-  skinny_linear_bwd_kernel<<<ceil_div(N, SKB_ROWS), 256, smem, st>>>(in, W, dout, ldo, B, N, K, act_in, dW, dbias, da);
+  skinny_linear_bwd_kernel<<<ceil_div(N, SKB_ROWS), 256, smem, st>>>(in, W, dout, ldo, B, N, K, act_in, segs, da);
   DGS_POST_LAUNCH();
   return DGS_OK;
+}
+
+int skinny_linear_bwd(const float* in, const float* W, const float* dout, int ldo, int B, int N, int K, int act_in,
+                      float* dW, float* dbias, float* da, cudaStream_t st) {
+  SkinnySegs segs;
+  segs.seg_rows = N; segs.n_seg = 1; segs.seg_stride = 0; segs.dW0 = dW; segs.db0 = dbias;
+  if (N % SKB_ROWS) {  // a single ragged segment: express it as a tail (no alignment requirement on the last one)
+    segs.seg_rows = 0; segs.n_seg = 0; segs.tail_rows[0] = 0; segs.tail_rows[1] = N; segs.tail_dW[1] = dW; segs.tail_db[1] = dbias;
+  }
+  return skinny_linear_bwd_segs(in, W, dout, ldo, B, N, K, act_in, segs, da, st);
 }
 
 int silu_bwd_inplace(float* d, const float* pre, int n, cudaStream_t st) {

@@ -81,6 +81,17 @@ int gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, int gat
 int ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* lnw, const float* scale, int mod_stride,
                     int B, int rows_in, int row_off, int rows_out, int D, float eps, float* dx, int accumulate,
                     float* dshift, float* dscale, float* dlnw, float* stats /* scratch [B*rows_out*2] */, cudaStream_t st);
+// Where the weight/bias gradient rows of a (stacked) skinny linear go: n_seg regular segments of seg_rows rows each
+// (segment i at dW0 + i*seg_stride floats, its bias gradient at db0 + i*seg_stride), then two tail segments.
+struct SkinnySegs {
+  int seg_rows = 0, n_seg = 0;
+  long long seg_stride = 0;
+  float* dW0 = nullptr; float* db0 = nullptr;
+  int tail_rows[2] = {0, 0};
+  float* tail_dW[2] = {nullptr, nullptr}; float* tail_db[2] = {nullptr, nullptr};
+};
+int skinny_linear_bwd_segs(const float* in, const float* W, const float* dout, int ldo, int B, int N, int K, int act_in,
+                           const SkinnySegs& segs, float* da, cudaStream_t st);
 // dout [B, ldo] (row stride ldo >= N): rows n of this linear are columns [0, N) of dout
 int skinny_linear_bwd(const float* in, const float* W, const float* dout, int ldo, int B, int N, int K, int act_in,
                       float* dW, float* dbias, float* da, cudaStream_t st);

@@ -64,6 +64,8 @@ struct GeomState {
   uint32_t* perm;      // sorted: Gaussian index at each depth rank
   uint32_t* tiles_sorted;  // tiles touched in depth-rank order
   uint32_t* offsets;       // inclusive scan of tiles_sorted
+  uint32_t* open_counts;   // phase B: open tiles touched per depth rank (0 for the near ranks) ...
+  uint32_t* open_offsets;  // ... and their inclusive scan
   uint32_t* view_meta;     // [NV][4] two-phase binning: {startA, startB, baseA, baseB} instance offsets per view
   uint32_t* totals;        // [4] {R, R_near, tiles not finished after phase A, -}
   Camera* cams;
@@ -83,6 +85,8 @@ struct GeomState {
     s.perm = c.take<uint32_t>(N);
     s.tiles_sorted = c.take<uint32_t>(N);
     s.offsets = c.take<uint32_t>(N);
+    s.open_counts = c.take<uint32_t>(N);
+    s.open_offsets = c.take<uint32_t>(N);
     s.view_meta = c.take<uint32_t>((size_t)NV * 4);
     s.totals = c.take<uint32_t>(4);
     s.cams = c.take<Camera>(NV);
@@ -126,6 +130,7 @@ struct ImgState {
   uint2* ranges_b;     // phase-B tile ranges (two-phase binning)
   float4* acc;         // per-pixel blend state between the phases: {C.r, C.g, C.b, T}
   uint32_t* contrib;   // entries visited so far | (finished << 31)
+  uint32_t* tile_open; // [views * tiles] 1 = the tile still has an unsaturated pixel after phase A
   static ImgState carve(void* base, int NV, int W, int H, size_t* total) {
     ImgState s;
     Carver c(base);
@@ -137,6 +142,7 @@ struct ImgState {
     s.ranges_b = c.take<uint2>(ntiles);
     s.acc = c.take<float4>(npix);
     s.contrib = c.take<uint32_t>(npix);
+    s.tile_open = c.take<uint32_t>(ntiles);
     if (total) *total = c.bytes();
     return s;
   }
@@ -561,6 +567,87 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(Problem pb, GeomState gs
   }
 }
 
+// Phase B of the two-phase binning only serves the tiles that are still OPEN after phase A (tile_open): per far rank,
+// count the open tiles of its rect (near ranks: 0) -- the scan of these counts gives the compact phase-B offsets.
+__global__ void __launch_bounds__(256) count_open_kernel(Problem pb, GeomState gs, const uint32_t* __restrict__ tile_open,
+                                                         int Pn) {
+  const int view = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= pb.P) return;
+  const size_t k = (size_t)view * pb.P + r;
+  uint32_t cnt = 0;
+  if (r >= Pn && gs.tiles_sorted[k]) {
+    const float4 g = gs.g0[(size_t)view * pb.P + gs.perm[k]];
+    int x0, y0, x1, y1;
+    tile_rect(g.x, g.y, __float_as_int(g.w), pb.gx, pb.gy, x0, y0, x1, y1);
+    const uint32_t* op = tile_open + (size_t)view * pb.tiles;
+    for (int y = y0; y < y1; y++)
+      for (int x = x0; x < x1; x++) cnt += op[y * pb.gx + x];
+  }
+  gs.open_counts[k] = cnt;
+}
+
+// phase-B emission: ranks [Pn, P), open tiles only, offsets = scan of count_open_kernel's counts
+__global__ void __launch_bounds__(256) emit_open_keys_kernel(Problem pb, GeomState gs, const uint32_t* __restrict__ tile_open,
+                                                             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                             int Pn) {
+  const int view = blockIdx.y;
+  const int r = Pn + blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool in_range = r < pb.P;
+  const size_t k = (size_t)view * pb.P + (in_range ? r : Pn);
+  const uint32_t cnt = in_range ? gs.open_counts[k] : 0;
+  uint32_t off = 0, id = 0;
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  if (cnt) {
+    off = gs.open_offsets[k] - cnt;  // inclusive scan
+    id = gs.perm[k];
+    const float4 g = gs.g0[(size_t)view * pb.P + id];
+    tile_rect(g.x, g.y, __float_as_int(g.w), pb.gx, pb.gy, x0, y0, x1, y1);
+  }
+  const uint32_t tile_base = (uint32_t)(view * pb.tiles);
+  const uint32_t* op = tile_open + (size_t)view * pb.tiles;
+  const int area = (x1 - x0) * (y1 - y0);
+  if (cnt && area < DUP_COOP_THRESHOLD) {
+    for (int y = y0; y < y1; y++)
+      for (int x = x0; x < x1; x++) {
+        const int t = y * pb.gx + x;
+        if (op[t]) {
+          keys[off] = tile_base + (uint32_t)t;
+          vals[off] = id;
+          off++;
+        }
+      }
+  }
+  unsigned big = __ballot_sync(0xffffffffu, cnt && area >= DUP_COOP_THRESHOLD);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    uint32_t o_ = __shfl_sync(0xffffffffu, off, src);
+    const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+    const int bx1 = __shfl_sync(0xffffffffu, x1, src);
+    const int barea = __shfl_sync(0xffffffffu, area, src);
+    const uint32_t bid = __shfl_sync(0xffffffffu, id, src);
+    const int w = bx1 - bx0;
+    for (int t0 = 0; t0 < barea; t0 += 32) {  // rect tiles in row-major order, 32 at a time, compacted by ballot
+      const int t = t0 + lane;
+      int tl = 0;
+      bool open = false;
+      if (t < barea) {
+        tl = (by0 + t / w) * pb.gx + bx0 + t % w;
+        open = op[tl] != 0;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, open);
+      if (open) {
+        const uint32_t pos = o_ + __popc(m & ((1u << lane) - 1u));
+        keys[pos] = tile_base + (uint32_t)tl;
+        vals[pos] = bid;
+      }
+      o_ += __popc(m);
+    }
+  }
+}
+
 // K5: tile ranges from the sorted keys (rasterizer_impl.cu:116-138)
 __global__ void tile_ranges_kernel(long long R, const uint32_t* __restrict__ keys, uint2* __restrict__ ranges) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -647,7 +734,10 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, Geo
       im.contrib[pix_g] = contributor | (done ? 0x80000000u : 0u);
     }
     const int unfinished = __syncthreads_or(!done);
-    if (threadIdx.x == 0 && unfinished) atomicAdd(gs.totals + 2, 1u);
+    if (threadIdx.x == 0) {
+      im.tile_open[tile_g] = unfinished ? 1u : 0u;
+      if (unfinished) atomicAdd(gs.totals + 2, 1u);
+    }
   }
   if (inside) {
     const size_t pid = (size_t)y * pb.W + x;
@@ -1139,7 +1229,7 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
   // phase A must be a real saving: at most half of the instances
   const bool split = may_split && R >= (1ll << 21) && 2ll * tot[1] <= R && tot[1] > 0;
   const long long RA = split ? (long long)tot[1] : R;
-  const long long RB = split ? R - RA : 0;
+  (void)0;  // (the far instance count R - RA is an upper bound only: phase B bins the open tiles)
   chunk_R[0] = RA;
   chunk_R[1] = 0;
 
@@ -1197,11 +1287,45 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
   DGS_CUDA_OK(cudaMemcpyAsync(&unfinished, gs.totals + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   DGS_CUDA_OK(cudaStreamSynchronize(st));
   if (unfinished == 0) return DGS_OK;
-  // ---- phase B: everything behind, continuing from the saved per-pixel state
+  // ---- phase B: everything behind the near ranks, for the OPEN tiles only, continuing from the saved per-pixel state.
+  // A tile that saturated in phase A never looks at its far entries, so they are neither counted, emitted nor sorted;
+  // an open tile gets every far Gaussian of its rect, in the same (depth, index) order as the single-pass list.
   {
-    int rc = bin_pass(RB, 2, Pn, pb.P, im.ranges_b, &bsb);
-    if (rc) return rc;
-    chunk_R[1] = RB;
+    uint32_t rb = 0;
+    {
+      ProfScope ps(st, PROF_RASTER_SCAN);
+      count_open_kernel<<<dim3(ceil_div(pb.P, 256), pb.NV), 256, 0, st>>>(pb, gs, im.tile_open, Pn);
+      DGS_LAUNCH_OK(st, debug);
+      DGS_CUDA_OK(cub::DeviceScan::InclusiveSum(gs.scan_temp, gs.scan_bytes, gs.open_counts, gs.open_offsets, (int)N, st));
+      DGS_CUDA_OK(cudaMemcpyAsync(&rb, gs.open_offsets + N - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      DGS_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    const long long RBo = (long long)rb;
+    size_t bbytes = 0;
+    BinState::carve(nullptr, RBo, &bbytes);
+    void* bbuf = bin_alloc(bbytes, bin_user);
+    if (!bbuf) { set_error("binning allocator returned NULL"); return DGS_ERR_ALLOC; }
+    bsb = BinState::carve(bbuf, RBo, nullptr);
+    DGS_CUDA_OK(cudaMemsetAsync(im.ranges_b, 0, ntiles * sizeof(uint2), st));
+    if (RBo > 0) {
+      {
+        ProfScope ps(st, PROF_RASTER_EMIT);
+        emit_open_keys_kernel<<<dim3(ceil_div(pb.P - Pn, 256), pb.NV), 256, 0, st>>>(pb, gs, im.tile_open, bsb.keys_in,
+                                                                                     bsb.vals_in, Pn);
+        DGS_LAUNCH_OK(st, debug);
+      }
+      {
+        ProfScope ps(st, PROF_RASTER_SORT);
+        DGS_CUDA_OK(cub::DeviceRadixSort::SortPairs(bsb.sort_temp, bsb.sort_bytes, bsb.keys_in, bsb.keys, bsb.vals_in,
+                                                    bsb.point_list, (int)RBo, 0, end_bit, st));
+      }
+      {
+        ProfScope ps(st, PROF_RASTER_RANGES);
+        tile_ranges_kernel<<<(unsigned)((RBo + 255) / 256), 256, 0, st>>>(RBo, bsb.keys, im.ranges_b);
+        DGS_LAUNCH_OK(st, debug);
+      }
+    }
+    chunk_R[1] = RBo;
     ProfScope ps(st, PROF_RASTER_BLEND_FWD);
     blend_forward_kernel<2><<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bsb.point_list, out_color);
     DGS_LAUNCH_OK(st, debug);

@@ -39,7 +39,9 @@ class _Arena:
             self.tensor = t
             self.tensors.append(t)
             return t.data_ptr()
-        except Exception:  # noqa: BLE001  (propagated as DGS_ERR_ALLOC by the C side)
+        except Exception as e:  # noqa: BLE001  (propagated as DGS_ERR_ALLOC by the C side)
+            import sys
+            print(f"[dgs_b200] arena allocation of {nbytes} bytes failed: {e!r}"[:600], file=sys.stderr)
             return None
 
 
