@@ -13,8 +13,11 @@
 //                        scores so that the key is the TMEM lane / the thread:  S^T = K Q_i^T, dP^T = V dO_i^T ->
 //                        P^T, dS^T (bf16, smem, K-major A operands) -> dV += P^T dO_i, dK += dS^T Q_i (dO_i, Q_i
 //                        consumed MN-major from the tiles that fed S^T / dP^T)
-// Both: 192 threads (TMA warp, MMA warp, 4 softmax warps), 2 CTAs per SM, 256 TMEM columns.  No row reductions are
-// needed in the backward (lse2 and Dsum are inputs), so a thread only does exp2 + 3 FMA-pipe ops + packing per element.
+// Both: 320 threads (TMA warp, MMA warp, 8 softmax warps), 2 CTAs per SM, 256 TMEM columns.  No row reductions are
+// needed in the backward (lse2 and Dsum are inputs), so a row is split between two threads (32 of the 64 columns each)
+// at no cost: 16 softmax warps per SM hide the TMEM-load / MUFU latencies that bound the 4-warp version
+// (profiles/r1_ncu_attn_bwd_v1.txt: XU 27-35 %, issue 31-38 %, 12 warps resident).  Per element: exp2 + 3 FMA-pipe ops
+// + half a pack; the tail-key mask is applied only in the last key block.
 #include "dgs_internal.h"
 #include "dit_kernels.h"
 #include "sm100_ptx.cuh"
@@ -28,7 +31,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 namespace {
 
-constexpr int AB_THREADS = 192, AB_HD = 64;
+constexpr int AB_THREADS = 320, AB_HD = 64;  // TMA warp + MMA warp + 8 softmax warps
+constexpr int AB_SOFT = 256;                // softmax threads: two per row / key, 32 columns each
 constexpr int AB_T128 = 128 * AB_HD * 2;  // [128 x 64] bf16 tile, 16 KB
 constexpr int AB_T64 = 64 * AB_HD * 2;    // [64 x 64] bf16 tile, 8 KB
 constexpr int AB_STAGES = 2;
@@ -110,7 +114,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
     mbar_init(q_full, 1);
     for (int s = 0; s < AB_STAGES; s++) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
     mbar_init(sdp_full, 1);
-    for (int s = 0; s < 2; s++) { mbar_init(ds_full + s, 128); mbar_init(dq_done + s, 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(ds_full + s, AB_SOFT); mbar_init(dq_done + s, 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -173,7 +177,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
       }
     }
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int ch = (warp - 2) >> 2;       // which 32 of the 64 key columns this thread handles
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const size_t stat = ((size_t)b * H + h) * Np + q0 + row;  // q0 + row < Np always
@@ -187,24 +192,29 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
       const int kv_valid = N - j * 64;
       uint8_t* ds_row = sdS + buf * AB_T128 + row * 128;
 #pragma unroll
-      for (int half = 0; half < 2; half++) {
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(t_lane + DQ_TM_S + (uint32_t)(half * 32), rs);
-        tmem_ld_32x32(t_lane + DQ_TM_DP + (uint32_t)(half * 32), rp);
+      for (int sub = 0; sub < 2; sub++) {
+        const int c0 = ch * 32 + sub * 16;
+        uint32_t rs[16], rp[16];
+        tmem_ld_32x16(t_lane + DQ_TM_S + (uint32_t)c0, rs);
+        tmem_ld_32x16(t_lane + DQ_TM_DP + (uint32_t)c0, rp);
         tmem_ld_wait();
-        float ds[32];
+        float ds[16];
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          float p = ex2_approx(fmaf(__uint_as_float(rs[i]), AB_SL2, -lse));
-          if (half * 32 + i >= kv_valid) p = 0.f;  // zero-filled tail keys (last block only)
+        for (int i = 0; i < 16; i++) {
+          const float p = ex2_approx(fmaf(__uint_as_float(rs[i]), AB_SL2, -lse));
           ds[i] = p * fmaf(__uint_as_float(rp[i]), AB_SCALE, -dsc);
         }
+        if (kv_valid < 64) {  // warp-uniform, last key block only: zero-filled tail keys contribute nothing
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+          for (int i = 0; i < 16; i++)
+            if (c0 + i >= kv_valid) ds[i] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
           uint4 pk;
           pk.x = ab_pack2(ds[8 * q], ds[8 * q + 1]); pk.y = ab_pack2(ds[8 * q + 2], ds[8 * q + 3]);
           pk.z = ab_pack2(ds[8 * q + 4], ds[8 * q + 5]); pk.w = ab_pack2(ds[8 * q + 6], ds[8 * q + 7]);
-          *reinterpret_cast<uint4*>(ds_row + (((half * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
+          *reinterpret_cast<uint4*>(ds_row + (((ch * 4 + sub * 2 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
         }
       }
       fence_proxy_async();
@@ -214,12 +224,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
     const int last = n_blocks - 1;
     mbar_wait(dq_done + (last & 1), (uint32_t)(last >> 1) & 1);
     tc_fence_after();
-    uint32_t r0[32], r1[32];
-    tmem_ld_32x32(t_lane + DQ_TM_DQ, r0);
-    tmem_ld_32x32(t_lane + DQ_TM_DQ + 32u, r1);
+    uint32_t r0[32];
+    tmem_ld_32x32(t_lane + DQ_TM_DQ + (uint32_t)(ch * 32), r0);
     tmem_ld_wait();
     if (q0 + row < N) {
-      __nv_bfloat16* dst = dqkv + ((size_t)b * N + q0 + row) * 3 * D + h * AB_HD;
+      __nv_bfloat16* dst = dqkv + ((size_t)b * N + q0 + row) * 3 * D + h * AB_HD + ch * 32;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 pk;
@@ -228,15 +237,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
         pk.z = ab_pack2(__uint_as_float(r0[i + 4]), __uint_as_float(r0[i + 5]));
         pk.w = ab_pack2(__uint_as_float(r0[i + 6]), __uint_as_float(r0[i + 7]));
         *reinterpret_cast<uint4*>(dst + i) = pk;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 pk;
-        pk.x = ab_pack2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
-        pk.y = ab_pack2(__uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3]));
-        pk.z = ab_pack2(__uint_as_float(r1[i + 4]), __uint_as_float(r1[i + 5]));
-        pk.w = ab_pack2(__uint_as_float(r1[i + 6]), __uint_as_float(r1[i + 7]));
-        *reinterpret_cast<uint4*>(dst + 32 + i) = pk;
       }
     }
   }
@@ -290,7 +290,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
     mbar_init(kv_full, 1);
     for (int s = 0; s < AB_STAGES; s++) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, 1); }
     mbar_init(stp_full, 1);
-    mbar_init(pt_full, 128);
+    mbar_init(pt_full, AB_SOFT);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -355,52 +355,58 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
     }
   } else {
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;  // key row of this thread
+    const int ch = (warp - 2) >> 2;       // which 32 of the 64 query columns this thread handles
+    const int row = quad * 32 + lane;     // key row of this thread
     const bool key_valid = k0 + row < N;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const size_t stat_base = ((size_t)b * H + h) * Np;
-    // per query block the 128 softmax threads stage lse2[64] | Dsum[64]/8 in smem (prefetched one block ahead)
-    const float* stat_src = (row < 64 ? lse2 : dsum) + stat_base + (row & 63);
-    const float stat_mul = row < 64 ? 1.0f : AB_SCALE;
-    float pre = stat_src[0] * stat_mul;  // block 0 (Np >= 128: in bounds)
+    // per query block, softmax threads 0..127 stage lse2[64] | Dsum[64]/8 in smem (prefetched one block ahead)
+    const int st_t = (warp - 2) * 32 + lane;  // 0..255
+    const float* stat_src = (st_t < 64 ? lse2 : dsum) + stat_base + (st_t & 63);
+    const float stat_mul = st_t < 64 ? 1.0f : AB_SCALE;
+    float pre = st_t < 128 ? stat_src[0] * stat_mul : 0.f;  // block 0 (Np >= 128: in bounds)
     for (int i = 0; i < n_blocks; i++) {
       float* st = s_stat + (i & 1) * 128;
-      st[row] = pre;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (i + 1 < n_blocks) pre = stat_src[(i + 1) * 64] * stat_mul;  // (i+1)*64 + 63 < Np
+      if (st_t < 128) st[st_t] = pre;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (st_t < 128 && i + 1 < n_blocks) pre = stat_src[(i + 1) * 64] * stat_mul;  // (i+1)*64 + 63 < Np
       mbar_wait(stp_full, (uint32_t)i & 1);
       tc_fence_after();
       if (i >= 1) mbar_wait(acc_done, (uint32_t)(i - 1) & 1);  // P^T / dS^T buffers consumed
       uint8_t* pt_row = sPt + row * 128;
       uint8_t* dst_row = sdSt + row * 128;
 #pragma unroll
-      for (int half = 0; half < 2; half++) {
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(t_lane + DKV_TM_ST + (uint32_t)(half * 32), rs);
-        tmem_ld_32x32(t_lane + DKV_TM_DPT + (uint32_t)(half * 32), rp);
+      for (int sub = 0; sub < 2; sub++) {
+        const int c0 = ch * 32 + sub * 16;
+        uint32_t rs[16], rp[16];
+        tmem_ld_32x16(t_lane + DKV_TM_ST + (uint32_t)c0, rs);
+        tmem_ld_32x16(t_lane + DKV_TM_DPT + (uint32_t)c0, rp);
         tmem_ld_wait();
-        float p[32], ds[32];
+        float p[16], ds[16];
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(st + half * 32 + c);        // smem broadcast
-          const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + half * 32 + c);
+        for (int c = 0; c < 16; c += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(st + c0 + c);        // smem broadcast
+          const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + c0 + c);
           const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
           for (int e = 0; e < 4; e++) {
-            float pe = ex2_approx(fmaf(__uint_as_float(rs[c + e]), AB_SL2, -lv[e]));  // pad queries: lse2 = +inf -> 0
-            if (!key_valid) pe = 0.f;
+            const float pe = ex2_approx(fmaf(__uint_as_float(rs[c + e]), AB_SL2, -lv[e]));  // pad queries: lse2 = +inf -> 0
             p[c + e] = pe;
             ds[c + e] = pe * fmaf(__uint_as_float(rp[c + e]), AB_SCALE, -dv[e]);
           }
         }
+        if (!key_valid) {  // zero-filled tail key rows (last key block only)
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+          for (int c = 0; c < 16; c++) { p[c] = 0.f; ds[c] = 0.f; }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
           uint4 pk, dk;
           pk.x = ab_pack2(p[8 * q], p[8 * q + 1]); pk.y = ab_pack2(p[8 * q + 2], p[8 * q + 3]);
           pk.z = ab_pack2(p[8 * q + 4], p[8 * q + 5]); pk.w = ab_pack2(p[8 * q + 6], p[8 * q + 7]);
           dk.x = ab_pack2(ds[8 * q], ds[8 * q + 1]); dk.y = ab_pack2(ds[8 * q + 2], ds[8 * q + 3]);
           dk.z = ab_pack2(ds[8 * q + 4], ds[8 * q + 5]); dk.w = ab_pack2(ds[8 * q + 6], ds[8 * q + 7]);
-          const int chunk = ((half * 4 + q) ^ (row & 7)) << 4;  // 128B swizzle
+          const int chunk = ((ch * 4 + sub * 2 + q) ^ (row & 7)) << 4;  // 128B swizzle
           *reinterpret_cast<uint4*>(pt_row + chunk) = pk;
           *reinterpret_cast<uint4*>(dst_row + chunk) = dk;
         }
@@ -413,13 +419,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
     tc_fence_after();
 #pragma unroll
     for (int which = 0; which < 2; which++) {  // 0: dK (qkv section 1), 1: dV (section 2)
-      uint32_t r0[32], r1[32];
-      const uint32_t col = which ? DKV_TM_DV : DKV_TM_DK;
+      uint32_t r0[32];
+      const uint32_t col = (which ? DKV_TM_DV : DKV_TM_DK) + (uint32_t)(ch * 32);
       tmem_ld_32x32(t_lane + col, r0);
-      tmem_ld_32x32(t_lane + col + 32u, r1);
       tmem_ld_wait();
       if (key_valid) {
-        __nv_bfloat16* dst = dqkv + ((size_t)b * N + k0 + row) * 3 * D + (size_t)(1 + which) * D + h * AB_HD;
+        __nv_bfloat16* dst = dqkv + ((size_t)b * N + k0 + row) * 3 * D + (size_t)(1 + which) * D + h * AB_HD + ch * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 pk;
@@ -428,15 +433,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
           pk.z = ab_pack2(__uint_as_float(r0[i + 4]), __uint_as_float(r0[i + 5]));
           pk.w = ab_pack2(__uint_as_float(r0[i + 6]), __uint_as_float(r0[i + 7]));
           *reinterpret_cast<uint4*>(dst + i) = pk;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 pk;
-          pk.x = ab_pack2(__uint_as_float(r1[i]), __uint_as_float(r1[i + 1]));
-          pk.y = ab_pack2(__uint_as_float(r1[i + 2]), __uint_as_float(r1[i + 3]));
-          pk.z = ab_pack2(__uint_as_float(r1[i + 4]), __uint_as_float(r1[i + 5]));
-          pk.w = ab_pack2(__uint_as_float(r1[i + 6]), __uint_as_float(r1[i + 7]));
-          *reinterpret_cast<uint4*>(dst + 32 + i) = pk;
         }
       }
     }

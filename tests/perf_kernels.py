@@ -41,6 +41,21 @@ def main():
     out = torch.empty(B, N, D, dtype=torch.bfloat16, device=DEV)
     ms = timeit(lambda: _lib.check(L.dgs_attention_fwd(qkv.data_ptr(), out.data_ptr(), B, N, H, st())))
     print(json.dumps(dict(kernel="attention", ms=ms, tflops=4 * N * N * D * B / ms / 1e9, **tag)))
+    if "--attn-bwd" in sys.argv or "--all" in sys.argv:
+        Bb = int(os.environ.get("DGS_PERF_B", "1"))
+        qkvb = (torch.randn(Bb, N, 3, H, 64, device=DEV) * 1.5).to(torch.bfloat16)
+        outb = torch.empty(Bb, N, D, dtype=torch.bfloat16, device=DEV)
+        dout = torch.randn(Bb, N, D, device=DEV).to(torch.bfloat16)
+        Np = (N + 127) // 128 * 128
+        lse = torch.empty(Bb, H, Np, device=DEV)
+        dsum = torch.empty(Bb, H, Np, device=DEV)
+        dqkv = torch.empty_like(qkvb)
+        _lib.check(L.dgs_attention_fwd_train(qkvb.data_ptr(), outb.data_ptr(), lse.data_ptr(), Bb, N, H, st()))
+        ms = timeit(lambda: _lib.check(L.dgs_attention_bwd(qkvb.data_ptr(), outb.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                                           dsum.data_ptr(), dqkv.data_ptr(), Bb, N, H, st())))
+        print(json.dumps(dict(kernel="attention_bwd", B=Bb, ms=ms, tflops_alg=2.5 * 4 * N * N * D * Bb / ms / 1e9, **tag)))
+        if "--attn-bwd" in sys.argv:
+            return
     for name, (n, k, epi) in dict(qkv=(3 * D, D, 0), proj=(D, D, 2), fc1=(4 * D, D, 1), fc2=(D, 4 * D, 2)).items():
         A = torch.randn(B * N, k, device=DEV).to(torch.bfloat16)
         W = (torch.randn(n, k, device=DEV) * 0.03).to(torch.bfloat16)
