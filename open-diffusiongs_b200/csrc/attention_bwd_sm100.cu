@@ -79,7 +79,7 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, const 
 // dQ
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int DQ_SMEM = 2 * AB_T128 /*Q, dO*/ + 2 * AB_T128 /*dS x2*/ + 2 * AB_STAGES * AB_T64 /*K, V*/ + 1024 + 256;
-constexpr uint32_t DQ_TM_S = 0, DQ_TM_DP = 64, DQ_TM_DQ = 128, DQ_TMEM_COLS = 256;
+constexpr uint32_t DQ_TM_S = 0 /* 2 buffers x 64 */, DQ_TM_DP = 128, DQ_TM_DQ = 192, DQ_TMEM_COLS = 256;
 
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_kv64,
@@ -97,8 +97,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
   uint64_t* q_full = bars;                    // Q + dO landed
   uint64_t* kv_full = bars + 1;               // [AB_STAGES]
   uint64_t* kv_empty = kv_full + AB_STAGES;   // [AB_STAGES]
-  uint64_t* sdp_full = kv_empty + AB_STAGES;  // S and dP of block j in TMEM
-  uint64_t* ds_full = sdp_full + 1;           // [2] dS_j written (and S/dP read out of TMEM)
+  uint64_t* s_full = kv_empty + AB_STAGES;    // [2] S of block j in TMEM (double-buffered: issued one block ahead)
+  uint64_t* dp_full = s_full + 2;             // dP of block j in TMEM (single buffer)
+  uint64_t* ds_full = dp_full + 1;            // [2] dS_j written (and S/dP read out of TMEM)
   uint64_t* dq_done = ds_full + 2;            // [2] dQ MMA of block j retired (dS buffer free)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_done + 2);
 
@@ -113,8 +114,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
     prefetch_tmap(&tm_do128);
     mbar_init(q_full, 1);
     for (int s = 0; s < AB_STAGES; s++) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
-    mbar_init(sdp_full, 1);
-    for (int s = 0; s < 2; s++) { mbar_init(ds_full + s, AB_SOFT); mbar_init(dq_done + s, 1); }
+    mbar_init(dp_full, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(s_full + s, 1); mbar_init(ds_full + s, AB_SOFT); mbar_init(dq_done + s, 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -145,21 +146,32 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
       constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 64, false, true);  // A K-major x B MN-major
       const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t dodesc = make_smem_desc_sw128(smem_u32(sdO), 16, 1024);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < n_blocks; j++) {
+      // Issue order (the softmax needs S first and dP only for its second half, so S runs one block ahead):
+      //   S(0) dP(0) | S(1) .. wait dS(0) .. dQ(0) dP(1) | S(2) .. wait dS(1) .. dQ(1) dP(2) | ...
+      auto issue_s = [&](int j) {
         const int s = j % AB_STAGES;
         mbar_wait(kv_full + s, (uint32_t)(j / AB_STAGES) & 1);
         tc_fence_after();
-        // S and dP are single-buffered: block j-1's softmax has read them (ds_full(j-1) was waited below)
         const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s * AB_T64), 16, 1024);
-        const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + s * AB_T64), 16, 1024);
+        const uint32_t d = tmem_base + DQ_TM_S + (uint32_t)((j & 1) * 64);
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          umma_bf16(tmem_base + DQ_TM_S, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+        for (int k = 0; k < 4; k++) umma_bf16(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+        umma_commit(s_full + (j & 1));
+      };
+      auto issue_dp = [&](int j) {  // kv_full(j) already observed by issue_s(j)
+        const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + (j % AB_STAGES) * AB_T64), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; k++)
           umma_bf16(tmem_base + DQ_TM_DP, dodesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
-        umma_commit(sdp_full);
+        umma_commit(dp_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      issue_dp(0);
+      for (int j = 0; j < n_blocks; j++) {
+        const int s = j % AB_STAGES;
+        // S buffer (j+1)&1 was last read by the softmax of block j-1, whose ds_full was observed one iteration ago
+        if (j + 1 < n_blocks) issue_s(j + 1);
         mbar_wait(ds_full + (j & 1), (uint32_t)(j >> 1) & 1);
         tc_fence_after();
         const uint32_t dsbase = smem_u32(sdS + (j & 1) * AB_T128);
@@ -174,6 +186,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
         }
         umma_commit(dq_done + (j & 1));
         umma_commit(kv_empty + s);
+        if (j + 1 < n_blocks) issue_dp(j + 1);  // dP(j) has been read (ds_full(j))
       }
     }
   } else {
@@ -186,29 +199,37 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
     const float dsc = dsum[stat] * AB_SCALE;
     for (int j = 0; j < n_blocks; j++) {
       const int buf = j & 1;
-      mbar_wait(sdp_full, (uint32_t)j & 1);
+      const int kv_valid = N - j * 64;
+      // ---- phase 1: P from S (runs while the tensor core still produces dQ(j-1) and dP(j)) ----
+      mbar_wait(s_full + buf, (uint32_t)(j >> 1) & 1);
+      tc_fence_after();
+      float p[32];
+#pragma unroll
+      for (int sub = 0; sub < 2; sub++) {
+        uint32_t rs[16];
+        tmem_ld_32x16(t_lane + DQ_TM_S + (uint32_t)(buf * 64 + ch * 32 + sub * 16), rs);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i++) p[sub * 16 + i] = ex2_approx(fmaf(__uint_as_float(rs[i]), AB_SL2, -lse));
+      }
+      if (kv_valid < 64) {  // warp-uniform, last key block only: zero-filled tail keys contribute nothing
+#pragma unroll
+        for (int i = 0; i < 32; i++)
+          if (ch * 32 + i >= kv_valid) p[i] = 0.f;
+      }
+      // ---- phase 2: dS = P * (dP - Dsum) / 8 ----
+      mbar_wait(dp_full, (uint32_t)j & 1);
       tc_fence_after();
       if (j >= 2) mbar_wait(dq_done + buf, (uint32_t)((j - 2) >> 1) & 1);  // dS buffer consumed
-      const int kv_valid = N - j * 64;
       uint8_t* ds_row = sdS + buf * AB_T128 + row * 128;
 #pragma unroll
       for (int sub = 0; sub < 2; sub++) {
-        const int c0 = ch * 32 + sub * 16;
-        uint32_t rs[16], rp[16];
-        tmem_ld_32x16(t_lane + DQ_TM_S + (uint32_t)c0, rs);
-        tmem_ld_32x16(t_lane + DQ_TM_DP + (uint32_t)c0, rp);
+        uint32_t rp[16];
+        tmem_ld_32x16(t_lane + DQ_TM_DP + (uint32_t)(ch * 32 + sub * 16), rp);
         tmem_ld_wait();
         float ds[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const float p = ex2_approx(fmaf(__uint_as_float(rs[i]), AB_SL2, -lse));
-          ds[i] = p * fmaf(__uint_as_float(rp[i]), AB_SCALE, -dsc);
-        }
-        if (kv_valid < 64) {  // warp-uniform, last key block only: zero-filled tail keys contribute nothing
-#pragma unroll
-          for (int i = 0; i < 16; i++)
-            if (c0 + i >= kv_valid) ds[i] = 0.f;
-        }
+        for (int i = 0; i < 16; i++) ds[i] = p[sub * 16 + i] * fmaf(__uint_as_float(rp[i]), AB_SCALE, -dsc);
 #pragma unroll
         for (int q = 0; q < 2; q++) {
           uint4 pk;
@@ -273,8 +294,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;              // [AB_STAGES]
   uint64_t* q_empty = q_full + AB_STAGES;   // [AB_STAGES]
-  uint64_t* stp_full = q_empty + AB_STAGES; // S^T and dP^T of block i in TMEM
-  uint64_t* pt_full = stp_full + 1;         // P^T, dS^T written (and S^T/dP^T read out of TMEM)
+  uint64_t* st_full = q_empty + AB_STAGES;  // S^T of block i in TMEM
+  uint64_t* dpt_full = st_full + 1;         // dP^T of block i in TMEM
+  uint64_t* pt_full = dpt_full + 1;         // P^T, dS^T written (and S^T/dP^T read out of TMEM)
   uint64_t* acc_done = pt_full + 1;         // dV/dK MMAs of block i retired (P^T/dS^T buffers free)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
@@ -289,7 +311,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
     prefetch_tmap(&tm_do64);
     mbar_init(kv_full, 1);
     for (int s = 0; s < AB_STAGES; s++) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, 1); }
-    mbar_init(stp_full, 1);
+    mbar_init(st_full, 1);
+    mbar_init(dpt_full, 1);
     mbar_init(pt_full, AB_SOFT);
     mbar_init(acc_done, 1);
     fence_barrier_init();
@@ -323,23 +346,35 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
       const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
       const uint32_t ptbase = smem_u32(sPt), dstbase = smem_u32(sdSt);
-      mbar_wait(kv_full, 0);
-      for (int i = 0; i < n_blocks; i++) {
+      // Issue order: the softmax of block i+1 only needs S^T to start (exp), so S^T(i+1) goes in FRONT of the
+      // dV/dK accumulation of block i, and dP^T(i+1) behind it:
+      //   St(0) dPt(0) | wait PT(0) : St(1) dV(0) dK(0) dPt(1) | wait PT(1) : St(2) dV(1) dK(1) dPt(2) | ...
+      auto issue_st = [&](int i) {
         const int s = i % AB_STAGES;
         mbar_wait(q_full + s, (uint32_t)(i / AB_STAGES) & 1);
         tc_fence_after();
-        const uint32_t qbase = smem_u32(sQ + s * AB_T64), dobase = smem_u32(sdO + s * AB_T64);
-        const uint64_t qdesc = make_smem_desc_sw128(qbase, 16, 1024);
-        const uint64_t dodesc = make_smem_desc_sw128(dobase, 16, 1024);
+        const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + s * AB_T64), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; k++)  // S^T = K Q_i^T : [128 keys x 64 queries]
           umma_bf16(tmem_base + DKV_TM_ST, kdesc + (uint64_t)(2 * k), qdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+        umma_commit(st_full);
+      };
+      auto issue_dpt = [&](int i) {
+        const uint64_t dodesc = make_smem_desc_sw128(smem_u32(sdO + (i % AB_STAGES) * AB_T64), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; k++)  // dP^T = V dO_i^T
           umma_bf16(tmem_base + DKV_TM_DPT, vdesc + (uint64_t)(2 * k), dodesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
-        umma_commit(stp_full);
-        mbar_wait(pt_full, (uint32_t)i & 1);
+        umma_commit(dpt_full);
+      };
+      mbar_wait(kv_full, 0);
+      issue_st(0);
+      issue_dpt(0);
+      for (int i = 0; i < n_blocks; i++) {
+        const int s = i % AB_STAGES;
+        mbar_wait(pt_full, (uint32_t)i & 1);  // softmax(i) has read S^T(i), dP^T(i) and written P^T, dS^T
         tc_fence_after();
+        if (i + 1 < n_blocks) issue_st(i + 1);
+        const uint32_t qbase = smem_u32(sQ + s * AB_T64), dobase = smem_u32(sdO + s * AB_T64);
 #pragma unroll
         for (int k = 0; k < 4; k++) {  // reduction over the 64 queries of the block, 16 per instruction
           const uint64_t pdesc = make_smem_desc_sw128(ptbase + (uint32_t)(k * 32), 16, 1024);
@@ -351,6 +386,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
         }
         umma_commit(acc_done);
         umma_commit(q_empty + s);
+        if (i + 1 < n_blocks) issue_dpt(i + 1);
       }
     }
   } else {
@@ -370,45 +406,63 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
       if (st_t < 128) st[st_t] = pre;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (st_t < 128 && i + 1 < n_blocks) pre = stat_src[(i + 1) * 64] * stat_mul;  // (i+1)*64 + 63 < Np
-      mbar_wait(stp_full, (uint32_t)i & 1);
+      // ---- phase 1: P^T from S^T (overlaps the dV/dK MMAs of block i-1) ----
+      mbar_wait(st_full, (uint32_t)i & 1);
       tc_fence_after();
-      if (i >= 1) mbar_wait(acc_done, (uint32_t)(i - 1) & 1);  // P^T / dS^T buffers consumed
-      uint8_t* pt_row = sPt + row * 128;
-      uint8_t* dst_row = sdSt + row * 128;
+      float p[32];
 #pragma unroll
       for (int sub = 0; sub < 2; sub++) {
         const int c0 = ch * 32 + sub * 16;
-        uint32_t rs[16], rp[16];
+        uint32_t rs[16];
         tmem_ld_32x16(t_lane + DKV_TM_ST + (uint32_t)c0, rs);
-        tmem_ld_32x16(t_lane + DKV_TM_DPT + (uint32_t)c0, rp);
         tmem_ld_wait();
-        float p[16], ds[16];
 #pragma unroll
         for (int c = 0; c < 16; c += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(st + c0 + c);        // smem broadcast
-          const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + c0 + c);
-          const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const float pe = ex2_approx(fmaf(__uint_as_float(rs[c + e]), AB_SL2, -lv[e]));  // pad queries: lse2 = +inf -> 0
-            p[c + e] = pe;
-            ds[c + e] = pe * fmaf(__uint_as_float(rp[c + e]), AB_SCALE, -dv[e]);
-          }
+          const float4 l4 = *reinterpret_cast<const float4*>(st + c0 + c);  // smem broadcast; pad queries: +inf -> P = 0
+          p[sub * 16 + c] = ex2_approx(fmaf(__uint_as_float(rs[c]), AB_SL2, -l4.x));
+          p[sub * 16 + c + 1] = ex2_approx(fmaf(__uint_as_float(rs[c + 1]), AB_SL2, -l4.y));
+          p[sub * 16 + c + 2] = ex2_approx(fmaf(__uint_as_float(rs[c + 2]), AB_SL2, -l4.z));
+          p[sub * 16 + c + 3] = ex2_approx(fmaf(__uint_as_float(rs[c + 3]), AB_SL2, -l4.w));
         }
-        if (!key_valid) {  // zero-filled tail key rows (last key block only)
+      }
+      if (!key_valid) {  // zero-filled tail key rows (last key block only)
 #pragma unroll
-          for (int c = 0; c < 16; c++) { p[c] = 0.f; ds[c] = 0.f; }
+        for (int c = 0; c < 32; c++) p[c] = 0.f;
+      }
+      if (i >= 1) mbar_wait(acc_done, (uint32_t)(i - 1) & 1);  // P^T / dS^T buffers consumed by dV/dK(i-1)
+      uint8_t* pt_row = sPt + row * 128;
+      uint8_t* dst_row = sdSt + row * 128;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        uint4 pk;
+        pk.x = ab_pack2(p[8 * q], p[8 * q + 1]); pk.y = ab_pack2(p[8 * q + 2], p[8 * q + 3]);
+        pk.z = ab_pack2(p[8 * q + 4], p[8 * q + 5]); pk.w = ab_pack2(p[8 * q + 6], p[8 * q + 7]);
+        *reinterpret_cast<uint4*>(pt_row + (((ch * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
+      }
+      // ---- phase 2: dS^T = P^T * (dP^T - Dsum) / 8 ----
+      mbar_wait(dpt_full, (uint32_t)i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int sub = 0; sub < 2; sub++) {
+        const int c0 = ch * 32 + sub * 16;
+        uint32_t rp[16];
+        tmem_ld_32x16(t_lane + DKV_TM_DPT + (uint32_t)c0, rp);
+        tmem_ld_wait();
+        float ds[16];
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + c0 + c);
+          ds[c] = p[sub * 16 + c] * fmaf(__uint_as_float(rp[c]), AB_SCALE, -d4.x);
+          ds[c + 1] = p[sub * 16 + c + 1] * fmaf(__uint_as_float(rp[c + 1]), AB_SCALE, -d4.y);
+          ds[c + 2] = p[sub * 16 + c + 2] * fmaf(__uint_as_float(rp[c + 2]), AB_SCALE, -d4.z);
+          ds[c + 3] = p[sub * 16 + c + 3] * fmaf(__uint_as_float(rp[c + 3]), AB_SCALE, -d4.w);
         }
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-          uint4 pk, dk;
-          pk.x = ab_pack2(p[8 * q], p[8 * q + 1]); pk.y = ab_pack2(p[8 * q + 2], p[8 * q + 3]);
-          pk.z = ab_pack2(p[8 * q + 4], p[8 * q + 5]); pk.w = ab_pack2(p[8 * q + 6], p[8 * q + 7]);
+          uint4 dk;
           dk.x = ab_pack2(ds[8 * q], ds[8 * q + 1]); dk.y = ab_pack2(ds[8 * q + 2], ds[8 * q + 3]);
           dk.z = ab_pack2(ds[8 * q + 4], ds[8 * q + 5]); dk.w = ab_pack2(ds[8 * q + 6], ds[8 * q + 7]);
-          const int chunk = ((ch * 4 + sub * 2 + q) ^ (row & 7)) << 4;  // 128B swizzle
-          *reinterpret_cast<uint4*>(pt_row + chunk) = pk;
-          *reinterpret_cast<uint4*>(dst_row + chunk) = dk;
+          *reinterpret_cast<uint4*>(dst_row + (((ch * 4 + sub * 2 + q) ^ (row & 7)) << 4)) = dk;
         }
       }
       fence_proxy_async();
