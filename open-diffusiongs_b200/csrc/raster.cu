@@ -661,6 +661,23 @@ __global__ void tile_ranges_kernel(long long R, const uint32_t* __restrict__ key
   if (idx == R - 1) ranges[cur].y = (uint32_t)R;
 }
 
+// The Gaussian falloff G = exp(power), power = -0.5 (A dx^2 + C dy^2) - B dx dy (forward.cu:326-329), is evaluated as
+// ex2(power * log2 e) on the MUFU pipe with the conic pre-scaled by -0.5 log2 e / -log2 e (5 FMA-pipe ops + 1 MUFU
+// instead of the 7 + ~10 of expf).  Forward and backward call the SAME two functions with explicitly rounded
+// intrinsics, so they take bit-identical contribute / skip decisions for every (pixel, Gaussian) pair.
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float4 conic_log2(float4 co) {
+  return make_float4(__fmul_rn(co.x, -0.5f * kLog2e), __fmul_rn(co.y, -kLog2e), __fmul_rn(co.z, -0.5f * kLog2e), co.w);
+}
+__device__ __forceinline__ float pair_power2(float4 c2, float dx, float dy) {
+  return __fmaf_rn(dx, __fmaf_rn(c2.x, dx, __fmul_rn(c2.y, dy)), __fmul_rn(__fmul_rn(c2.z, dy), dy));
+}
+__device__ __forceinline__ float ex2_mufu(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K6: per-tile front-to-back alpha blend (forward.cu:261-374), one CTA per (view, tile)
 // ---------------------------------------------------------------------------------------------
@@ -704,27 +721,31 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, Geo
       const size_t g = gbase + point_list[e];
       const float4 a0 = gs.g0[g];
       s_xy[threadIdx.x] = make_float2(a0.x, a0.y);
-      s_co[threadIdx.x] = gs.g1[g];
+      s_co[threadIdx.x] = conic_log2(gs.g1[g]);
       s_rgb[threadIdx.x] = gs.g2[g];
     }
     __syncthreads();
     const int nb = min(TILE_PIX, todo);
-    for (int j = 0; !done && j < nb; j++) {
-      contributor++;
+    // Branch-free body (the reference's three `continue`s become predicates): every lane evaluates every staged entry
+    // until its whole warp is done; ~28 instructions per (pixel, entry) pair instead of 24 (rejected) / 54 (blended).
+    for (int j = 0; j < nb; j++) {
+      if ((j & 3) == 0 && __all_sync(0xffffffffu, done)) break;
       const float2 xy = s_xy[j];
-      const float dx = xy.x - pxf, dy = xy.y - pyf;
       const float4 co = s_co[j];
-      const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-      if (power > 0.0f) continue;
-      const float alpha = fminf(0.99f, co.w * expf(power));
-      if (alpha < ALPHA_MIN) continue;
-      const float test_T = T * (1 - alpha);
-      if (test_T < T_EPS) { done = true; continue; }
       const float4 col = s_rgb[j];
-      const float w = alpha * T;
-      C0 += col.x * w; C1 += col.y * w; C2 += col.z * w;
-      T = test_T;
-      last = contributor;
+      const float dx = xy.x - pxf, dy = xy.y - pyf;
+      const float power2 = pair_power2(co, dx, dy);
+      const float alpha = fminf(0.99f, co.w * ex2_mufu(power2));
+      contributor += done ? 0u : 1u;
+      bool ok = !done && power2 <= 0.0f && alpha >= ALPHA_MIN;
+      const float test_T = T * (1 - alpha);
+      const bool sat = ok && test_T < T_EPS;
+      done |= sat;
+      ok = ok && !sat;
+      const float w = ok ? alpha * T : 0.f;
+      C0 = fmaf(col.x, w, C0); C1 = fmaf(col.y, w, C1); C2 = fmaf(col.z, w, C2);
+      T = ok ? test_T : T;
+      last = ok ? contributor : last;
     }
   }
   if (MODE == 1) {
@@ -847,9 +868,9 @@ __global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(Problem pb, Ge
         const float2 xy = s_xy[j];
         const float dx = xy.x - pxf, dy = xy.y - pyf;
         const float4 co = s_co[j];
-        const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-        if (power <= 0.0f) {
-          const float G = expf(power);
+        const float power2 = pair_power2(conic_log2(co), dx, dy);  // same bits as the forward's decision
+        if (power2 <= 0.0f) {
+          const float G = ex2_mufu(power2);
           const float alpha = fminf(0.99f, co.w * G);
           if (alpha >= ALPHA_MIN) {
             active = true;
