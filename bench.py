@@ -229,6 +229,7 @@ def run_train(args, rank, local_rank, world):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ["NCCL_DEBUG"] = os.environ.get("DGS_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/dgs_nccl_%h_%p.log")  # keep even the version banner off stdout
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)  # identical initial weights on every rank (what DDP's broadcast establishes)
     model = DGSDenoiser(dict(patch_size=PATCH)).to(dev)
@@ -381,7 +382,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("DGS_NCCL_DEBUG", "WARN")  # keep stdout = the one JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("DGS_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/dgs_nccl_%h_%p.log")  # keep even the version banner off stdout  # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
