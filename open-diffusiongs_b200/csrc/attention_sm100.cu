@@ -35,16 +35,16 @@ constexpr int ATT_ONES_BYTES = 16 * 128;           // [16 x 64] bf16 ones, K-maj
 constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES * 3 + 2 * ATT_KV_STAGES * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;
 constexpr uint32_t TMEM_S = 0, TMEM_O = 2 * ATT_BN, TMEM_L = TMEM_O + ATT_HD, ATT_TMEM_COLS = 256;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;
-// exponentials per 8 evaluated as an FMA-pipe polynomial instead of MUFU ex2: template parameter POLY_OF_8,
-// selected at run time by DGS_ATT_POLY (0, 2 or 4; default below)
-constexpr int ATT_POLY_DEFAULT = 0;  // log2 units: rescale O only if the row max grew by > 2^8
+// Probabilities: fp32 ex2.approx per element, rounded to bf16 for the P V MMA.  Measured alternatives (r1): the packed
+// half-precision MUFU forms do not help -- ex2.approx.ftz.bf16x2 compiles to two MUFU.EX2.BF16 (same 135 us, error
+// 2.1e-3 -> 4.5e-3), and an fp16 P against the bf16 V is rejected by the hardware (kind::f16 needs A and B of one
+// format: illegal instruction); an FMA-pipe polynomial for a fraction of the exponentials was slower (issue-bound).
 
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int ATT_POLY_OF_8>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int Np, int N, int H) {
@@ -89,6 +89,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // programmatic dependent launch: the next kernel may start its prologue now ...
+  griddep_wait();               // ... and this one touches global memory only after its predecessor has completed
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -210,15 +212,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       const float moff = m_run * sl2;
       uint8_t* p_row = sP + buf * ATT_Q_BYTES + row * 128;
-      // exponentials: ATT_POLY_OF_8 of every 8 as a polynomial on the FMA pipe, the rest on the MUFU pipe (ex2.approx)
 #pragma unroll
       for (int half = 0; half < 2; half++) {
         float p[32];
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const float x = fmaf(__uint_as_float(half ? r1[i] : r0[i]), sl2, -moff);
-          p[i] = ((i & 7) < ATT_POLY_OF_8) ? ex2_poly3(x) : ex2_approx(x);
-        }
+        for (int i = 0; i < 32; i++) p[i] = ex2_approx(fmaf(__uint_as_float(half ? r1[i] : r0[i]), sl2, -moff));
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           uint4 pk;
@@ -287,19 +285,14 @@ int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, 
   if (rc) return rc;
   rc = make_tmap_bf16(&tm_kv, qkv, 3, dims, str, box_kv);
   if (rc) return rc;
-  static int poly = -1;
-  if (poly < 0) {
-    const char* e = getenv("DGS_ATT_POLY");
-    poly = e ? atoi(e) : ATT_POLY_DEFAULT;
-    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+  static bool configured = false;
+  if (!configured) {
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    configured = true;
   }
   dim3 grid(ceil_div(N, ATT_BM), H, B);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (poly >= 4) attention_fwd_kernel<4><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, lse2, Np, N, H);
-  else if (poly >= 2) attention_fwd_kernel<2><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, lse2, Np, N, H);
-  else attention_fwd_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tm_q, tm_kv, o, lse2, Np, N, H);
+  DGS_CUDA_OK(launch_pdl(attention_fwd_kernel, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tm_q, tm_kv, o, lse2, Np, N, H));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }

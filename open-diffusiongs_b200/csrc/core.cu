@@ -1,4 +1,5 @@
 // core.cu -- error reporting and version of libdgs_b200.so
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -15,6 +16,14 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 
 unsigned long long g_kernel_launches = 0;
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DGS_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 bool g_prof_on = false;
 
 namespace {

@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
                                                           int row_off, int rows_out, float eps, int split) {
   constexpr int PER_LANE = D / 32;  // 32 for D = 1024
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL (sm100_ptx.cuh): launched via launch_pdl
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (warp >= B * rows_out) return;
   const int b = warp / rows_out, r = warp - b * rows_out;
   const float* xr = x + ((size_t)b * rows_in + row_off + r) * D;
@@ -79,8 +81,8 @@ int ln_modulate(const float* x, const float* ln_weight, const float* shift, cons
   DGS_REQUIRE(D == 1024, "ln_modulate: width %d not supported (1024 only)", D);
   const long long warps = (long long)B * rows_out;
   const int blocks = (int)((warps * 32 + 255) / 256);
-  ln_modulate_kernel<1024><<<blocks, 256, 0, st>>>(x, ln_weight, shift, scale, mod_stride, h, B, rows_in, row_off,
-                                                   rows_out, eps, split);
+  DGS_CUDA_OK(launch_pdl(ln_modulate_kernel<1024>, dim3(blocks), dim3(256), 0, st, x, ln_weight, shift, scale, mod_stride, h,
+                         B, rows_in, row_off, rows_out, eps, split));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }

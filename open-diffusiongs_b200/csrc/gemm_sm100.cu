@@ -114,6 +114,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // PDL: see sm100_ptx.cuh
+  griddep_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -212,7 +214,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, ep, M, N, K);
+  DGS_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, ep, M, N, K));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }
