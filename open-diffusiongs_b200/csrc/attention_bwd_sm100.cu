@@ -49,6 +49,8 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, const 
                                      float* __restrict__ lse2, float* __restrict__ dsum, int N, int Np, int H) {
   const int n = blockIdx.x, b = blockIdx.y, t = threadIdx.x;  // blockDim.x = H * 16
   const int D = H * AB_HD;
+  griddep_launch_dependents();  // PDL (sm100_ptx.cuh)
+  griddep_wait();
   if (n >= N) {
     if (t < H) {
       lse2[((size_t)b * H + t) * Np + n] = INFINITY;
@@ -126,6 +128,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // PDL (sm100_ptx.cuh)
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -325,6 +329,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // PDL (sm100_ptx.cuh)
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -530,15 +536,15 @@ int attention_bwd(const void* qkv, const void* out, const void* dout, float* lse
     DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
     configured = true;
   }
-  attn_bwd_prep_kernel<<<dim3(Np, B), H * 16 < 32 ? 32 : H * 16, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse2, dsum,
-                                                       N, Np, H);
+  DGS_CUDA_OK(launch_pdl(attn_bwd_prep_kernel, dim3(Np, B), dim3(H * 16 < 32 ? 32 : H * 16), 0, st,
+                         (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse2, dsum, N, Np, H));
   DGS_POST_LAUNCH();
   dim3 grid(ceil_div(N, 128), H, B);
-  attn_bwd_dq_kernel<<<grid, AB_THREADS, DQ_SMEM, st>>>(tm_qkv128, tm_qkv64, tm_do128, lse2, dsum,
-                                                        (__nv_bfloat16*)dqkv, N, Np, H);
+  DGS_CUDA_OK(launch_pdl(attn_bwd_dq_kernel, grid, dim3(AB_THREADS), DQ_SMEM, st, tm_qkv128, tm_qkv64, tm_do128,
+                         (const float*)lse2, (const float*)dsum, (__nv_bfloat16*)dqkv, N, Np, H));
   DGS_POST_LAUNCH();
-  attn_bwd_dkv_kernel<<<grid, AB_THREADS, DKV_SMEM, st>>>(tm_qkv128, tm_qkv64, tm_do64, lse2, dsum,
-                                                          (__nv_bfloat16*)dqkv, N, Np, H);
+  DGS_CUDA_OK(launch_pdl(attn_bwd_dkv_kernel, grid, dim3(AB_THREADS), DKV_SMEM, st, tm_qkv128, tm_qkv64, tm_do64,
+                         (const float*)lse2, (const float*)dsum, (__nv_bfloat16*)dqkv, N, Np, H));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }

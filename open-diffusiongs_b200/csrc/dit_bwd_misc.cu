@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ i
   __shared__ __align__(16) __nv_bfloat16 tile[64 * TP];
   __shared__ float red[4 * 64];
   const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64, t = threadIdx.x;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: launched via launch_pdl
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   in += (size_t)blockIdx.z * in_bstride;   // batched use (weight refresh): one matrix per blockIdx.z
   out += (size_t)blockIdx.z * out_bstride;
   {
@@ -102,6 +104,8 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__
   __shared__ float prod[64 * 65];
   __shared__ float red[3 * 4 * 64];
   const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64, t = threadIdx.x;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: launched via launch_pdl
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   {
     const int lr = t >> 2, lc = (t & 3) * 16;
     const int m = m0 + lr;
@@ -195,6 +199,8 @@ __global__ void __launch_bounds__(256) ln_bwd_rows_kernel(const float* __restric
                                                           float* __restrict__ dx, int accumulate,
                                                           float2* __restrict__ stats) {
   constexpr int D = 1024, PER = 32;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: launched via launch_pdl
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int b = blockIdx.y, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows_out) return;
@@ -262,6 +268,8 @@ __global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const float* __restric
                                                           float* __restrict__ dscale, float* __restrict__ dlnw) {
   constexpr int D = 1024, ROWS = 128;
   __shared__ float red[3 * 4 * 64];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: launched via launch_pdl
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int b = blockIdx.z, c = blockIdx.x * 64 + (threadIdx.x & 63), rq = threadIdx.x >> 6;
   const int r0 = blockIdx.y * ROWS;
   const float w = lnw ? __ldg(lnw + c) : 1.0f;
@@ -500,11 +508,11 @@ int transpose_to_bf16(const void* in, int in_is_f32, int ldi, int B, int rows_in
   const int M = B * rows_out, Mp = (M + 63) / 64 * 64;
   dim3 grid(Mp / 64, C / 64);
   if (in_is_f32)
-    transpose_kernel<float><<<grid, 256, 0, st>>>((const float*)in, ldi, rows_in, row_off, rows_out, M, Mp, out, colsum,
-                                                  nullptr, C, 0, 0, 0);
+    DGS_CUDA_OK(launch_pdl(transpose_kernel<float>, grid, dim3(256), 0, st, (const float*)in, ldi, rows_in, row_off, rows_out,
+                           M, Mp, out, colsum, (__nv_bfloat16*)nullptr, C, (size_t)0, (size_t)0, (size_t)0));
   else
-    transpose_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, ldi, rows_in, row_off, rows_out, M,
-                                                          Mp, out, colsum, nullptr, C, 0, 0, 0);
+    DGS_CUDA_OK(launch_pdl(transpose_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, (const __nv_bfloat16*)in, ldi, rows_in,
+                           row_off, rows_out, M, Mp, out, colsum, (__nv_bfloat16*)nullptr, C, (size_t)0, (size_t)0, (size_t)0));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }
@@ -514,8 +522,8 @@ int cast_transpose_f32(const float* in, long long in_bstride, int batch, int M, 
                        __nv_bfloat16* outT, cudaStream_t st) {
   DGS_REQUIRE(M % 64 == 0 && C % 64 == 0 && outT != nullptr, "cast_transpose: need M, C multiples of 64 and outT");
   dim3 grid(M / 64, C / 64, batch);
-  transpose_kernel<float><<<grid, 256, 0, st>>>(in, C, M, 0, M, M, M, outT, nullptr, out_rm, C, (size_t)in_bstride,
-                                                (size_t)M * C, (size_t)M * C);
+  DGS_CUDA_OK(launch_pdl(transpose_kernel<float>, grid, dim3(256), 0, st, in, C, M, 0, M, M, M, outT, (float*)nullptr, out_rm, C,
+                         (size_t)in_bstride, (size_t)M * C, (size_t)M * C));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }
@@ -524,8 +532,8 @@ int gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, int gat
              int C, __nv_bfloat16* dy, __nv_bfloat16* dyT, float* dgate, float* dbias, cudaStream_t st) {
   DGS_REQUIRE(C % 64 == 0 && rows_per_sample >= 64, "gate_bwd: need C %% 64 == 0 and >= 64 rows per sample");
   const int Mp = (M + 63) / 64 * 64;
-  gate_bwd_kernel<<<dim3(Mp / 64, C / 64), 256, 0, st>>>(dx, y, gate, gate_stride, rows_per_sample, M, Mp, C, dy, dyT,
-                                                         dgate, dbias);
+  DGS_CUDA_OK(launch_pdl(gate_bwd_kernel, dim3(Mp / 64, C / 64), dim3(256), 0, st, dx, y, gate, gate_stride, rows_per_sample, M,
+                         Mp, C, dy, dyT, dgate, dbias));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }
@@ -542,21 +550,21 @@ int ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* 
   const dim3 grid_r((rows_out + 7) / 8, B), grid_c(D / 64, (rows_out + 127) / 128, B);
   const bool cols = dshift != nullptr || dlnw != nullptr;
   if (dh_is_f32) {
-    ln_bwd_rows_kernel<float><<<grid_r, 256, 0, st>>>(x, (const float*)dh, lnw, scale, mod_stride, rows_in, row_off,
-                                                      rows_out, eps, dx, accumulate, s2);
+    DGS_CUDA_OK(launch_pdl(ln_bwd_rows_kernel<float>, grid_r, dim3(256), 0, st, x, (const float*)dh, lnw, scale, mod_stride,
+                           rows_in, row_off, rows_out, eps, dx, accumulate, s2));
     DGS_POST_LAUNCH();
     if (cols) {
-      ln_bwd_cols_kernel<float><<<grid_c, 256, 0, st>>>(x, (const float*)dh, lnw, scale, mod_stride, rows_in, row_off,
-                                                        rows_out, s2, dshift, dscale, dlnw);
+      DGS_CUDA_OK(launch_pdl(ln_bwd_cols_kernel<float>, grid_c, dim3(256), 0, st, x, (const float*)dh, lnw, scale, mod_stride,
+                             rows_in, row_off, rows_out, (const float2*)s2, dshift, dscale, dlnw));
       DGS_POST_LAUNCH();
     }
   } else {
-    ln_bwd_rows_kernel<__nv_bfloat16><<<grid_r, 256, 0, st>>>(x, (const __nv_bfloat16*)dh, lnw, scale, mod_stride,
-                                                              rows_in, row_off, rows_out, eps, dx, accumulate, s2);
+    DGS_CUDA_OK(launch_pdl(ln_bwd_rows_kernel<__nv_bfloat16>, grid_r, dim3(256), 0, st, x, (const __nv_bfloat16*)dh, lnw, scale,
+                           mod_stride, rows_in, row_off, rows_out, eps, dx, accumulate, s2));
     DGS_POST_LAUNCH();
     if (cols) {
-      ln_bwd_cols_kernel<__nv_bfloat16><<<grid_c, 256, 0, st>>>(x, (const __nv_bfloat16*)dh, lnw, scale, mod_stride,
-                                                                rows_in, row_off, rows_out, s2, dshift, dscale, dlnw);
+      DGS_CUDA_OK(launch_pdl(ln_bwd_cols_kernel<__nv_bfloat16>, grid_c, dim3(256), 0, st, x, (const __nv_bfloat16*)dh, lnw, scale,
+                             mod_stride, rows_in, row_off, rows_out, (const float2*)s2, dshift, dscale, dlnw));
       DGS_POST_LAUNCH();
     }
   }

@@ -169,8 +169,9 @@ def _batch_args(xyz, features, scaling, rotation, opacity, C2W, fxfycxcy, H, W, 
 def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, fxfycxcy, scale_modifier=None,
                          arena_cache=None, near_log2=None):
     """All (sample, view) pairs in one launch set -> (images [B,V,3,H,W] fp32, state).
-    `arena_cache` (a dict): re-use grow-only arenas across calls -- only valid when no backward will follow (the
-    inference / denoise-step path); stream order makes the re-use safe."""
+    `arena_cache` (a dict): re-use grow-only arenas across calls; the caller must not hand the same dict to another
+    forward while this call's state is still needed (renderer.py keeps one dict for inference and a pool of dicts for
+    differentiated forwards); stream order makes the re-use safe."""
     _require_cuda(xyz, "xyz")
     dev = xyz.device
     tens = [_f32c(t) for t in (xyz, features, scaling, rotation, opacity, C2W, fxfycxcy)]
@@ -193,14 +194,14 @@ def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, f
     return out, state
 
 
-def render_batch_backward(state, grad_images):
+def render_batch_backward(state, grad_images, arena_cache=None):
     """-> (d_xyz, d_features, d_scaling, d_rotation, d_opacity), re-using the forward's sorted lists."""
     tens = state["tensors"]
     dev = tens[0].device
     g = _f32c(grad_images)
     with torch.cuda.device(dev):
         outs = [torch.empty_like(t) for t in tens[:5]]
-        scratch = _Arena(dev)
+        scratch = _Arena(dev, arena_cache, "bwd_scratch")
         a = _batch_args(*tens, state["H"], state["W"], state["scale_modifier"], near_log2=state["near_log2"])
         chunks = (C.c_longlong * 2)(*state["chunks"])
         check(_lib.lib().dgs_render_batch_backward(

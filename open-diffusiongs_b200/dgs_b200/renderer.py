@@ -22,19 +22,34 @@ class BatchedGaussianRender(torch.autograd.Function):
     def forward(ctx, xyz, features, scaling, rotation, opacity, height, width, C2W, fxfycxcy,
                 scaling_modifier=None, use_gssplat=False, arena_cache=None):
         needs_bwd = any(ctx.needs_input_grad[:5])
+        # Arenas: the inference path re-uses ONE grow-only set (arena_cache["infer"]); a forward that will be
+        # differentiated checks a set out of a pool and its backward returns it, so steady-state training does no
+        # allocator traffic either (cudaMalloc / cudaFree of multi-GB arenas showed up as 40-70 ms step outliers)
+        # while two live forwards (e.g. two renders feeding one loss) never share buffers.
+        cache = None
+        if arena_cache is not None:
+            if needs_bwd:
+                pool = arena_cache.setdefault("pool", [])
+                cache = pool.pop() if pool else {}
+            else:
+                cache = arena_cache.setdefault("infer", {})
         with torch.no_grad():
             images, state = _raster.render_batch_forward(xyz, features, scaling, rotation, opacity, height, width,
-                                                         C2W, fxfycxcy, scaling_modifier,
-                                                         arena_cache=None if needs_bwd else arena_cache)
+                                                         C2W, fxfycxcy, scaling_modifier, arena_cache=cache)
         ctx.state = state
+        ctx.pool = (arena_cache, cache) if needs_bwd and arena_cache is not None else None
         ctx.in_dtypes = (xyz.dtype, features.dtype, scaling.dtype, rotation.dtype, opacity.dtype)
         ctx.num_rendered = state["R"]
         return images
 
     @staticmethod
     def backward(ctx, grad_output):
-        grads = _raster.render_batch_backward(ctx.state, grad_output)
-        ctx.state = None  # release the arenas
+        cache = ctx.pool[1] if ctx.pool else None
+        grads = _raster.render_batch_backward(ctx.state, grad_output, arena_cache=cache)
+        ctx.state = None  # release the arenas ...
+        if ctx.pool:      # ... back into the pool for the next step
+            ctx.pool[0]["pool"].append(cache)
+            ctx.pool = None
         grads = tuple(g.to(dt) for g, dt in zip(grads, ctx.in_dtypes))
         return (*grads, None, None, None, None, None, None, None)
 
