@@ -243,7 +243,12 @@ int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const 
   }
   if (use_m256 && epi != EPI_DGELU_BF16 && !ep.lda && !ep.ldb && N % 256 == 0 && M >= 256 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_m256(A, W, M, N, K, epi, ep, st);
   // wide tiles when they still fill the machine, else 128-wide tiles for more CTAs
-  const bool wide = (N % 256 == 0) && (ceil_div(M, BM) * (N / 256) >= 120);
+  static int wide_min = -1;
+  if (wide_min < 0) {
+    const char* e = getenv("DGS_GEMM_WIDE_MIN");
+    wide_min = e ? atoi(e) : 120;
+  }
+  const bool wide = (N % 256 == 0) && (ceil_div(M, BM) * (N / 256) >= wide_min);
   const int BN = wide ? 256 : 128;
   CUtensorMap tmA, tmB;
   {
