@@ -9,8 +9,11 @@
 // <= 168 registers each) so one CTA's tensor-core work runs under the other's softmax:
 //   warp 0      TMA producer: Q once, K/V blocks of 64 keys through a 3-stage ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:  S_j = Q K_j^T  and  PV_j = P_j V_j
-//   warps 2..5  online softmax, one query row per thread: S_j (TMEM) -> p = ex2(..) -> P_j (bf16, swizzled smem,
-//               A operand of the PV MMA).  O accumulates IN TMEM across all key blocks (the PV MMA adds into it);
+//   warps 2..5  online softmax, one query row per thread: S_j (TMEM) -> p = ex2(..) -> P_j (packed bf16) written BACK
+//               INTO TENSOR MEMORY over the first 32 columns of S_j: the P V MMA and the row-sum MMA read their A
+//               operand from TMEM, so P never touches shared memory (the smem operand fetch of the MMAs, 82 KB per
+//               key block at 128 B/clk, was the binding resource -- more softmax warps made the kernel SLOWER).
+//               O accumulates IN TMEM across all key blocks (the PV MMA adds into it);
 //               the softmax rows rescale it (tcgen05.ld / st) only when their running max grows by more than 2^8
 //               -- otherwise the stale max keeps being used, which is exact after the final 1/l normalisation.
 // S is double-buffered in TMEM so QK^T of block j+1 runs under the softmax of block j.  The softmax is bound by
@@ -28,11 +31,11 @@ namespace dgs {
 
 using namespace ptx;
 
-constexpr int ATT_BM = 128, ATT_BN = 64, ATT_HD = 64, ATT_KV_STAGES = 3, ATT_THREADS = 192;
+constexpr int ATT_BM = 128, ATT_BN = 64, ATT_HD = 64, ATT_KV_STAGES = 4, ATT_THREADS = 192;
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_HD * 2;    // [128 x 64] bf16 (Q, and one P buffer: 128 rows x 64 keys)
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_HD * 2;   // [64 x 64] bf16 (one K or V block)
 constexpr int ATT_ONES_BYTES = 16 * 128;           // [16 x 64] bf16 ones, K-major (B operand of the row-sum MMA)
-constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES * 3 + 2 * ATT_KV_STAGES * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;
+constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES + 2 * ATT_KV_STAGES * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;
 constexpr uint32_t TMEM_S = 0, TMEM_O = 2 * ATT_BN, TMEM_L = TMEM_O + ATT_HD, ATT_TMEM_COLS = 256;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;
 // Probabilities: fp32 ex2.approx per element, rounded to bf16 for the P V MMA.  Measured alternatives (r1): the packed
@@ -52,8 +55,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sQ = smem;
-  uint8_t* sP = sQ + ATT_Q_BYTES;                      // 2 buffers x [128 x 64] bf16
-  uint8_t* sK = sP + 2 * ATT_Q_BYTES;
+  uint8_t* sK = sQ + ATT_Q_BYTES;
   uint8_t* sV = sK + ATT_KV_STAGES * ATT_KV_BYTES;
   uint8_t* sOnes = sV + ATT_KV_STAGES * ATT_KV_BYTES;  // 2 KB, 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ATT_ONES_BYTES);
@@ -133,17 +135,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         mbar_wait(p_full + (j & 1), (uint32_t)(j >> 1) & 1);
         mbar_wait(v_full + s, (uint32_t)(j / ATT_KV_STAGES) & 1);
         tc_fence_after();
-        const uint32_t pbase = smem_u32(sP + (j & 1) * ATT_Q_BYTES);
+        const uint32_t p_tmem = tmem_base + TMEM_S + (uint32_t)((j & 1) * ATT_BN);  // P_j: packed bf16 over S_j
         const uint32_t vbase = smem_u32(sV + s * ATT_KV_BYTES);
         const uint32_t d = tmem_base + TMEM_O;
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; k++) {
-          // A = P: K-major [128 rows x 64 keys]; 16 keys = 32 bytes inside the swizzled 128-byte row
-          const uint64_t pdesc = make_smem_desc_sw128(pbase + (uint32_t)(k * 32), 16, 1024);
-          // B = V: MN-major ([key][64 dims] rows of 128 bytes); 16 keys = 2 groups of 8 rows = 2048 bytes
+          // A = P from TMEM: 16 keys = 8 packed columns;  B = V: MN-major ([key][64 dims] rows of 128 bytes),
+          // 16 keys = 2 groups of 8 rows = 2048 bytes
           const uint64_t vdesc = make_smem_desc_sw128(vbase + (uint32_t)(k * 2048), ATT_KV_BYTES, 1024);
-          umma_bf16(d, pdesc, vdesc, idesc_pv, (j | k) ? 1u : 0u);  // O += P_j V_j (first block overwrites)
-          umma_bf16(tmem_base + TMEM_L, pdesc, odesc + (uint64_t)(2 * k), idesc_l, (j | k) ? 1u : 0u);  // L += rowsum(P_j)
+          umma_bf16_ts(d, p_tmem + (uint32_t)(k * 8), vdesc, idesc_pv, (j | k) ? 1u : 0u);  // O += P_j V_j
+          umma_bf16_ts(tmem_base + TMEM_L, p_tmem + (uint32_t)(k * 8), odesc + (uint64_t)(2 * k), idesc_l, (j | k) ? 1u : 0u);
         }
         umma_commit(pv_full + (j & 1));
         umma_commit(kv_empty + s);
@@ -189,8 +190,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         alpha = ex2_approx((m_run - m_blk) * sl2);  // 0 on the first block
         m_run = m_blk;
       }
-      // P_{j-2} (same smem buffer) must have been consumed, and for a rescale O must hold every earlier block:
-      if (j >= 2) mbar_wait(pv_full + buf, (uint32_t)((j - 2) >> 1) & 1);
+      // (P_j overwrites the head of S_j in TMEM.  The tensor core executes in issue order, so S_j -- observed complete
+      // through s_full -- was written after P V(j-2) had read P_{j-2} from the same columns: nothing to wait for.)
+      // For a rescale O must hold every earlier block:
       if (j >= 1 && __any_sync(0xffffffffu, grow)) {
         mbar_wait(pv_full + (buf ^ 1), (uint32_t)((j - 1) >> 1) & 1);
         tc_fence_after();
@@ -211,22 +213,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tmem_st_wait();
       }
       const float moff = m_run * sl2;
-      uint8_t* p_row = sP + buf * ATT_Q_BYTES + row * 128;
+      uint32_t pk[32];  // 64 probabilities, two bf16 per word: key 2i in the low half (K order of the MMA's A operand)
 #pragma unroll
-      for (int half = 0; half < 2; half++) {
-        float p[32];
-#pragma unroll
-        for (int i = 0; i < 32; i++) p[i] = ex2_approx(fmaf(__uint_as_float(half ? r1[i] : r0[i]), sl2, -moff));
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          uint4 pk;
-          pk.x = pack2_bf16(p[8 * q], p[8 * q + 1]); pk.y = pack2_bf16(p[8 * q + 2], p[8 * q + 3]);
-          pk.z = pack2_bf16(p[8 * q + 4], p[8 * q + 5]); pk.w = pack2_bf16(p[8 * q + 6], p[8 * q + 7]);
-          *reinterpret_cast<uint4*>(p_row + (((half * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
-        }
+      for (int i = 0; i < 16; i++) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(r0[2 * i]), sl2, -moff));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(r0[2 * i + 1]), sl2, -moff));
+        pk[i] = pack2_bf16(p0, p1);
       }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();    // our tcgen05.ld/st of S_j and O are complete before the issuer proceeds
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(r1[2 * i]), sl2, -moff));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(r1[2 * i + 1]), sl2, -moff));
+        pk[16 + i] = pack2_bf16(p0, p1);
+      }
+      tmem_st_32x32(t_s, pk);
+      tmem_st_wait();
+      tc_fence_before();  // our tcgen05.ld of S_j / O and the store of P_j are complete before the issuer proceeds
       mbar_arrive(p_full + buf);
     }
     {  // all blocks accumulated -> normalise and store
