@@ -201,6 +201,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
     const size_t stat = ((size_t)b * H + h) * Np + q0 + row;  // q0 + row < Np always
     const float lse = lse2[stat];                             // +inf on pad rows -> P = 0
     const float dsc = dsum[stat] * AB_SCALE;
+    const uint64_t sl2_2 = pack_f32x2(AB_SL2, AB_SL2), nlse_2 = pack_f32x2(-lse, -lse);
+    const uint64_t scale_2 = pack_f32x2(AB_SCALE, AB_SCALE), ndsc_2 = pack_f32x2(-dsc, -dsc);
     for (int j = 0; j < n_blocks; j++) {
       const int buf = j & 1;
       const int kv_valid = N - j * 64;
@@ -214,7 +216,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
         tmem_ld_32x16(t_lane + DQ_TM_S + (uint32_t)(buf * 64 + ch * 32 + sub * 16), rs);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; i++) p[sub * 16 + i] = ex2_approx(fmaf(__uint_as_float(rs[i]), AB_SL2, -lse));
+        for (int i = 0; i < 16; i += 2) {  // packed fp32 pairs (FFMA2): x = s * c - lse
+          float x0, x1;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1])), sl2_2, nlse_2), x0, x1);
+          p[sub * 16 + i] = ex2_approx(x0);
+          p[sub * 16 + i + 1] = ex2_approx(x1);
+        }
       }
       if (kv_valid < 64) {  // warp-uniform, last key block only: zero-filled tail keys contribute nothing
 #pragma unroll
@@ -233,7 +240,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
         tmem_ld_wait();
         float ds[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) ds[i] = p[sub * 16 + i] * fmaf(__uint_as_float(rp[i]), AB_SCALE, -dsc);
+        for (int i = 0; i < 16; i += 2) {  // dS = P * (dP / 8 - Dsum / 8): FFMA2 + FMUL2
+          const uint64_t t = fma_f32x2(pack_f32x2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])), scale_2, ndsc_2);
+          unpack_f32x2(mul_f32x2(pack_f32x2(p[sub * 16 + i], p[sub * 16 + i + 1]), t), ds[i], ds[i + 1]);
+        }
 #pragma unroll
         for (int q = 0; q < 2; q++) {
           uint4 pk;
@@ -402,10 +412,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
     const bool key_valid = k0 + row < N;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const size_t stat_base = ((size_t)b * H + h) * Np;
-    // per query block, softmax threads 0..127 stage lse2[64] | Dsum[64]/8 in smem (prefetched one block ahead)
+    // per query block, softmax threads 0..127 stage -lse2[64] | -Dsum[64]/8 in smem (prefetched one block ahead)
     const int st_t = (warp - 2) * 32 + lane;  // 0..255
     const float* stat_src = (st_t < 64 ? lse2 : dsum) + stat_base + (st_t & 63);
-    const float stat_mul = st_t < 64 ? 1.0f : AB_SCALE;
+    const float stat_mul = st_t < 64 ? -1.0f : -AB_SCALE;  // staged NEGATED: they are the addends of the packed FMAs
+    const uint64_t sl2_2 = pack_f32x2(AB_SL2, AB_SL2), scale_2 = pack_f32x2(AB_SCALE, AB_SCALE);
     float pre = st_t < 128 ? stat_src[0] * stat_mul : 0.f;  // block 0 (Np >= 128: in bounds)
     for (int i = 0; i < n_blocks; i++) {
       float* st = s_stat + (i & 1) * 128;
@@ -424,11 +435,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 16; c += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(st + c0 + c);  // smem broadcast; pad queries: +inf -> P = 0
-          p[sub * 16 + c] = ex2_approx(fmaf(__uint_as_float(rs[c]), AB_SL2, -l4.x));
-          p[sub * 16 + c + 1] = ex2_approx(fmaf(__uint_as_float(rs[c + 1]), AB_SL2, -l4.y));
-          p[sub * 16 + c + 2] = ex2_approx(fmaf(__uint_as_float(rs[c + 2]), AB_SL2, -l4.z));
-          p[sub * 16 + c + 3] = ex2_approx(fmaf(__uint_as_float(rs[c + 3]), AB_SL2, -l4.w));
+          // smem broadcast of -lse2 for 4 queries (pad queries: -inf -> P = 0), consumed as two packed fp32 pairs
+          const ulonglong2 l4 = *reinterpret_cast<const ulonglong2*>(st + c0 + c);
+          float x0, x1, x2, x3;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(rs[c]), __uint_as_float(rs[c + 1])), sl2_2, l4.x), x0, x1);
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(rs[c + 2]), __uint_as_float(rs[c + 3])), sl2_2, l4.y), x2, x3);
+          p[sub * 16 + c] = ex2_approx(x0);
+          p[sub * 16 + c + 1] = ex2_approx(x1);
+          p[sub * 16 + c + 2] = ex2_approx(x2);
+          p[sub * 16 + c + 3] = ex2_approx(x3);
         }
       }
       if (!key_valid) {  // zero-filled tail key rows (last key block only)
@@ -457,11 +472,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
         float ds[16];
 #pragma unroll
         for (int c = 0; c < 16; c += 4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + c0 + c);
-          ds[c] = p[sub * 16 + c] * fmaf(__uint_as_float(rp[c]), AB_SCALE, -d4.x);
-          ds[c + 1] = p[sub * 16 + c + 1] * fmaf(__uint_as_float(rp[c + 1]), AB_SCALE, -d4.y);
-          ds[c + 2] = p[sub * 16 + c + 2] * fmaf(__uint_as_float(rp[c + 2]), AB_SCALE, -d4.z);
-          ds[c + 3] = p[sub * 16 + c + 3] * fmaf(__uint_as_float(rp[c + 3]), AB_SCALE, -d4.w);
+          const ulonglong2 d4 = *reinterpret_cast<const ulonglong2*>(st + 64 + c0 + c);  // -Dsum / 8 of 4 queries
+          const uint64_t t0 = fma_f32x2(pack_f32x2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), scale_2, d4.x);
+          const uint64_t t1 = fma_f32x2(pack_f32x2(__uint_as_float(rp[c + 2]), __uint_as_float(rp[c + 3])), scale_2, d4.y);
+          unpack_f32x2(mul_f32x2(pack_f32x2(p[sub * 16 + c], p[sub * 16 + c + 1]), t0), ds[c], ds[c + 1]);
+          unpack_f32x2(mul_f32x2(pack_f32x2(p[sub * 16 + c + 2], p[sub * 16 + c + 3]), t1), ds[c + 2], ds[c + 3]);
         }
 #pragma unroll
         for (int q = 0; q < 2; q++) {

@@ -41,13 +41,17 @@ constexpr float ATT_RESCALE_THRESHOLD = 8.0f;
 // Probabilities: fp32 ex2.approx per element, rounded to bf16 for the P V MMA.  Measured alternatives (r1): the packed
 // half-precision MUFU forms do not help -- ex2.approx.ftz.bf16x2 compiles to two MUFU.EX2.BF16 (same 135 us, error
 // 2.1e-3 -> 4.5e-3), and an fp16 P against the bf16 V is rejected by the hardware (kind::f16 needs A and B of one
-// format: illegal instruction); an FMA-pipe polynomial for a fraction of the exponentials was slower (issue-bound).
+// format: illegal instruction).
+constexpr int ATT_POLY_DEFAULT = 0;
 
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// POLY_OF_8: how many of every 8 exponentials are evaluated by a degree-3 polynomial on the FMA/ALU pipes instead of
+// the MUFU pipe (which is the busiest unit of this kernel: XU 58 %, 27 % of the stall samples on MUFU.EX2)
+template <int POLY_OF_8>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int Np, int N, int H) {
@@ -214,16 +218,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       const float moff = m_run * sl2;
       uint32_t pk[32];  // 64 probabilities, two bf16 per word: key 2i in the low half (K order of the MMA's A operand)
+      const uint64_t sl2_2 = pack_f32x2(sl2, sl2), moff_2 = pack_f32x2(-moff, -moff);  // x = s * sl2 - moff as FFMA2
 #pragma unroll
       for (int i = 0; i < 16; i++) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(r0[2 * i]), sl2, -moff));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(r0[2 * i + 1]), sl2, -moff));
+        float x0, x1;
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1])), sl2_2, moff_2), x0, x1);
+        const float p0 = (((2 * i) & 7) < POLY_OF_8) ? ex2_poly3(x0) : ex2_approx(x0);
+        const float p1 = (((2 * i + 1) & 7) < POLY_OF_8) ? ex2_poly3(x1) : ex2_approx(x1);
         pk[i] = pack2_bf16(p0, p1);
       }
 #pragma unroll
       for (int i = 0; i < 16; i++) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(r1[2 * i]), sl2, -moff));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(r1[2 * i + 1]), sl2, -moff));
+        float x0, x1;
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1])), sl2_2, moff_2), x0, x1);
+        const float p0 = (((2 * i) & 7) < POLY_OF_8) ? ex2_poly3(x0) : ex2_approx(x0);
+        const float p1 = (((2 * i + 1) & 7) < POLY_OF_8) ? ex2_poly3(x1) : ex2_approx(x1);
         pk[16 + i] = pack2_bf16(p0, p1);
       }
       tmem_st_32x32(t_s, pk);
@@ -287,14 +296,20 @@ int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, 
   if (rc) return rc;
   rc = make_tmap_bf16(&tm_kv, qkv, 3, dims, str, box_kv);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    configured = true;
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("DGS_ATT_POLY");
+    poly = e ? atoi(e) : ATT_POLY_DEFAULT;
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
   }
   dim3 grid(ceil_div(N, ATT_BM), H, B);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  DGS_CUDA_OK(launch_pdl(attention_fwd_kernel, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tm_q, tm_kv, o, lse2, Np, N, H));
+  auto kern = poly == 1 ? attention_fwd_kernel<1> : poly == 2 ? attention_fwd_kernel<2> : poly >= 3 ? attention_fwd_kernel<3>
+                                                                                                   : attention_fwd_kernel<0>;
+  DGS_CUDA_OK(launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tm_q, tm_kv, o, lse2, Np, N, H));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }

@@ -180,6 +180,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// ---- packed fp32 pairs (sm_100: FFMA2 / FMUL2 -- two fp32 operations per lane per issued instruction) ----
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f via the 1.5*2^23 magic constant, degree-3
 // near-minimax polynomial for 2^f on [-0.5, 0.5] (max rel err 7.7e-5), exponent patched in with integer adds.
 // x <= ~100; -inf and very negative inputs clamp to 2^-126 (~1e-38, i.e. zero at bf16/fp32-sum precision).

@@ -35,7 +35,7 @@ def timeit(fn, iters=20, warmup=3):
 
 def main():
     L = _lib.lib()
-    tag = {k: os.environ.get(k) for k in ("DGS_ATT_EXP", "DGS_GEMM_2CTA", "DGS_GEMM_M256") if os.environ.get(k)}
+    tag = {k: os.environ.get(k) for k in ("DGS_ATT_POLY", "DGS_GEMM_2CTA", "DGS_GEMM_M256") if os.environ.get(k)}
     B, N, H, D = 1, 4098, 16, 1024
     qkv = (torch.randn(B, N, 3, H, 64, device=DEV) * 1.5).to(torch.bfloat16)
     out = torch.empty(B, N, D, dtype=torch.bfloat16, device=DEV)
