@@ -7,12 +7,14 @@
 // Two kernels, no atomics, every operand read straight from the [B, N, 3, H, 64] qkv tensor / the [B, N, H*64] dO
 // tensor through 3-D TMA maps and written straight into the [B, N, 3, H, 64] dqkv tensor:
 //   attn_bwd_dq_kernel   one CTA per (128 queries, head, sample), loops over 64-key blocks:
-//                        S = Q K_j^T, dP = dO V_j^T (TMEM) -> dS_j (bf16, smem) -> dQ += dS_j K_j (TMEM accumulator;
-//                        K_j consumed MN-major from the same smem tile that fed S)
+//                        S = Q K_j^T, dP = dO V_j^T (TMEM) -> dS_j (bf16, written back into TENSOR MEMORY over dP_j) ->
+//                        dQ += dS_j K_j (A operand from TMEM, TMEM accumulator; K_j consumed MN-major from the same
+//                        smem tile that fed S)
 //   attn_bwd_dkv_kernel  one CTA per (128 keys, head, sample), loops over 64-query blocks, works on the TRANSPOSED
 //                        scores so that the key is the TMEM lane / the thread:  S^T = K Q_i^T, dP^T = V dO_i^T ->
-//                        P^T, dS^T (bf16, smem, K-major A operands) -> dV += P^T dO_i, dK += dS^T Q_i (dO_i, Q_i
-//                        consumed MN-major from the tiles that fed S^T / dP^T)
+//                        P^T (bf16, smem, K-major A operand), dS^T (bf16, written back into TENSOR MEMORY over dP^T: the
+//                        dK MMA reads its A operand from TMEM) -> dV += P^T dO_i, dK += dS^T Q_i (dO_i, Q_i consumed
+//                        MN-major from the tiles that fed S^T / dP^T)
 // Both: 320 threads (TMA warp, MMA warp, 8 softmax warps), 2 CTAs per SM, 256 TMEM columns.  No row reductions are
 // needed in the backward (lse2 and Dsum are inputs), so a row is split between two threads (32 of the 64 columns each)
 // at no cost: 16 softmax warps per SM hide the TMEM-load / MUFU latencies that bound the 4-warp version
@@ -80,7 +82,8 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, const 
 // ---------------------------------------------------------------------------------------------------------------
 // dQ
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int DQ_SMEM = 2 * AB_T128 /*Q, dO*/ + 2 * AB_T128 /*dS x2*/ + 2 * AB_STAGES * AB_T64 /*K, V*/ + 1024 + 256;
+constexpr int DQ_STAGES = 3;
+constexpr int DQ_SMEM = 2 * AB_T128 /*Q, dO*/ + 2 * DQ_STAGES * AB_T64 /*K, V*/ + 1024 + 256;
 constexpr uint32_t DQ_TM_S = 0 /* 2 buffers x 64 */, DQ_TM_DP = 128, DQ_TM_DQ = 192, DQ_TMEM_COLS = 256;
 
 __global__ void __launch_bounds__(AB_THREADS, 2)
@@ -92,17 +95,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + AB_T128;
-  uint8_t* sdS = sdO + AB_T128;  // 2 buffers
-  uint8_t* sK = sdS + 2 * AB_T128;
-  uint8_t* sV = sK + AB_STAGES * AB_T64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AB_STAGES * AB_T64);
+  uint8_t* sK = sdO + AB_T128;
+  uint8_t* sV = sK + DQ_STAGES * AB_T64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + DQ_STAGES * AB_T64);
   uint64_t* q_full = bars;                    // Q + dO landed
-  uint64_t* kv_full = bars + 1;               // [AB_STAGES]
-  uint64_t* kv_empty = kv_full + AB_STAGES;   // [AB_STAGES]
-  uint64_t* s_full = kv_empty + AB_STAGES;    // [2] S of block j in TMEM (double-buffered: issued one block ahead)
+  uint64_t* kv_full = bars + 1;               // [DQ_STAGES]
+  uint64_t* kv_empty = kv_full + DQ_STAGES;   // [DQ_STAGES]
+  uint64_t* s_full = kv_empty + DQ_STAGES;    // [2] S of block j in TMEM (double-buffered: issued one block ahead)
   uint64_t* dp_full = s_full + 2;             // dP of block j in TMEM (single buffer)
-  uint64_t* ds_full = dp_full + 1;            // [2] dS_j written (and S/dP read out of TMEM)
-  uint64_t* dq_done = ds_full + 2;            // [2] dQ MMA of block j retired (dS buffer free)
+  uint64_t* ds_full = dp_full + 1;            // [2] dS_j written over dP_j in TMEM (and S_j read out)
+  uint64_t* dq_done = ds_full + 2;            // [2] dQ MMA of block j retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,7 +117,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
     prefetch_tmap(&tm_kv64);
     prefetch_tmap(&tm_do128);
     mbar_init(q_full, 1);
-    for (int s = 0; s < AB_STAGES; s++) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
+    for (int s = 0; s < DQ_STAGES; s++) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
     mbar_init(dp_full, 1);
     for (int s = 0; s < 2; s++) { mbar_init(s_full + s, 1); mbar_init(ds_full + s, AB_SOFT); mbar_init(dq_done + s, 1); }
     fence_barrier_init();
@@ -137,8 +139,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
       tma_load_3d(sQ, &tm_q128, q_full, h * AB_HD, q0, b);
       tma_load_3d(sdO, &tm_do128, q_full, h * AB_HD, q0, b);
       for (int j = 0; j < n_blocks; j++) {
-        const int s = j % AB_STAGES;
-        mbar_wait(kv_empty + s, ((uint32_t)(j / AB_STAGES) & 1) ^ 1);
+        const int s = j % DQ_STAGES;
+        mbar_wait(kv_empty + s, ((uint32_t)(j / DQ_STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(kv_full + s, 2 * AB_T64);
         tma_load_3d(sK + s * AB_T64, &tm_kv64, kv_full + s, D + h * AB_HD, j * 64, b);
         tma_load_3d(sV + s * AB_T64, &tm_kv64, kv_full + s, 2 * D + h * AB_HD, j * 64, b);
@@ -153,8 +155,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
       // Issue order (the softmax needs S first and dP only for its second half, so S runs one block ahead):
       //   S(0) dP(0) | S(1) .. wait dS(0) .. dQ(0) dP(1) | S(2) .. wait dS(1) .. dQ(1) dP(2) | ...
       auto issue_s = [&](int j) {
-        const int s = j % AB_STAGES;
-        mbar_wait(kv_full + s, (uint32_t)(j / AB_STAGES) & 1);
+        const int s = j % DQ_STAGES;
+        mbar_wait(kv_full + s, (uint32_t)(j / DQ_STAGES) & 1);
         tc_fence_after();
         const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s * AB_T64), 16, 1024);
         const uint32_t d = tmem_base + DQ_TM_S + (uint32_t)((j & 1) * 64);
@@ -163,7 +165,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
         umma_commit(s_full + (j & 1));
       };
       auto issue_dp = [&](int j) {  // kv_full(j) already observed by issue_s(j)
-        const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + (j % AB_STAGES) * AB_T64), 16, 1024);
+        const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + (j % DQ_STAGES) * AB_T64), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; k++)
           umma_bf16(tmem_base + DQ_TM_DP, dodesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
@@ -173,20 +175,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
       issue_s(0);
       issue_dp(0);
       for (int j = 0; j < n_blocks; j++) {
-        const int s = j % AB_STAGES;
+        const int s = j % DQ_STAGES;
         // S buffer (j+1)&1 was last read by the softmax of block j-1, whose ds_full was observed one iteration ago
         if (j + 1 < n_blocks) issue_s(j + 1);
         mbar_wait(ds_full + (j & 1), (uint32_t)(j >> 1) & 1);
         tc_fence_after();
-        const uint32_t dsbase = smem_u32(sdS + (j & 1) * AB_T128);
         const uint32_t kbase = smem_u32(sK + s * AB_T64);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          // A = dS_j: K-major [128 q x 64 keys], 16 keys = 32 B inside the swizzled row;
+          // A = dS_j from TENSOR MEMORY: packed bf16 pairs written by the softmax threads over their own dP columns --
+          // keys 0..31 in columns [0,16), keys 32..63 in columns [32,48) of the dP buffer; 16 keys = 8 columns.
           // B = K_j: MN-major ([key][64 dims] rows of 128 B), 16 keys = 2 groups of 8 rows = 2048 B
-          const uint64_t adesc = make_smem_desc_sw128(dsbase + (uint32_t)(k * 32), 16, 1024);
+          const uint32_t a_tmem = tmem_base + DQ_TM_DP + (uint32_t)((k >> 1) * 32 + (k & 1) * 8);
           const uint64_t bdesc = make_smem_desc_sw128(kbase + (uint32_t)(k * 2048), AB_T64, 1024);
-          umma_bf16(tmem_base + DQ_TM_DQ, adesc, bdesc, idesc_kmn, (j | k) ? 1u : 0u);
+          umma_bf16_ts(tmem_base + DQ_TM_DQ, a_tmem, bdesc, idesc_kmn, (j | k) ? 1u : 0u);
         }
         umma_commit(dq_done + (j & 1));
         umma_commit(kv_empty + s);
@@ -231,8 +233,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
       // ---- phase 2: dS = P * (dP - Dsum) / 8 ----
       mbar_wait(dp_full, (uint32_t)j & 1);
       tc_fence_after();
-      if (j >= 2) mbar_wait(dq_done + buf, (uint32_t)((j - 2) >> 1) & 1);  // dS buffer consumed
-      uint8_t* ds_row = sdS + buf * AB_T128 + row * 128;
+      // (dP_j is complete => every earlier MMA, including dQ(j-1) which read dS_{j-1} from these columns, is too)
+      uint32_t dsw[16];  // this thread's 32 dS values, two bf16 per word
 #pragma unroll
       for (int sub = 0; sub < 2; sub++) {
         uint32_t rp[16];
@@ -245,14 +247,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
           unpack_f32x2(mul_f32x2(pack_f32x2(p[sub * 16 + i], p[sub * 16 + i + 1]), t), ds[i], ds[i + 1]);
         }
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-          uint4 pk;
-          pk.x = ab_pack2(ds[8 * q], ds[8 * q + 1]); pk.y = ab_pack2(ds[8 * q + 2], ds[8 * q + 3]);
-          pk.z = ab_pack2(ds[8 * q + 4], ds[8 * q + 5]); pk.w = ab_pack2(ds[8 * q + 6], ds[8 * q + 7]);
-          *reinterpret_cast<uint4*>(ds_row + (((ch * 4 + sub * 2 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
-        }
+        for (int i = 0; i < 8; i++) dsw[sub * 8 + i] = ab_pack2(ds[2 * i], ds[2 * i + 1]);
       }
-      fence_proxy_async();
+      tmem_st_32x16(t_lane + DQ_TM_DP + (uint32_t)(ch * 32), dsw);  // over the head of this thread's own dP columns
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(ds_full + buf);
     }
@@ -286,7 +284,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
 // ---------------------------------------------------------------------------------------------------------------
 // dK, dV
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int DKV_SMEM = 2 * AB_T128 /*K, V*/ + 2 * AB_T128 /*P^T, dS^T*/ + 2 * AB_STAGES * AB_T64 /*Q, dO*/ +
+constexpr int DKV_SMEM = 2 * AB_T128 /*K, V*/ + AB_T128 /*P^T*/ + 2 * AB_STAGES * AB_T64 /*Q, dO*/ +
                          2 * 128 * 4 /*lse2 | Dsum of a query block, x2*/ + 1024 + 256;
 constexpr uint32_t DKV_TM_ST = 0, DKV_TM_DPT = 64, DKV_TM_DV = 128, DKV_TM_DK = 192, DKV_TMEM_COLS = 256;
 
@@ -300,8 +298,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
   uint8_t* sK = smem;
   uint8_t* sV = sK + AB_T128;
   uint8_t* sPt = sV + AB_T128;
-  uint8_t* sdSt = sPt + AB_T128;
-  uint8_t* sQ = sdSt + AB_T128;
+  uint8_t* sQ = sPt + AB_T128;
   uint8_t* sdO = sQ + AB_STAGES * AB_T64;
   float* s_stat = reinterpret_cast<float*>(sdO + AB_STAGES * AB_T64);  // [2][128]: lse2[64] | Dsum/8 [64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 2 * 128);
@@ -361,7 +358,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
       constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 64, false, true);
       const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
-      const uint32_t ptbase = smem_u32(sPt), dstbase = smem_u32(sdSt);
+      const uint32_t ptbase = smem_u32(sPt);
       // Issue order: the softmax of block i+1 only needs S^T to start (exp), so S^T(i+1) goes in FRONT of the
       // dV/dK accumulation of block i, and dP^T(i+1) behind it:
       //   St(0) dPt(0) | wait PT(0) : St(1) dV(0) dK(0) dPt(1) | wait PT(1) : St(2) dV(1) dK(1) dPt(2) | ...
@@ -394,11 +391,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
 #pragma unroll
         for (int k = 0; k < 4; k++) {  // reduction over the 64 queries of the block, 16 per instruction
           const uint64_t pdesc = make_smem_desc_sw128(ptbase + (uint32_t)(k * 32), 16, 1024);
-          const uint64_t dsdesc = make_smem_desc_sw128(dstbase + (uint32_t)(k * 32), 16, 1024);
+          // dS^T comes from TENSOR MEMORY: packed bf16 pairs over the dP^T buffer, queries 0..31 in columns [0,16),
+          // queries 32..63 in columns [32,48) (each softmax thread overwrites the head of its own dP^T columns)
+          const uint32_t ds_tmem = tmem_base + DKV_TM_DPT + (uint32_t)((k >> 1) * 32 + (k & 1) * 8);
           const uint64_t dob = make_smem_desc_sw128(dobase + (uint32_t)(k * 2048), AB_T64, 1024);  // MN-major
           const uint64_t qb = make_smem_desc_sw128(qbase + (uint32_t)(k * 2048), AB_T64, 1024);    // MN-major
           umma_bf16(tmem_base + DKV_TM_DV, pdesc, dob, idesc_kmn, (i | k) ? 1u : 0u);   // dV += P^T dO_i
-          umma_bf16(tmem_base + DKV_TM_DK, dsdesc, qb, idesc_kmn, (i | k) ? 1u : 0u);   // dK += dS^T Q_i
+          umma_bf16_ts(tmem_base + DKV_TM_DK, ds_tmem, qb, idesc_kmn, (i | k) ? 1u : 0u);  // dK += dS^T Q_i
         }
         umma_commit(acc_done);
         umma_commit(q_empty + s);
@@ -450,9 +449,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
 #pragma unroll
         for (int c = 0; c < 32; c++) p[c] = 0.f;
       }
-      if (i >= 1) mbar_wait(acc_done, (uint32_t)(i - 1) & 1);  // P^T / dS^T buffers consumed by dV/dK(i-1)
+      if (i >= 1) mbar_wait(acc_done, (uint32_t)(i - 1) & 1);  // P^T buffer consumed by dV(i-1)
       uint8_t* pt_row = sPt + row * 128;
-      uint8_t* dst_row = sdSt + row * 128;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         uint4 pk;
@@ -463,6 +461,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
       // ---- phase 2: dS^T = P^T * (dP^T - Dsum) / 8 ----
       mbar_wait(dpt_full, (uint32_t)i & 1);
       tc_fence_after();
+      uint32_t dsw[16];  // this thread's 32 dS^T values, two bf16 per word
 #pragma unroll
       for (int sub = 0; sub < 2; sub++) {
         const int c0 = ch * 32 + sub * 16;
@@ -479,13 +478,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
           unpack_f32x2(mul_f32x2(pack_f32x2(p[sub * 16 + c + 2], p[sub * 16 + c + 3]), t1), ds[c + 2], ds[c + 3]);
         }
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-          uint4 dk;
-          dk.x = ab_pack2(ds[8 * q], ds[8 * q + 1]); dk.y = ab_pack2(ds[8 * q + 2], ds[8 * q + 3]);
-          dk.z = ab_pack2(ds[8 * q + 4], ds[8 * q + 5]); dk.w = ab_pack2(ds[8 * q + 6], ds[8 * q + 7]);
-          *reinterpret_cast<uint4*>(dst_row + (((ch * 4 + sub * 2 + q) ^ (row & 7)) << 4)) = dk;
-        }
+        for (int e = 0; e < 8; e++) dsw[sub * 8 + e] = ab_pack2(ds[2 * e], ds[2 * e + 1]);
       }
+      tmem_st_32x16(t_lane + DKV_TM_DPT + (uint32_t)(ch * 32), dsw);
+      tmem_st_wait();
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(pt_full);
