@@ -12,9 +12,9 @@
 //                        smem tile that fed S)
 //   attn_bwd_dkv_kernel  one CTA per (128 keys, head, sample), loops over 64-query blocks, works on the TRANSPOSED
 //                        scores so that the key is the TMEM lane / the thread:  S^T = K Q_i^T, dP^T = V dO_i^T ->
-//                        P^T (bf16, smem, K-major A operand), dS^T (bf16, written back into TENSOR MEMORY over dP^T: the
-//                        dK MMA reads its A operand from TMEM) -> dV += P^T dO_i, dK += dS^T Q_i (dO_i, Q_i consumed
-//                        MN-major from the tiles that fed S^T / dP^T)
+//                        P^T, dS^T (bf16, written back into TENSOR MEMORY over dP^T: the dV / dK MMAs read their A operands
+//                        from TMEM) -> dV += P^T dO_i, dK += dS^T Q_i (dO_i, Q_i consumed MN-major from the tiles that
+//                        fed S^T / dP^T)
 // Both: 320 threads (TMA warp, MMA warp, 8 softmax warps), 2 CTAs per SM, 256 TMEM columns.  No row reductions are
 // needed in the backward (lse2 and Dsum are inputs), so a row is split between two threads (32 of the 64 columns each)
 // at no cost: 16 softmax warps per SM hide the TMEM-load / MUFU latencies that bound the 4-warp version
@@ -284,7 +284,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
 // ---------------------------------------------------------------------------------------------------------------
 // dK, dV
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int DKV_SMEM = 2 * AB_T128 /*K, V*/ + AB_T128 /*P^T*/ + 2 * AB_STAGES * AB_T64 /*Q, dO*/ +
+constexpr int DKV_STAGES = 3;
+constexpr int DKV_SMEM = 2 * AB_T128 /*K, V*/ + 2 * DKV_STAGES * AB_T64 /*Q, dO*/ +
                          2 * 128 * 4 /*lse2 | Dsum of a query block, x2*/ + 1024 + 256;
 constexpr uint32_t DKV_TM_ST = 0, DKV_TM_DPT = 64, DKV_TM_DV = 128, DKV_TM_DK = 192, DKV_TMEM_COLS = 256;
 
@@ -297,15 +298,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sK = smem;
   uint8_t* sV = sK + AB_T128;
-  uint8_t* sPt = sV + AB_T128;
-  uint8_t* sQ = sPt + AB_T128;
-  uint8_t* sdO = sQ + AB_STAGES * AB_T64;
-  float* s_stat = reinterpret_cast<float*>(sdO + AB_STAGES * AB_T64);  // [2][128]: lse2[64] | Dsum/8 [64]
+  uint8_t* sQ = sV + AB_T128;
+  uint8_t* sdO = sQ + DKV_STAGES * AB_T64;
+  float* s_stat = reinterpret_cast<float*>(sdO + DKV_STAGES * AB_T64);  // [2][128]: lse2[64] | Dsum/8 [64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 2 * 128);
   uint64_t* kv_full = bars;
-  uint64_t* q_full = bars + 1;              // [AB_STAGES]
-  uint64_t* q_empty = q_full + AB_STAGES;   // [AB_STAGES]
-  uint64_t* st_full = q_empty + AB_STAGES;  // S^T of block i in TMEM
+  uint64_t* q_full = bars + 1;              // [DKV_STAGES]
+  uint64_t* q_empty = q_full + DKV_STAGES;   // [DKV_STAGES]
+  uint64_t* st_full = q_empty + DKV_STAGES;  // S^T of block i in TMEM
   uint64_t* dpt_full = st_full + 1;         // dP^T of block i in TMEM
   uint64_t* pt_full = dpt_full + 1;         // P^T, dS^T written (and S^T/dP^T read out of TMEM)
   uint64_t* acc_done = pt_full + 1;         // dV/dK MMAs of block i retired (P^T/dS^T buffers free)
@@ -321,7 +321,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
     prefetch_tmap(&tm_q64);
     prefetch_tmap(&tm_do64);
     mbar_init(kv_full, 1);
-    for (int s = 0; s < AB_STAGES; s++) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, 1); }
+    for (int s = 0; s < DKV_STAGES; s++) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, 1); }
     mbar_init(st_full, 1);
     mbar_init(dpt_full, 1);
     mbar_init(pt_full, AB_SOFT);
@@ -345,8 +345,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
       tma_load_3d(sK, &tm_kv128, kv_full, D + h * AB_HD, k0, b);
       tma_load_3d(sV, &tm_kv128, kv_full, 2 * D + h * AB_HD, k0, b);
       for (int i = 0; i < n_blocks; i++) {
-        const int s = i % AB_STAGES;
-        mbar_wait(q_empty + s, ((uint32_t)(i / AB_STAGES) & 1) ^ 1);
+        const int s = i % DKV_STAGES;
+        mbar_wait(q_empty + s, ((uint32_t)(i / DKV_STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(q_full + s, 2 * AB_T64);
         tma_load_3d(sQ + s * AB_T64, &tm_q64, q_full + s, h * AB_HD, i * 64, b);
         tma_load_3d(sdO + s * AB_T64, &tm_do64, q_full + s, h * AB_HD, i * 64, b);
@@ -358,13 +358,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
       constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 64, false, true);
       const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
-      const uint32_t ptbase = smem_u32(sPt);
       // Issue order: the softmax of block i+1 only needs S^T to start (exp), so S^T(i+1) goes in FRONT of the
       // dV/dK accumulation of block i, and dP^T(i+1) behind it:
       //   St(0) dPt(0) | wait PT(0) : St(1) dV(0) dK(0) dPt(1) | wait PT(1) : St(2) dV(1) dK(1) dPt(2) | ...
       auto issue_st = [&](int i) {
-        const int s = i % AB_STAGES;
-        mbar_wait(q_full + s, (uint32_t)(i / AB_STAGES) & 1);
+        const int s = i % DKV_STAGES;
+        mbar_wait(q_full + s, (uint32_t)(i / DKV_STAGES) & 1);
         tc_fence_after();
         const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + s * AB_T64), 16, 1024);
 #pragma unroll
@@ -373,7 +372,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
         umma_commit(st_full);
       };
       auto issue_dpt = [&](int i) {
-        const uint64_t dodesc = make_smem_desc_sw128(smem_u32(sdO + (i % AB_STAGES) * AB_T64), 16, 1024);
+        const uint64_t dodesc = make_smem_desc_sw128(smem_u32(sdO + (i % DKV_STAGES) * AB_T64), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; k++)  // dP^T = V dO_i^T
           umma_bf16(tmem_base + DKV_TM_DPT, vdesc + (uint64_t)(2 * k), dodesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
@@ -383,20 +382,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
       issue_st(0);
       issue_dpt(0);
       for (int i = 0; i < n_blocks; i++) {
-        const int s = i % AB_STAGES;
+        const int s = i % DKV_STAGES;
         mbar_wait(pt_full, (uint32_t)i & 1);  // softmax(i) has read S^T(i), dP^T(i) and written P^T, dS^T
         tc_fence_after();
         if (i + 1 < n_blocks) issue_st(i + 1);
         const uint32_t qbase = smem_u32(sQ + s * AB_T64), dobase = smem_u32(sdO + s * AB_T64);
 #pragma unroll
         for (int k = 0; k < 4; k++) {  // reduction over the 64 queries of the block, 16 per instruction
-          const uint64_t pdesc = make_smem_desc_sw128(ptbase + (uint32_t)(k * 32), 16, 1024);
-          // dS^T comes from TENSOR MEMORY: packed bf16 pairs over the dP^T buffer, queries 0..31 in columns [0,16),
-          // queries 32..63 in columns [32,48) (each softmax thread overwrites the head of its own dP^T columns)
+          // P^T and dS^T come from TENSOR MEMORY: packed bf16 pairs written by the softmax threads over their own
+          // dP^T columns -- for queries 0..31: dS^T in columns [0,16), P^T in [16,32); for queries 32..63: [32,48), [48,64)
           const uint32_t ds_tmem = tmem_base + DKV_TM_DPT + (uint32_t)((k >> 1) * 32 + (k & 1) * 8);
+          const uint32_t p_tmem = ds_tmem + 16u;
           const uint64_t dob = make_smem_desc_sw128(dobase + (uint32_t)(k * 2048), AB_T64, 1024);  // MN-major
           const uint64_t qb = make_smem_desc_sw128(qbase + (uint32_t)(k * 2048), AB_T64, 1024);    // MN-major
-          umma_bf16(tmem_base + DKV_TM_DV, pdesc, dob, idesc_kmn, (i | k) ? 1u : 0u);   // dV += P^T dO_i
+          umma_bf16_ts(tmem_base + DKV_TM_DV, p_tmem, dob, idesc_kmn, (i | k) ? 1u : 0u);   // dV += P^T dO_i
           umma_bf16_ts(tmem_base + DKV_TM_DK, ds_tmem, qb, idesc_kmn, (i | k) ? 1u : 0u);  // dK += dS^T Q_i
         }
         umma_commit(acc_done);
@@ -449,15 +448,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
 #pragma unroll
         for (int c = 0; c < 32; c++) p[c] = 0.f;
       }
-      if (i >= 1) mbar_wait(acc_done, (uint32_t)(i - 1) & 1);  // P^T buffer consumed by dV(i-1)
-      uint8_t* pt_row = sPt + row * 128;
+      uint32_t pw[16];  // P^T of this thread's 32 queries, two bf16 per word
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        uint4 pk;
-        pk.x = ab_pack2(p[8 * q], p[8 * q + 1]); pk.y = ab_pack2(p[8 * q + 2], p[8 * q + 3]);
-        pk.z = ab_pack2(p[8 * q + 4], p[8 * q + 5]); pk.w = ab_pack2(p[8 * q + 6], p[8 * q + 7]);
-        *reinterpret_cast<uint4*>(pt_row + (((ch * 4 + q) ^ (row & 7)) << 4)) = pk;  // 128B swizzle
-      }
+      for (int e = 0; e < 16; e++) pw[e] = ab_pack2(p[2 * e], p[2 * e + 1]);
       // ---- phase 2: dS^T = P^T * (dP^T - Dsum) / 8 ----
       mbar_wait(dpt_full, (uint32_t)i & 1);
       tc_fence_after();
@@ -480,9 +473,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
 #pragma unroll
         for (int e = 0; e < 8; e++) dsw[sub * 8 + e] = ab_pack2(ds[2 * e], ds[2 * e + 1]);
       }
+      // dP^T(i) complete => dV/dK(i-1), which read the previous P^T / dS^T from these columns, are complete too
       tmem_st_32x16(t_lane + DKV_TM_DPT + (uint32_t)(ch * 32), dsw);
+      tmem_st_32x16(t_lane + DKV_TM_DPT + (uint32_t)(ch * 32 + 16), pw);
       tmem_st_wait();
-      fence_proxy_async();
       tc_fence_before();
       mbar_arrive(pt_full);
     }
