@@ -290,6 +290,9 @@ int dgs_attention_bwd(const void* qkv, const void* out, const void* dout, float*
 int dgs_gemm_bf16_ex(const void* A, const void* W, const float* bias, const float* gate, void* out, void* aux,
                      const float* resid, int M, int N, int K, int lda, int ldb, int epi, int ldc, int gate_stride,
                      int rows_per_sample, void* stream);
+/* out[M,N] (fp32, row stride ldc) = A^T W for A [K,M], W [K,N] bf16 row-major with row strides lda / ldb (0 = M / N):
+ * the weight-gradient GEMM (K = tokens) on MN-major tcgen05 operands -- no transposed copies */
+int dgs_gemm_bf16_tn(const void* A, const void* W, float* out, int M, int N, int K, int lda, int ldb, int ldc, void* stream);
 /* backward of dgs_ln_modulate: dx (+)= ..., dshift/dscale [B, mod_stride] += ..., dln_w += ... (NULL where absent);
  * stats = scratch of 2*B*rows floats (per-row mean / rstd handed from the row kernel to the column kernel) */
 int dgs_ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* ln_w, const float* scale,

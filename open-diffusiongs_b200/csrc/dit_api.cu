@@ -72,8 +72,8 @@ struct TrainState {
   __nv_bfloat16* dyb;       // [M, w]      gated branch gradient / generic [M, w] bf16
   __nv_bfloat16* dh;        // [M, w]
   __nv_bfloat16* big0;      // [M, 4w]     du / dqkv / d_img_gs
-  __nv_bfloat16* bigT0;     // [4w, Mp]    transposed gradient operand
-  __nv_bfloat16* bigT1;     // [4w, Mp]    transposed activation operand
+  __nv_bfloat16* bigT0;     // [w, Mp]     transposed token gradient (tokenizer weight gradient only)
+  __nv_bfloat16* bigT1;     // [w, Mp]     transposed patches        (tokenizer weight gradient only)
   size_t bytes;
   TrainState(void* base, const dgs_dit_weights* w, int B, int V, int H, int W) {
     const size_t T = (size_t)V * (H / w->patch) * (W / w->patch), N = T + w->n_gaussians, D = w->width, L = w->layers;
@@ -105,8 +105,8 @@ struct TrainState {
     dyb = c.take<__nv_bfloat16>(M * D);
     dh = c.take<__nv_bfloat16>(M * D);
     big0 = c.take<__nv_bfloat16>(M * wide);
-    bigT0 = c.take<__nv_bfloat16>(wide * Mp);
-    bigT1 = c.take<__nv_bfloat16>(wide * Mp);
+    bigT0 = c.take<__nv_bfloat16>(D * Mp);
+    bigT1 = c.take<__nv_bfloat16>(D * Mp);
     bytes = c.bytes();
   }
 };
@@ -304,6 +304,12 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
     ep.out = dW; ep.ldc = n_in;
     return gemm_bf16(dyT, xT, n_out, n_in, kp, EPI_F32, ep, st);
   };
+  auto wgrad_tn = [&](const __nv_bfloat16* dy, int ld_dy, const __nv_bfloat16* x, int ld_x, float* dW, int n_out, int n_in,
+                      int rows) -> int {
+    GemmEpilogue ep;  // dW[n_out, n_in] = dY[rows, n_out]^T X[rows, n_in]: MN-major operands, nothing transposed in memory
+    ep.out = dW; ep.ldc = n_in; ep.lda = ld_dy; ep.ldb = ld_x;
+    return gemm_bf16_tn(dy, x, n_out, n_in, rows, ep, st);
+  };
   auto dgrad = [&](const __nv_bfloat16* dy, const void* wt, __nv_bfloat16* dxo, int rows, int n_in, int n_out, int epi,
                    void* aux) -> int {
     GemmEpilogue ep;  // dX[rows, n_in] = dY [rows, n_out] x (W^T [n_in, n_out])^T
@@ -324,9 +330,7 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
                                    io->scene_depth, io->range_near, io->range_far, st));
     // image_token_decoder: dh = d_img W, dW = d_img^T h
     DGS_TRY(dgrad(d_img, wT->dec_wT, ts.dh, Mt, D, Ndec, EPI_BIAS_BF16, nullptr));
-    DGS_TRY(transpose_to_bf16(d_img, 0, Ndec, 1, Mt, 0, Mt, Ndec, ts.bigT0, nullptr, st));
-    DGS_TRY(transpose_to_bf16(ts.hdec, 0, 3 * D, 1, Mt, 0, Mt, D, ts.bigT1, nullptr, st));  // hi part of [hi|lo|hi]
-    DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->dec_w, Ndec, D, Mtp));
+    DGS_TRY(wgrad_tn(d_img, Ndec, ts.hdec, 3 * D, g->dec_w, Ndec, D, Mt));  // hi part of the [hi|lo|hi] operand
     DGS_TRY(ln_modulate_bwd(x_fin, ts.dh, 0, w->dec_ln_w, md + D, mod_stride, B, N, G, T, D, 1e-5f, ts.dx, 0, dmd, dmd + D,
                             g->dec_ln_w, ts.ln_stats, st));
     if (G > 0) {  // upsampler (the free Gaussian tokens, rows 0..G of every sample)
@@ -345,13 +349,12 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
     // -- MLP branch: x_out = x_mid + gate_mlp * (fc2(gelu(fc1(h2))) )
     {
       ProfScope ps(st, PROF_DIT_BWD_ELEM);
-      DGS_TRY(gate_bwd(ts.dx, ts.fc2_out + (size_t)l * MD, m + 5 * D, mod_stride, N, M, D, ts.dyb, ts.bigT0, dm + 5 * D,
+      DGS_TRY(gate_bwd(ts.dx, ts.fc2_out + (size_t)l * MD, m + 5 * D, mod_stride, N, M, D, ts.dyb, nullptr, dm + 5 * D,
                        g->fc2_b + l * LS, st));
-      DGS_TRY(transpose_to_bf16(ts.u + (size_t)l * MU, 0, U, 1, M, 0, M, U, ts.bigT1, nullptr, st));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_WGRAD);
-      DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->fc2_w + l * LS, D, U, Mp));
+      DGS_TRY(wgrad_tn(ts.dyb, D, ts.u + (size_t)l * MU, U, g->fc2_w + l * LS, D, U, M));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_DGRAD);
@@ -360,12 +363,11 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_ELEM);
-      DGS_TRY(transpose_to_bf16(ts.big0, 0, U, 1, M, 0, M, U, ts.bigT0, g->fc1_b + l * LS, st));
-      DGS_TRY(transpose_to_bf16(ts.h2 + (size_t)l * MD, 0, D, 1, M, 0, M, D, ts.bigT1, nullptr, st));
+      DGS_TRY(colsum_bf16(ts.big0, M, U, g->fc1_b + l * LS, st));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_WGRAD);
-      DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->fc1_w + l * LS, U, D, Mp));
+      DGS_TRY(wgrad_tn(ts.big0, U, ts.h2 + (size_t)l * MD, D, g->fc1_w + l * LS, U, D, M));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_DGRAD);
@@ -376,13 +378,12 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
       DGS_TRY(ln_modulate_bwd(x_mid, ts.dh, 0, nullptr, m + 4 * D, mod_stride, B, N, 0, N, D, 1e-6f, ts.dx, 1, dm + 3 * D,
                               dm + 4 * D, nullptr, ts.ln_stats, st));
       // -- attention branch: x_mid = x_in + gate_msa * proj(attn(qkv(h1)))
-      DGS_TRY(gate_bwd(ts.dx, ts.proj_out + (size_t)l * MD, m + 2 * D, mod_stride, N, M, D, ts.dyb, ts.bigT0, dm + 2 * D,
+      DGS_TRY(gate_bwd(ts.dx, ts.proj_out + (size_t)l * MD, m + 2 * D, mod_stride, N, M, D, ts.dyb, nullptr, dm + 2 * D,
                        g->proj_b + l * LS, st));
-      DGS_TRY(transpose_to_bf16(ts.attn + (size_t)l * MD, 0, D, 1, M, 0, M, D, ts.bigT1, nullptr, st));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_WGRAD);
-      DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->proj_w + l * LS, D, D, Mp));
+      DGS_TRY(wgrad_tn(ts.dyb, D, ts.attn + (size_t)l * MD, D, g->proj_w + l * LS, D, D, M));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_DGRAD);
@@ -395,12 +396,11 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_ELEM);
-      DGS_TRY(transpose_to_bf16(ts.big0, 0, 3 * D, 1, M, 0, M, 3 * D, ts.bigT0, g->qkv_b + l * LS, st));
-      DGS_TRY(transpose_to_bf16(ts.h1 + (size_t)l * MD, 0, D, 1, M, 0, M, D, ts.bigT1, nullptr, st));
+      DGS_TRY(colsum_bf16(ts.big0, M, 3 * D, g->qkv_b + l * LS, st));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_WGRAD);
-      DGS_TRY(wgrad(ts.bigT0, ts.bigT1, g->qkv_w + l * LS, 3 * D, D, Mp));
+      DGS_TRY(wgrad_tn(ts.big0, 3 * D, ts.h1 + (size_t)l * MD, D, g->qkv_w + l * LS, 3 * D, D, M));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_DGRAD);
@@ -483,6 +483,13 @@ int dgs_gemm_bf16_ex(const void* A, const void* Wt, const float* bias, const flo
   return gemm_bf16(A, Wt, M, N, K, epi, ep, (cudaStream_t)stream);
 }
 
+int dgs_gemm_bf16_tn(const void* A, const void* W, float* out, int M, int N, int K, int lda, int ldb, int ldc, void* stream) {
+  DGS_REQUIRE(A && W && out, "NULL pointer");
+  GemmEpilogue ep;
+  ep.out = out; ep.ldc = ldc; ep.lda = lda; ep.ldb = ldb;
+  return gemm_bf16_tn(A, W, M, N, K, ep, (cudaStream_t)stream);
+}
+
 int dgs_ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const float* ln_w, const float* scale,
                         int mod_stride, int B, int rows, int width, float eps, float* dx, int accumulate, float* dshift,
                         float* dscale, float* dln_w, float* stats, void* stream) {
@@ -493,7 +500,7 @@ int dgs_ln_modulate_bwd(const float* x, const void* dh, int dh_is_f32, const flo
 
 int dgs_gate_bwd(const float* dx, const void* y, const float* gate, int gate_stride, int rows_per_sample, int M, int C,
                  void* dy, void* dyT, float* dgate, float* dbias, void* stream) {
-  DGS_REQUIRE(dx && y && gate && dy && dyT && dgate, "NULL pointer");
+  DGS_REQUIRE(dx && y && gate && dy && dgate, "NULL pointer");
   return gate_bwd(dx, (const __nv_bfloat16*)y, gate, gate_stride, rows_per_sample, M, C, (__nv_bfloat16*)dy,
                   (__nv_bfloat16*)dyT, dgate, dbias, (cudaStream_t)stream);
 }

@@ -154,9 +154,11 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__
     const float p = prod[(mc + i) * 65 + c];
     if (mc + i < split) g0 += p; else g1 += p;
   }
-  __nv_bfloat16* dst = dyT + (size_t)(c0 + c) * Mp + m0 + mc;
-  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
-  *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<const uint4*>(o + 8);
+  if (dyT) {  // transposed copy (only the K-major weight-gradient path wants it)
+    __nv_bfloat16* dst = dyT + (size_t)(c0 + c) * Mp + m0 + mc;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+    *reinterpret_cast<uint4*>(dst + 8) = *reinterpret_cast<const uint4*>(o + 8);
+  }
   red[mq * 64 + c] = s;
   red[256 + mq * 64 + c] = g0;
   red[512 + mq * 64 + c] = g1;
@@ -297,6 +299,23 @@ __global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const float* __restric
     }
     if (dlnw) atomicAdd(dlnw + c, sgx * sc1);                     // sum g (1 + scale) xhat
   }
+}
+
+// colsum[c] += sum_m in[m, c]  (bias gradient of a linear whose output gradient `in` is [M, C] bf16)
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ in, int M, int C,
+                                                     float* __restrict__ colsum) {
+  __shared__ float red[4 * 64];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: launched via launch_pdl
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63), rq = threadIdx.x >> 6;
+  const int r0 = blockIdx.y * 256, r_end = min(M, r0 + 256);
+  float a = 0.f;
+#pragma unroll 8
+  for (int r = r0 + rq; r < r_end; r += 4) a += __bfloat162float(in[(size_t)r * C + c]);
+  red[rq * 64 + (threadIdx.x & 63)] = a;
+  __syncthreads();
+  if (threadIdx.x < 64) atomicAdd(colsum + blockIdx.x * 64 + threadIdx.x, red[threadIdx.x] + red[64 + threadIdx.x] +
+                                                                               red[128 + threadIdx.x] + red[192 + threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -534,6 +553,13 @@ int gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, int gat
   const int Mp = (M + 63) / 64 * 64;
   DGS_CUDA_OK(launch_pdl(gate_bwd_kernel, dim3(Mp / 64, C / 64), dim3(256), 0, st, dx, y, gate, gate_stride, rows_per_sample, M,
                          Mp, C, dy, dyT, dgate, dbias));
+  DGS_POST_LAUNCH();
+  return DGS_OK;
+}
+
+int colsum_bf16(const __nv_bfloat16* in, int M, int C, float* colsum, cudaStream_t st) {
+  DGS_REQUIRE(C % 64 == 0, "colsum: need C %% 64 == 0");
+  DGS_CUDA_OK(launch_pdl(colsum_kernel, dim3(C / 64, ceil_div(M, 256)), dim3(256), 0, st, in, M, C, colsum));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }

@@ -27,6 +27,9 @@ struct GemmEpilogue {
 // C = epi(A[M,K] * W[N,K]^T), bf16 operands, fp32 accumulate (gemm_sm100.cu)
 int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st);
 
+// C[M,N] fp32 = A^T W for A [K,M], W [K,N] bf16 row-major (MN-major UMMA operands; ep.lda/ldb = row strides, 0 = M/N)
+int gemm_bf16_tn(const void* A, const void* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t st);
+
 // CTA-pair (cta_group::2) variant, 256 x 256 tiles, needs N % 256 == 0 (gemm2_sm100.cu); gemm_bf16 dispatches to it
 int gemm_bf16_2cta(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st);
 
@@ -90,6 +93,7 @@ struct SkinnySegs {
   int tail_rows[2] = {0, 0};
   float* tail_dW[2] = {nullptr, nullptr}; float* tail_db[2] = {nullptr, nullptr};
 };
+int colsum_bf16(const __nv_bfloat16* in, int M, int C, float* colsum, cudaStream_t st);
 int skinny_linear_bwd_segs(const float* in, const float* W, const float* dout, int ldo, int B, int N, int K, int act_in,
                            const SkinnySegs& segs, float* da, cudaStream_t st);
 // dout [B, ldo] (row stride ldo >= N): rows n of this linear are columns [0, N) of dout

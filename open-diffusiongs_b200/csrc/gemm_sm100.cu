@@ -79,7 +79,12 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * 2 * BN * 4 /*bias+gate x2*/;
 };
 
-template <int BN, int EPI>
+// MN = false:  C = A[M,K] x W[N,K]^T, both operands K-major (rows of 64 K elements = one 128-byte swizzle row).
+// MN = true :  C = A^T x W   for A [K, M], W [K, N] row-major, i.e. both operands MN-major (the weight-gradient GEMM
+//              dW = dY^T X with K = tokens: neither operand has to be transposed in memory).  A stage then holds
+//              BM/64 (resp. BN/64) swizzle atoms of [64 K rows x 64 M/N elements]; the UMMA descriptors use
+//              LBO = 8192 B (atom to atom along M/N), SBO = 1024 B (8 K rows), and step 16 K rows = 2048 B per MMA.
+template <int BN, int EPI, bool MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
                  int M, int N, int K) {
@@ -127,8 +132,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_k; kb++) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           mbar_arrive_expect_tx(full_bar + stage, Cfg::STAGE_BYTES);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, full_bar + stage, kb * BK, m0);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, full_bar + stage, kb * BK, n0);
+          if (!MN) {
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, full_bar + stage, kb * BK, m0);
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, full_bar + stage, kb * BK, n0);
+          } else {  // one [64 K x 64 MN] box per swizzle atom
+#pragma unroll
+            for (int a = 0; a < BM / 64; a++)
+              tma_load_2d(sA + stage * Cfg::A_BYTES + a * 8192, &tmA, full_bar + stage, m0 + a * 64, kb * BK);
+#pragma unroll
+            for (int a = 0; a < BN / 64; a++)
+              tma_load_2d(sB + stage * Cfg::B_BYTES + a * 8192, &tmB, full_bar + stage, n0 + a * 64, kb * BK);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -136,7 +150,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, MN, MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -148,12 +162,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_k; kb++) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES), 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES), 16, 1024);
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES), MN ? 8192 : 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES), MN ? 8192 : 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; k++) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (>>4) address field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            // K-major: advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (>>4) address field;
+            // MN-major: advance 16 K rows = 2048 bytes: +128
+            const uint64_t adv = MN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);
+            umma_bf16(d_tmem, adesc + adv, bdesc + adv, idesc, (kb | k) ? 1u : 0u);
           }
           umma_commit(empty_bar + stage);  // frees the smem slot once these MMAs have read it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -197,11 +213,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool MN = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int N, int K,
                        cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, EPI>;
+  auto kern = gemm_bf16_kernel<BN, EPI, MN>;
   static bool configured = false;
   if (!configured) {
     DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -277,6 +293,29 @@ int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const 
       return DGS_ERR_INVALID_ARGUMENT;
   }
 #undef DGS_GEMM_CASE
+}
+
+// C[M, N] (fp32) = A^T W for A [K, M], W [K, N] bf16 row-major (lda / ldb = row strides in elements, 0 = M / N):
+// the weight-gradient GEMM  dW[n_out, n_in] = dY[tokens, n_out]^T  X[tokens, n_in]  without transposed copies.
+int gemm_bf16_tn(const void* A, const void* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t st) {
+  DGS_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_tn: bad shape %dx%dx%d", M, N, K);
+  const int lda = ep.lda ? ep.lda : M, ldb = ep.ldb ? ep.ldb : N;
+  DGS_REQUIRE(N % 32 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm_tn: need N %% 32 == 0 and row strides %% 8 == 0");
+  DGS_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm_tn: operands must be 16-byte aligned");
+  const bool wide = (N % 256 == 0) && (ceil_div(M, BM) * (N / 256) >= 120);
+  CUtensorMap tmA, tmB;
+  uint32_t box[2] = {64, BK};  // [64 contiguous M/N elements (128 B) x 64 K rows]
+  {
+    uint64_t dims[2] = {(uint64_t)M, (uint64_t)K}, str[1] = {(uint64_t)lda * 2};
+    int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)K}, str[1] = {(uint64_t)ldb * 2};
+    int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  return wide ? launch_gemm<256, EPI_F32, true>(tmA, tmB, ep, M, N, K, st) : launch_gemm<128, EPI_F32, true>(tmA, tmB, ep, M, N, K, st);
 }
 
 }  // namespace dgs

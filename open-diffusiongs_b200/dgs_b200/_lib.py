@@ -111,6 +111,7 @@ def lib():
         L.dgs_attention_fwd_train.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
         L.dgs_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
         L.dgs_gemm_bf16_ex.argtypes = [vp] * 7 + [C.c_int] * 9 + [vp]
+        L.dgs_gemm_bf16_tn.argtypes = [vp, vp, vp] + [C.c_int] * 6 + [vp]
         L.dgs_ln_modulate_bwd.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp,
                                           C.c_int, vp, vp, vp, vp, vp]
         L.dgs_gate_bwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
@@ -149,5 +150,5 @@ EXPORTED = [  # every symbol include/dgs_b200.h declares (checked by tests/test_
     "dgs_dit_workspace_bytes", "dgs_dit_forward", "dgs_gemm_bf16", "dgs_attention_fwd", "dgs_ln_modulate",
     "dgs_rays_from_cameras", "dgs_q_sample", "dgs_p_sample_step",
     "dgs_dit_train_state_bytes", "dgs_dit_backward", "dgs_transpose_bf16", "dgs_adamw_step", "dgs_attention_fwd_train",
-    "dgs_attention_bwd", "dgs_gemm_bf16_ex", "dgs_ln_modulate_bwd", "dgs_gate_bwd", "dgs_cast_transpose_f32",
+    "dgs_attention_bwd", "dgs_gemm_bf16_ex", "dgs_ln_modulate_bwd", "dgs_gate_bwd", "dgs_cast_transpose_f32", "dgs_gemm_bf16_tn",
 ]

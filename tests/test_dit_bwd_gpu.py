@@ -288,3 +288,19 @@ def test_train_steps_reduce_loss_and_track_oracle():
     print("train steps: ours", losses, "oracle", ref_losses)
     assert losses[2] < losses[1] < losses[0]
     assert all(abs(a - b) <= 5e-3 * abs(b) for a, b in zip(losses, ref_losses))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1024, 1024, 4098), (896, 1024, 4096), (3072, 1024, 16392),
+                                   (1024, 576, 4096), (200, 160, 104), (4096, 1024, 4098), (1024, 4096, 8196)])
+def test_gemm_tn_mn_major_operands(M, N, K):
+    """dW = dY^T X on MN-major tcgen05 operands (no transposed copies): fp32 accumulation of exact bf16 products."""
+    from dgs_b200 import _lib
+    g = torch.Generator(DEV).manual_seed(M + N + K)
+    A = torch.randn(K, M, device=DEV, generator=g).to(torch.bfloat16)        # dY [tokens, n_out]
+    W = (torch.randn(K, N, device=DEV, generator=g) * 0.1).to(torch.bfloat16)  # X  [tokens, n_in]
+    out = torch.full((M, N), float("nan"), device=DEV)
+    _lib.check(_lib.lib().dgs_gemm_bf16_tn(ptr(A), ptr(W), ptr(out), M, N, K, 0, 0, N, stream()))
+    ref = A.float().t() @ W.float()
+    e = rel(out, ref)
+    print(f"gemm_tn {M}x{N}x{K}: rel={e:.2e}")
+    assert e < 4e-5  # fp32 accumulation-order error grows ~ sqrt(K) (K up to 16392 tokens)
