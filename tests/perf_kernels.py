@@ -41,6 +41,15 @@ def main():
     out = torch.empty(B, N, D, dtype=torch.bfloat16, device=DEV)
     ms = timeit(lambda: _lib.check(L.dgs_attention_fwd(qkv.data_ptr(), out.data_ptr(), B, N, H, st())))
     print(json.dumps(dict(kernel="attention", ms=ms, tflops=4 * N * N * D * B / ms / 1e9, **tag)))
+    if "--gemm-sweep" in sys.argv:
+        for (m, n, k) in [(8192, 4096, 4096), (8192, 4096, 1024), (4096, 4096, 8192), (16384, 1024, 1024)]:
+            A = torch.randn(m, k, device=DEV).to(torch.bfloat16)
+            W = (torch.randn(n, k, device=DEV) * 0.03).to(torch.bfloat16)
+            o = torch.zeros(m, n, dtype=torch.bfloat16, device=DEV)
+            ms = timeit(lambda: _lib.check(L.dgs_gemm_bf16(A.data_ptr(), W.data_ptr(), None, None, o.data_ptr(), m, n, k, 0, n, 0,
+                                                           1, st())))
+            print(json.dumps(dict(kernel=f"gemm_{m}x{n}x{k}", ms=ms, tflops=2 * m * n * k / ms / 1e9, **tag)))
+        return
     if "--attn-bwd" in sys.argv or "--all" in sys.argv:
         Bb = int(os.environ.get("DGS_PERF_B", "1"))
         qkvb = (torch.randn(Bb, N, 3, H, 64, device=DEV) * 1.5).to(torch.bfloat16)
