@@ -7,11 +7,16 @@
 // EACH CTA's TMEM.  Operand traffic drops to 32 KB per CTA per k-block (64 MAC/B).
 //
 // Protocol (leader = cluster rank 0):
-//   full[s]    lives in the LEADER: count 2 = leader producer's arrive.expect_tx(2 x 32 KB) + peer producer's remote
-//              arrive; both CTAs' TMA loads complete_tx on it (cp.async.bulk.tensor ... cta_group::2, leader address)
+//   full[s]    lives in the LEADER: count 1 = the leader producer's arrive.expect_tx(2 x 32 KB); both CTAs' TMA loads
+//              complete_tx on it (cp.async.bulk.tensor ... cta_group::2, leader address).  The peer producer does NOT
+//              arrive: its loads for phase n+1 can only be issued after its empty[s] completed phase n, i.e. after the
+//              leader's full[s] phase n was consumed, so a transiently negative tx-count is the worst that can happen.
+//              (A remote mbarrier.arrive.release.cluster per k-block in the peer's producer loop cost ~1400 clk per
+//              iteration and was THE reason this kernel ran at half the single-CTA rate: profiles/r1_gemm_probe_v1.txt.)
 //   empty[s]   one per CTA, released by the leader's tcgen05.commit ... multicast::cluster (mask 0b11)
 //   tfull[a]   one per CTA, same multicast commit when an accumulator is complete
-//   tempty[a]  lives in the leader: count 256 = both CTAs' 128 epilogue threads (the peer's arrive remotely)
+//   tempty[a]  lives in the leader: count 2 = one elected epilogue thread per CTA (after a 128-thread named barrier);
+//              the peer's arrives remotely, once per tile
 // Same fused epilogues as gemm_sm100.cu (each CTA drains its own 128 rows).
 #include "dgs_internal.h"
 #include "dit_kernels.h"
@@ -105,8 +110,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 2); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 256); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 2); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -118,6 +123,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   cluster_sync();  // both CTAs' barriers are initialised before any remote arrive / multicast commit / 2SM TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // PDL: see sm100_ptx.cuh
+  griddep_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (one per CTA) =====================
@@ -131,7 +138,6 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(empty_bar + stage, phase ^ 1);
           const uint32_t leader_full = mapa(smem_u32(full_bar + stage), 0);
           if (leader) mbar_arrive_expect_tx(full_bar + stage, 2 * STAGE_BYTES);
-          else mbar_arrive_remote(leader_full);
           tma_load_2d_2sm(sA + stage * A_BYTES, &tmA, leader_full, kb * BK, m0);
           tma_load_2d_2sm(sB + stage * B_BYTES, &tmB, leader_full, kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -184,8 +190,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       epilogue_drain_row<EPI, BN>(ep, s_vec, uniform_gate, t_row, row, n0, M, N);
       tc_fence_before();
-      if (leader) mbar_arrive(tempty_bar + acc);
-      else mbar_arrive_remote(leader_tempty0 + (uint32_t)(acc * 8));
+      epi_bar_sync<128>();
+      if (et == 0) {
+        if (leader) mbar_arrive(tempty_bar + acc);
+        else mbar_arrive_remote(leader_tempty0 + (uint32_t)(acc * 8));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -212,7 +221,8 @@ static int launch_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int tiles = ceil_div(M, 2 * g2::BM_CTA) * ceil_div(N, g2::BN);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
-  kern<<<2 * clusters, g2::THREADS, g2::SMEM_BYTES, st>>>(tmA, tmB, ep, M, N, K);
+  // cluster dims come from the kernel's __cluster_dims__ attribute; PDL as for the single-CTA kernel
+  DGS_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(g2::THREADS), g2::SMEM_BYTES, st, tmA, tmB, ep, M, N, K));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }

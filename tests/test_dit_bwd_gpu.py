@@ -90,7 +90,8 @@ def test_gemm_training_epilogues(M, N, K):
     assert rel(o32, A[:, :K - 8].float() @ W[:, :K - 8].float().t()) < 2e-5
 
 
-@pytest.mark.parametrize("B,N,H", [(1, 4098, 16), (2, 1026, 16), (1, 128, 2), (2, 200, 2), (1, 77, 4), (1, 64, 2), (1, 130, 1)])
+@pytest.mark.parametrize("B,N,H", [(1, 4098, 16), (2, 1026, 16), (1, 128, 2), (2, 200, 2), (1, 77, 4), (1, 64, 2), (1, 130, 1),
+                                   (1, 16386, 1)])
 def test_attention_backward_vs_autograd(B, N, H):
     from dgs_b200 import _lib
     L = _lib.lib()

@@ -90,7 +90,8 @@ def test_gemm_gate_residual_epilogue():
     assert rel(out, ref) < 2e-5
 
 
-@pytest.mark.parametrize("B,N,H", [(1, 4098, 16), (2, 1026, 16), (1, 128, 2), (1, 130, 1), (2, 77, 4), (1, 1, 1)])
+# (1, 16386, 2): the 512x512 configurations (obj-512 / scene-512 / the pipline_obj.py demo), two heads bound the fp32 reference
+@pytest.mark.parametrize("B,N,H", [(1, 4098, 16), (2, 1026, 16), (1, 128, 2), (1, 130, 1), (2, 77, 4), (1, 1, 1), (1, 16386, 2)])
 def test_attention_vs_fp32_softmax(B, N, H):
     from dgs_b200 import _lib
     g = torch.Generator(DEV).manual_seed(N)
