@@ -32,6 +32,7 @@ int gemm_bf16_tn(const void* A, const void* W, int M, int N, int K, const GemmEp
 
 // CTA-pair (cta_group::2) variant, 256 x 256 tiles, needs N % 256 == 0 (gemm2_sm100.cu); gemm_bf16 dispatches to it
 int gemm_bf16_2cta(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st);
+int gemm_bf16_tn_2cta(const void* A, const void* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t st);
 
 // single-CTA 256 x 256 tile variant (gemm3_sm100.cu), needs N % 256 == 0
 int gemm_bf16_m256(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st);

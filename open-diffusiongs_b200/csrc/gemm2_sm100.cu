@@ -18,6 +18,8 @@
 //   tempty[a]  lives in the leader: count 2 = one elected epilogue thread per CTA (after a 128-thread named barrier);
 //              the peer's arrives remotely, once per tile
 // Same fused epilogues as gemm_sm100.cu (each CTA drains its own 128 rows).
+#include <cstdlib>
+
 #include "dgs_internal.h"
 #include "dit_kernels.h"
 #include "gemm_epilogue.cuh"
@@ -29,10 +31,17 @@ using namespace ptx;
 
 namespace g2 {
 
-constexpr int BM_CTA = 128, BN = 256, BN_CTA = 128, BK = 64, UMMA_K = 16, STAGES = 6, THREADS = 192;
+constexpr int BM_CTA = 128, BN = 256, BN_CTA = 128, BK = 64, UMMA_K = 16, THREADS = 192;
 constexpr int A_BYTES = BM_CTA * BK * 2, B_BYTES = BN_CTA * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int TMEM_COLS = 2 * BN;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2 * 2 * BN * 4;
+// TMAEPI (gemm_epilogue.cuh: outputs leave through shared-memory staging + TMA store / reduce-add): 5 operand stages +
+// 32 KB of staging; else 6 stages.  (The probe measured no difference between 4 and 7 stages on the DiT shapes.)
+template <bool TMAEPI>
+struct Cfg2 {
+  static constexpr int STAGES = TMAEPI ? 5 : 6;
+  static constexpr int STG_BYTES = TMAEPI ? EPI_TMA_STAGING_BYTES : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256 + 2 * 2 * BN * 4;
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -85,16 +94,21 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 }
 
 
-template <int EPI>
+// MN = false: C = A[M,K] x W[N,K]^T (K-major operands).  MN = true: C = A^T x W for A [K,M], W [K,N] row-major (both
+// operands MN-major: the weight-gradient GEMM, see gemm_sm100.cu); a CTA's stage then holds 2 + 2 swizzle atoms of
+// [64 K rows x 64 M/N elements].
+template <int EPI, bool MN, bool TMAEPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
-                      int M, int N, int K) {
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmO, GemmEpilogue ep, int M, int N, int K) {
+  constexpr int STAGES = Cfg2<TMAEPI>::STAGES, STG_BYTES = Cfg2<TMAEPI>::STG_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;  // TMAEPI: 4 warps x 2 x 4 KB, 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -110,6 +124,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (TMAEPI) prefetch_tmap(&tmO);
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; s++) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 2); }
     fence_barrier_init();
@@ -138,8 +153,17 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(empty_bar + stage, phase ^ 1);
           const uint32_t leader_full = mapa(smem_u32(full_bar + stage), 0);
           if (leader) mbar_arrive_expect_tx(full_bar + stage, 2 * STAGE_BYTES);
-          tma_load_2d_2sm(sA + stage * A_BYTES, &tmA, leader_full, kb * BK, m0);
-          tma_load_2d_2sm(sB + stage * B_BYTES, &tmB, leader_full, kb * BK, n0);
+          if (!MN) {
+            tma_load_2d_2sm(sA + stage * A_BYTES, &tmA, leader_full, kb * BK, m0);
+            tma_load_2d_2sm(sB + stage * B_BYTES, &tmB, leader_full, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BM_CTA / 64; a++)
+              tma_load_2d_2sm(sA + stage * A_BYTES + a * 8192, &tmA, leader_full, m0 + a * 64, kb * BK);
+#pragma unroll
+            for (int a = 0; a < BN_CTA / 64; a++)
+              tma_load_2d_2sm(sB + stage * B_BYTES + a * 8192, &tmB, leader_full, n0 + a * 64, kb * BK);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -147,7 +171,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer: one thread of the LEADER CTA =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM_CTA, BN, false, false);
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM_CTA, BN, MN, MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -159,11 +183,13 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int kb = 0; kb < num_k; kb++) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * A_BYTES), 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * B_BYTES), 16, 1024);
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * A_BYTES), MN ? 8192 : 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * B_BYTES), MN ? 8192 : 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; k++)
-            umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; k++) {
+            const uint64_t adv = MN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);  // 16 K rows = 2048 B  |  16 bf16 = 32 B
+            umma_bf16_2sm(d_tmem, adesc + adv, bdesc + adv, idesc, (kb | k) ? 1u : 0u);
+          }
           umma_commit_2sm(empty_bar + stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -175,7 +201,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // ===================== epilogue warps 2..5: each CTA drains its own 128 rows (gemm_epilogue.cuh) ==========
     const int quad = warp & 3;
     const int et = (warp - 2) * 32 + lane;
-    float* s_vec_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
+    float* s_vec_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + STG_BYTES + 256);
     const uint32_t leader_tempty0 = mapa(smem_u32(tempty_bar), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -188,7 +214,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_drain_row<EPI, BN>(ep, s_vec, uniform_gate, t_row, row, n0, M, N);
+      if constexpr (TMAEPI)
+        epilogue_drain_row_tma<EPI, BN>(ep, s_vec, uniform_gate, t_row, row, m0 + quad * 32, n0, M, N,
+                                        stg_base + (warp - 2) * 8192, lane, &tmO);
+      else
+        epilogue_drain_row<EPI, BN>(ep, s_vec, uniform_gate, t_row, row, n0, M, N);
       tc_fence_before();
       epi_bar_sync<128>();
       if (et == 0) {
@@ -197,6 +227,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (TMAEPI && lane == 0) epi_bulk_wait_all();  // the staging buffers must outlive the bulk stores reading them
   }
   tc_fence_before();
   __syncthreads();
@@ -209,20 +240,21 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 }  // namespace g2
 
-template <int EPI>
-static int launch_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int N, int K,
-                       int num_sms, cudaStream_t st) {
-  auto kern = g2::gemm_bf16_2cta_kernel<EPI>;
+template <int EPI, bool MN = false, bool TMAEPI = false>
+static int launch_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmEpilogue& ep, int M,
+                       int N, int K, int num_sms, cudaStream_t st) {
+  auto kern = g2::gemm_bf16_2cta_kernel<EPI, MN, TMAEPI>;
+  constexpr int SMEM = g2::Cfg2<TMAEPI>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
-    DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g2::SMEM_BYTES));
+    DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
   const int tiles = ceil_div(M, 2 * g2::BM_CTA) * ceil_div(N, g2::BN);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
   // cluster dims come from the kernel's __cluster_dims__ attribute; PDL as for the single-CTA kernel
-  DGS_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(g2::THREADS), g2::SMEM_BYTES, st, tmA, tmB, ep, M, N, K));
+  DGS_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(g2::THREADS), SMEM, st, tmA, tmB, tmO, ep, M, N, K));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }
@@ -237,24 +269,71 @@ int gemm_bf16_2cta(const void* A, const void* W, int M, int N, int K, int epi, c
   }
   CUtensorMap tmA, tmB;
   {
-    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)K * 2};
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)(ep.lda ? ep.lda : K) * 2};
     uint32_t box[2] = {g2::BK, g2::BM_CTA};
     int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K * 2};
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)(ep.ldb ? ep.ldb : K) * 2};
     uint32_t box[2] = {g2::BK, g2::BN_CTA};
     int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
     if (rc) return rc;
   }
+  // TMA epilogue (gemm_epilogue.cuh): the inference-mode forms of the three block epilogues -- no aux store, residual
+  // updated in place -- with a 16-byte aligned output whose row stride is a multiple of 16 bytes.  DGS_GEMM_TMA_EPI=0 disables.
+  static int tma_epi = -1;
+  if (tma_epi < 0) {
+    const char* e = getenv("DGS_GEMM_TMA_EPI");
+    tma_epi = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool out_f32 = epi == EPI_GATE_RESID_F32;
+  const bool can_tma = tma_epi && !ep.aux && !ep.resid && (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || out_f32) &&
+                       ((uintptr_t)ep.out % 16) == 0 && ((size_t)ep.ldc * (out_f32 ? 4 : 2)) % 16 == 0;
+  CUtensorMap tmO = tmA;  // placeholder when the TMA epilogue is not used (never dereferenced)
+  if (can_tma) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)ep.ldc * (out_f32 ? 4 : 2)};
+    uint32_t box[2] = {out_f32 ? 32u : 64u, 32u};  // 128-byte rows x 32 rows
+    int rc = out_f32 ? make_tmap_f32(&tmO, ep.out, 2, dims, str, box) : make_tmap_bf16(&tmO, ep.out, 2, dims, str, box);
+    if (rc) return rc;
+    switch (epi) {
+      case EPI_BIAS_BF16: return launch_2cta<EPI_BIAS_BF16, false, true>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
+      case EPI_BIAS_GELU_BF16: return launch_2cta<EPI_BIAS_GELU_BF16, false, true>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
+      default: return launch_2cta<EPI_GATE_RESID_F32, false, true>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
+    }
+  }
   switch (epi) {
-    case EPI_BIAS_BF16: return launch_2cta<EPI_BIAS_BF16>(tmA, tmB, ep, M, N, K, num_sms, st);
-    case EPI_BIAS_GELU_BF16: return launch_2cta<EPI_BIAS_GELU_BF16>(tmA, tmB, ep, M, N, K, num_sms, st);
-    case EPI_GATE_RESID_F32: return launch_2cta<EPI_GATE_RESID_F32>(tmA, tmB, ep, M, N, K, num_sms, st);
-    case EPI_F32: return launch_2cta<EPI_F32>(tmA, tmB, ep, M, N, K, num_sms, st);
+    case EPI_BIAS_BF16: return launch_2cta<EPI_BIAS_BF16>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
+    case EPI_BIAS_GELU_BF16: return launch_2cta<EPI_BIAS_GELU_BF16>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
+    case EPI_GATE_RESID_F32: return launch_2cta<EPI_GATE_RESID_F32>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
+    case EPI_F32: return launch_2cta<EPI_F32>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
+    case EPI_DGELU_BF16: return launch_2cta<EPI_DGELU_BF16>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
     default: set_error("gemm: unknown epilogue %d", epi); return DGS_ERR_INVALID_ARGUMENT;
   }
+}
+
+// CTA-pair variant of gemm_bf16_tn (C[M,N] fp32 = A^T W, MN-major operands); requires N % 256 == 0
+int gemm_bf16_tn_2cta(const void* A, const void* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t st) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    DGS_CUDA_OK(cudaGetDevice(&dev));
+    DGS_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int lda = ep.lda ? ep.lda : M, ldb = ep.ldb ? ep.ldb : N;
+  CUtensorMap tmA, tmB;
+  uint32_t box[2] = {64, g2::BK};  // [64 contiguous M/N elements (128 B) x 64 K rows]
+  {
+    uint64_t dims[2] = {(uint64_t)M, (uint64_t)K}, str[1] = {(uint64_t)lda * 2};
+    int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)K}, str[1] = {(uint64_t)ldb * 2};
+    int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  return launch_2cta<EPI_F32, true>(tmA, tmB, tmA, ep, M, N, K, num_sms, st);
 }
 
 }  // namespace dgs

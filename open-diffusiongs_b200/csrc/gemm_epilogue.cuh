@@ -146,4 +146,112 @@ __device__ __forceinline__ void epilogue_drain_row(const GemmEpilogue& ep, const
   }
 }
 
+// ---- TMA epilogue (CTA-pair kernel, inference-mode epilogues) -------------------------------------------------------
+// The row-per-thread global stores above touch 32 different 128-byte lines per warp instruction (one per row), so the
+// drain of a 128 x 256 tile is bound by LSU wavefronts (~4-7k clk, profiles/r1_gemm_probe_v2.txt) -- fully exposed on
+// the last tile of every CTA and on the single-wave GEMMs (proj, fc2).  Here each epilogue warp stages its 32-row slab
+// in shared memory in the 128-byte-swizzled layout of a tensor map (thread = row, conflict-free 16-byte stores) and ONE
+// lane hands a [32 rows x 128 bytes] box to the TMA:
+//   bf16 outputs:  cp.async.bulk.tensor store, 64 columns per box;
+//   gate+residual: x += gate * (acc + b) as cp.reduce.async.bulk.tensor ... add.f32, 32 columns per box -- the fp32
+//                  residual stream is updated in L2 by the TMA and never read by the SM.
+// Rows >= M are clipped by the tensor map.  Two staging buffers per warp; a buffer is reused once the bulk group that
+// read it has completed its shared-memory reads (cp.async.bulk.wait_group.read).
+__device__ __forceinline__ void epi_tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void epi_tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void epi_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void epi_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void epi_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+constexpr int EPI_TMA_STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 bytes)
+
+// `stg` = this warp's two staging buffers (8 KB, 1024-byte aligned); slab_row0 = first output row of the warp's slab.
+template <int EPI, int BN>
+__device__ __forceinline__ void epilogue_drain_row_tma(const GemmEpilogue& ep, const float* s_vec, bool uniform_gate,
+                                                       uint32_t t_row, int row, int slab_row0, int n0, int M, int N,
+                                                       uint8_t* stg, int lane, const CUtensorMap* tm_out) {
+  using namespace ptx;
+  static_assert(EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_GATE_RESID_F32, "TMA epilogue: unsupported");
+  const int crow = row < M ? row : M - 1;  // rows past the end compute on a valid row's gate; their box rows are clipped
+  const float* gate_row = nullptr;
+  if (EPI == EPI_GATE_RESID_F32 && !uniform_gate) gate_row = ep.gate + (size_t)(crow / ep.rows_per_sample) * ep.gate_stride;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  if (EPI == EPI_GATE_RESID_F32) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; c++) {
+      const int n = n0 + c * 32;
+      if (n >= N) break;
+      uint32_t r[32];
+      tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
+      uint8_t* buf = stg + (c & 1) * 4096;
+      if (lane == 0) epi_bulk_wait_read1();
+      __syncwarp();
+      tmem_ld_wait();
+      const float* sb = s_vec + c * 32;
+      const float* sg = s_vec + BN + c * 32;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float4 g4;
+        if (uniform_gate) g4 = make_float4(sg[4 * j], sg[4 * j + 1], sg[4 * j + 2], sg[4 * j + 3]);
+        else g4 = __ldg(reinterpret_cast<const float4*>(gate_row + n + 4 * j));
+        float4 v4;
+        v4.x = g4.x * (__uint_as_float(r[4 * j]) + sb[4 * j]);
+        v4.y = g4.y * (__uint_as_float(r[4 * j + 1]) + sb[4 * j + 1]);
+        v4.z = g4.z * (__uint_as_float(r[4 * j + 2]) + sb[4 * j + 2]);
+        v4.w = g4.w * (__uint_as_float(r[4 * j + 3]) + sb[4 * j + 3]);
+        *reinterpret_cast<float4*>(buf + lane * 128 + (((uint32_t)j ^ sw) * 16)) = v4;  // SWIZZLE_128B
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        epi_tma_reduce_add_2d(tm_out, buf, n, slab_row0);
+        epi_bulk_commit();
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < BN / 64; c++) {
+      const int n = n0 + c * 64;
+      if (n >= N) break;
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(t_row + (uint32_t)(c * 64), r0);
+      tmem_ld_32x32(t_row + (uint32_t)(c * 64 + 32), r1);
+      uint8_t* buf = stg + (c & 1) * 4096;
+      if (lane == 0) epi_bulk_wait_read1();
+      __syncwarp();
+      tmem_ld_wait();
+      const float* sb = s_vec + c * 64;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t* r = (j < 4) ? (r0 + 8 * j) : (r1 + 8 * (j - 4));
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          v[i] = __uint_as_float(r[i]) + sb[8 * j + i];
+          if (EPI == EPI_BIAS_GELU_BF16) v[i] = epi_gelu_tanh(v[i]);
+        }
+        uint4 pk;
+        pk.x = epi_pack_bf16(v[0], v[1]); pk.y = epi_pack_bf16(v[2], v[3]);
+        pk.z = epi_pack_bf16(v[4], v[5]); pk.w = epi_pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(buf + lane * 128 + (((uint32_t)j ^ sw) * 16)) = pk;  // SWIZZLE_128B
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        epi_tma_store_2d(tm_out, buf, n, slab_row0);
+        epi_bulk_commit();
+      }
+    }
+  }
+}
+
 }  // namespace dgs

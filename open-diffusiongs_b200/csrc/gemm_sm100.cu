@@ -48,15 +48,25 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
+}
+static int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)"); return DGS_ERR_CUDA; }
   cuuint64_t gdim[5], gstr[5];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DGS_ERR_CUDA; }
@@ -250,7 +260,7 @@ int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const 
     const char* e = getenv("DGS_GEMM_2CTA");
     use_2cta = (e && e[0] == '1') ? 1 : 0;
   }
-  if (use_2cta && epi != EPI_DGELU_BF16 && !ep.lda && !ep.ldb && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_2cta(A, W, M, N, K, epi, ep, st);
+  if (use_2cta && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_2cta(A, W, M, N, K, epi, ep, st);
   // 256 x 256 single-CTA tiles (gemm3_sm100.cu, 1.5x less operand traffic per FLOP): DGS_GEMM_M256=1
   static int use_m256 = -1;
   if (use_m256 < 0) {
@@ -302,6 +312,10 @@ int gemm_bf16_tn(const void* A, const void* W, int M, int N, int K, const GemmEp
   const int lda = ep.lda ? ep.lda : M, ldb = ep.ldb ? ep.ldb : N;
   DGS_REQUIRE(N % 32 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm_tn: need N %% 32 == 0 and row strides %% 8 == 0");
   DGS_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm_tn: operands must be 16-byte aligned");
+  {
+    const char* e = getenv("DGS_GEMM_2CTA");
+    if (e && e[0] == '1' && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_tn_2cta(A, W, M, N, K, ep, st);
+  }
   const bool wide = (N % 256 == 0) && (ceil_div(M, BM) * (N / 256) >= 120);
   CUtensorMap tmA, tmB;
   uint32_t box[2] = {64, BK};  // [64 contiguous M/N elements (128 B) x 64 K rows]

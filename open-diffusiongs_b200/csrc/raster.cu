@@ -67,7 +67,7 @@ struct GeomState {
   uint32_t* open_counts;   // phase B: open tiles touched per depth rank (0 for the near ranks) ...
   uint32_t* open_offsets;  // ... and their inclusive scan
   uint32_t* view_meta;     // [NV][4] two-phase binning: {startA, startB, baseA, baseB} instance offsets per view
-  uint32_t* totals;        // [4] {R, R_near, tiles not finished after phase A, -}
+  uint32_t* totals;        // [6] {R, R_near, tiles not finished after phase A, -, exact 64-bit instance count (lo, hi)}
   Camera* cams;
   void* scan_temp;
   size_t scan_bytes;
@@ -88,7 +88,7 @@ struct GeomState {
     s.open_counts = c.take<uint32_t>(N);
     s.open_offsets = c.take<uint32_t>(N);
     s.view_meta = c.take<uint32_t>((size_t)NV * 4);
-    s.totals = c.take<uint32_t>(4);
+    s.totals = c.take<uint32_t>(6);
     s.cams = c.take<Camera>(NV);
     size_t scan_b = 0, sort_b = 0;
     cub::DeviceScan::InclusiveSum(nullptr, scan_b, s.tiles_sorted, s.offsets, (int)N);
@@ -481,11 +481,20 @@ __global__ void __launch_bounds__(256) project_kernel(Problem pb, GeomState gs, 
 }
 
 // tiles touched in depth-rank order (input of the instance-offset scan)
+// Also accumulates the EXACT instance count in 64 bits (totals[4..5]): the 32-bit scan below wraps silently beyond
+// 2^32 instances, and the host must be able to tell "too many for one batch" from a small wrapped number.
 __global__ void gather_tiles_kernel(size_t N, int P, GeomState gs) {
   const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= N) return;
-  const size_t view = k / P;
-  gs.tiles_sorted[k] = gs.tiles[view * P + gs.perm[k]];
+  uint32_t t = 0;
+  if (k < N) {
+    const size_t view = k / P;
+    t = gs.tiles[view * P + gs.perm[k]];
+    gs.tiles_sorted[k] = t;
+  }
+  unsigned long long sum = t;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0 && sum) atomicAdd(reinterpret_cast<unsigned long long*>(gs.totals + 4), sum);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1228,6 +1237,7 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
     const int depth_end_bit = 32 + bits_for((uint32_t)pb.NV);
     DGS_CUDA_OK(cub::DeviceRadixSort::SortPairs(gs.scan_temp, gs.scan_bytes, gs.dkey_in, gs.dkey, gs.perm_in, gs.perm,
                                                 (int)N, 0, depth_end_bit, st));
+    DGS_CUDA_OK(cudaMemsetAsync(gs.totals, 0, 6 * sizeof(uint32_t), st));
     gather_tiles_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, pb.P, gs);
     DGS_LAUNCH_OK(st, debug);
     DGS_CUDA_OK(cub::DeviceScan::InclusiveSum(gs.scan_temp, gs.scan_bytes, gs.tiles_sorted, gs.offsets, (int)N, st));
@@ -1235,17 +1245,22 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
   // two-phase binning candidates need the near/far split of the instance counts; it rides on the same single sync
   const int Pn = (pb.near_log2 > 0) ? (pb.P >> pb.near_log2) : 0;
   const bool may_split = Pn >= 1024;
-  uint32_t tot[2] = {0, 0};
+  uint32_t tot[6] = {0, 0, 0, 0, 0, 0};
   if (may_split) {
     chunk_meta_kernel<<<1, 32, 0, st>>>(pb.NV, pb.P, Pn, gs.offsets, gs.view_meta, gs.totals);
     DGS_LAUNCH_OK(st, debug);
-    DGS_CUDA_OK(cudaMemcpyAsync(tot, gs.totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    DGS_CUDA_OK(cudaMemcpyAsync(tot, gs.totals, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   } else {
     DGS_CUDA_OK(cudaMemcpyAsync(tot, gs.offsets + N - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    DGS_CUDA_OK(cudaMemcpyAsync(tot + 4, gs.totals + 4, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   }
   DGS_CUDA_OK(cudaStreamSynchronize(st));  // the one host sync per batch (two-phase: a second, after phase A)
+  const long long R64 = (long long)(((unsigned long long)tot[5] << 32) | tot[4]);  // exact, never wrapped
+  if (R64 >= (long long)INT32_MAX) {
+    set_error("instance count %lld exceeds 2^31-1 (render the views in smaller batches)", R64);
+    return DGS_ERR_OVERFLOW;
+  }
   const long long R = (long long)tot[0];
-  if (R >= (long long)INT32_MAX) { set_error("instance count %lld exceeds 2^31-1", R); return DGS_ERR_OVERFLOW; }
   *R_out = R;
   // phase A must be a real saving: at most half of the instances
   const bool split = may_split && R >= (1ll << 21) && 2ll * tot[1] <= R && tot[1] > 0;

@@ -253,5 +253,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+// same, fp32 elements (TMA store / reduce-add of the fp32 residual stream)
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
 
 }  // namespace dgs

@@ -74,8 +74,11 @@ class GaussianDiffusionB200:
             self._dev_tables[key] = {k: torch.from_numpy(v).to(dev).float().contiguous() for k, v in self.tables_f64.items()}
         return self._dev_tables[key]
 
-    def map_timesteps(self, ts):  # _WrappedModel.__call__, respace.py:121-137
-        return torch.as_tensor(self.timestep_map, device=ts.device, dtype=ts.dtype)[ts]
+    def map_timesteps(self, ts):  # _WrappedModel.__call__, respace.py:121-137 (the map is uploaded once per device)
+        key = ("map", str(ts.device), ts.dtype)
+        if key not in self._dev_tables:
+            self._dev_tables[key] = torch.as_tensor(self.timestep_map, device=ts.device, dtype=ts.dtype)
+        return self._dev_tables[key][ts]
 
     def q_sample(self, x_start, t, noise=None):
         if not x_start.is_cuda:
@@ -105,6 +108,78 @@ class GaussianDiffusionB200:
                                                tab["model_log_variance"].data_ptr(), tt.data_ptr(), x.shape[0],
                                                x[0].numel(), out.data_ptr(), _stream(x.device)))
         return out
+
+
+    # ---- sampler loop: p_mean_variance / p_sample / p_sample_loop[_progressive] with the reference's
+    #      signatures and dict keys (gaussian_diffusion.py:316-459, 479-518, 520-603; respace.py:93-96, 121-137) ----
+    def p_mean_variance(self, model, input_batch, t, clip_denoised=True, model_kwargs=None):
+        """image = cat(cond view, x_t) -> model(input_batch, timestep_map[t]) = (renders, gaussians); pred_xstart =
+        renders[:, 1:] (x0-prediction); posterior mean through the fused step kernel.  `variance` / `log_variance` are the
+        FIXED_LARGE table entries broadcast lazily (0-stride views), as nothing on the live path reads them densely."""
+        x = input_batch["image_noisy"]
+        B = x.shape[0]
+        assert t.shape == (B,)
+        input_batch["image"] = torch.cat([input_batch["image"][:, 0:1], x.to(input_batch["image"].dtype)], dim=1)
+        render_imgs, pred_gaussians = model(input_batch, self.map_timesteps(t))
+        pred_xstart = render_imgs[:, 1:]
+        if clip_denoised:
+            pred_xstart = pred_xstart.clamp(-1, 1)
+        mean = self._posterior_mean(pred_xstart, x, t)
+        logv = self._tables(x.device)["model_log_variance"][t].view(B, *([1] * (x.dim() - 1))).expand_as(x)
+        return dict(mean=mean, variance=logv.exp(), log_variance=logv, pred_xstart=pred_xstart,
+                    denoiser_output_dict=dict(render_images=render_imgs, pred_gaussians=pred_gaussians))
+
+    def _posterior_mean(self, pred_xstart, x_t, t):
+        # q_posterior_mean_variance (gaussian_diffusion.py:291-312) = the step kernel with zero noise
+        return self.p_sample_step(pred_xstart, x_t, t, noise=torch.zeros_like(x_t, dtype=torch.float32))
+
+    def p_sample(self, model, input_batch, t, clip_denoised=True, model_kwargs=None, noise=None):
+        """One ancestral step.  x_{t-1} = mean + (t != 0) sigma_t noise in ONE kernel launch (the reference: ~10 elementwise
+        kernels + an H2D copy of the schedule table per `_extract_into_tensor` + a host sync on `t[0] > 0`)."""
+        x = input_batch["image_noisy"]
+        B = x.shape[0]
+        input_batch["image"] = torch.cat([input_batch["image"][:, 0:1], x.to(input_batch["image"].dtype)], dim=1)
+        render_imgs, pred_gaussians = model(input_batch, self.map_timesteps(t))
+        pred_xstart = render_imgs[:, 1:]
+        if clip_denoised:
+            pred_xstart = pred_xstart.clamp(-1, 1)
+        sample = self.p_sample_step(pred_xstart, x, t, noise=noise).to(x.dtype)
+        input_batch["image_noisy"] = sample
+        return dict(sample=sample, pred_xstart=pred_xstart, input_batch=input_batch,
+                    denoiser_output_dict=dict(render_images=render_imgs, pred_gaussians=pred_gaussians))
+
+    def p_sample_loop_progressive(self, model, shape, input_batch=None, clip_denoised=True, model_kwargs=None, device=None,
+                                  progress=False, noise_fn=None):
+        """Generator over the outputs of p_sample for i = num_timesteps-1 .. 0.  The step indices live on the device
+        (one arange upload for the whole loop), x_t never leaves HBM, and there is no host sync inside the loop besides
+        the rasterizer's own instance-count read-back.  `noise_fn(i, like)` overrides torch.randn_like (tests)."""
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        steps = torch.arange(self.num_timesteps, device=device, dtype=torch.int64)
+        indices = range(self.num_timesteps - 1, -1, -1)
+        if progress:
+            try:
+                from tqdm.auto import tqdm
+                indices = tqdm(indices)
+            except ImportError:
+                pass
+        for i in indices:
+            t = steps[i:i + 1].expand(shape[0])
+            with torch.no_grad():
+                noise = None if noise_fn is None else noise_fn(i, input_batch["image_noisy"])
+                out = self.p_sample(model, input_batch, t, clip_denoised=clip_denoised, model_kwargs=model_kwargs, noise=noise)
+                yield out
+                input_batch = out["input_batch"]
+
+    def p_sample_loop(self, model, shape, input_batch=None, clip_denoised=True, model_kwargs=None, device=None,
+                      progress=True, noise_fn=None):
+        final = None
+        for sample in self.p_sample_loop_progressive(model, shape, input_batch=input_batch, clip_denoised=clip_denoised,
+                                                     model_kwargs=model_kwargs, device=device, progress=progress,
+                                                     noise_fn=noise_fn):
+            final = sample
+        return final
 
 
 def create_diffusion(timestep_respacing=None, noise_schedule="squaredcos_cap_v2", predict_xstart=True,

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ALLOC_FN, RasterArgs, RenderBatchArgs, check
+from ._lib import ALLOC_FN, DgsError, RasterArgs, RenderBatchArgs, check
 
 
 LAST_NUM_RENDERED = None  # instance count R of the most recent batched forward (bench/roofline bookkeeping)
@@ -168,8 +168,33 @@ def _batch_args(xyz, features, scaling, rotation, opacity, C2W, fxfycxcy, H, W, 
 
 def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, fxfycxcy, scale_modifier=None,
                          arena_cache=None, near_log2=None):
-    """All (sample, view) pairs in one launch set -> (images [B,V,3,H,W] fp32, state).
-    `arena_cache` (a dict): re-use grow-only arenas across calls; the caller must not hand the same dict to another
+    """All (sample, view) pairs in one launch set -> (images [B,V,3,H,W] fp32, state).  When the batch holds more than
+    2^31-1 instances (e.g. a random-init denoiser at 512x512: ~6e8 per view) the views are rendered in halves,
+    recursively -- the reference renders one view per call anyway (gs_core.py:990-1001); `state` then carries one
+    sub-state per chunk and render_batch_backward sums the chunks' gradients."""
+    try:
+        return _render_batch_forward_one(xyz, features, scaling, rotation, opacity, H, W, C2W, fxfycxcy, scale_modifier,
+                                         arena_cache, near_log2)
+    except DgsError as e:
+        V = C2W.shape[1]
+        if "exceeds 2^31-1" not in str(e) or V < 2:
+            raise
+    global LAST_NUM_RENDERED
+    outs, subs, total = [], [], 0
+    for ci, (v0, v1) in enumerate(((0, V // 2), (V // 2, V))):
+        sub_cache = None if arena_cache is None else arena_cache.setdefault(("views", ci), {})
+        o, st = render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W[:, v0:v1].contiguous(),
+                                     fxfycxcy[:, v0:v1].contiguous(), scale_modifier, sub_cache, near_log2)
+        outs.append(o)
+        subs.append((v0, v1, st))
+        total += st["R"]
+    LAST_NUM_RENDERED = total
+    return torch.cat(outs, dim=1), dict(sub=subs, R=total, tensors=subs[0][2]["tensors"])
+
+
+def _render_batch_forward_one(xyz, features, scaling, rotation, opacity, H, W, C2W, fxfycxcy, scale_modifier=None,
+                              arena_cache=None, near_log2=None):
+    """One launch set over every (sample, view) pair.  `arena_cache` (a dict): re-use grow-only arenas across calls; the caller must not hand the same dict to another
     forward while this call's state is still needed (renderer.py keeps one dict for inference and a pool of dicts for
     differentiated forwards); stream order makes the re-use safe."""
     _require_cuda(xyz, "xyz")
@@ -196,6 +221,13 @@ def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, f
 
 def render_batch_backward(state, grad_images, arena_cache=None):
     """-> (d_xyz, d_features, d_scaling, d_rotation, d_opacity), re-using the forward's sorted lists."""
+    if "sub" in state:  # view-chunked forward: the per-Gaussian gradients are sums over views
+        total = None
+        for ci, (v0, v1, st) in enumerate(state["sub"]):
+            sub_cache = None if arena_cache is None else arena_cache.setdefault(("views", ci), {})
+            g = render_batch_backward(st, grad_images[:, v0:v1], sub_cache)
+            total = g if total is None else tuple(a + b for a, b in zip(total, g))
+        return total
     tens = state["tensors"]
     dev = tens[0].device
     g = _f32c(grad_images)

@@ -90,3 +90,24 @@ def transform_input(image, c2w, fxfycxcy):
     o = m[:, :3, 3][:, None, :].expand_as(d)
     return (o.reshape(b, v, h, w, 3).permute(0, 1, 4, 2, 3).contiguous(),
             d.reshape(b, v, h, w, 3).permute(0, 1, 4, 2, 3).contiguous())
+
+
+def p_sample_loop_progressive(tab, model, shape, input_batch, clip_denoised=False, noise_fn=None):
+    """Restatement of p_sample_loop_progressive / p_sample / p_mean_variance (gaussian_diffusion.py:560-603, 479-518,
+    316-459) and of `_WrappedModel.__call__` (respace.py:121-137: the model sees timestep_map[t]) for the START_X /
+    FIXED_LARGE configuration.  `model(input_batch, mapped_t) -> (render_imgs [b, v, 3, h, w], gaussians)`."""
+    n = len(tab.betas)
+    tmap = torch.tensor(tab.timestep_map)
+    for i in list(range(n))[::-1]:
+        x = input_batch["image_noisy"]
+        t = torch.tensor([i] * shape[0], device=x.device)
+        input_batch["image"] = torch.cat([input_batch["image"][:, 0:1], input_batch["image_noisy"]], dim=1)
+        render_imgs, gaussians = model(input_batch, tmap.to(x.device)[t])
+        pred_xstart = render_imgs[:, 1:]
+        if clip_denoised:
+            pred_xstart = pred_xstart.clamp(-1, 1)
+        noise = torch.randn_like(x) if noise_fn is None else noise_fn(i, x)
+        sample = p_sample_step(tab, pred_xstart, x, t, noise)
+        input_batch["image_noisy"] = sample
+        yield dict(sample=sample, pred_xstart=pred_xstart, input_batch=input_batch,
+                   denoiser_output_dict=dict(render_images=render_imgs, pred_gaussians=gaussians))

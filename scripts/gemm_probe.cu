@@ -33,13 +33,14 @@ using namespace dgs::ptx;
   } while (0)
 
 namespace dgs {
+static CUtensorMapDataType g_tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box) {
   cuuint64_t gdim[5], gstr[5];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
-  CUresult r = cuTensorMapEncodeTiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim,
+  CUresult r = cuTensorMapEncodeTiled(out, g_tmap_dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim,
                                       gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 1;
@@ -112,6 +113,23 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int WAIT>
 __device__ __forceinline__ void pwait(uint64_t* bar, uint32_t parity) {
   if (WAIT == 0) { mbar_wait(bar, parity); return; }
@@ -127,14 +145,17 @@ __device__ __forceinline__ void pwait(uint64_t* bar, uint32_t parity) {
 //                               5 total cycles of the mma thread, 6 tiles, 7 total cycles of the producer
 template <int WAIT, int EPI, int LOAD, int STAGES, int CL4, int NOARR, int TE1>
 __global__ void __launch_bounds__(THREADS, 1)
-probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, __nv_bfloat16* out, int ldc,
+probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmF, __nv_bfloat16* out, int ldc,
              int M, int N, int K, unsigned long long* dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  constexpr int STG_BYTES = (EPI >= 2) ? 4 * 2 * 4096 : 0;  // per epilogue warp: two 32-row x 128-byte staging buffers
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -280,6 +301,61 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
+      if (EPI == 2) {
+        // bf16 tile through swizzled smem staging + TMA store: one 32-row x 64-column box (128-byte rows) per step
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+        uint8_t* stg = stg_base + (warp - 2) * 8192;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; c++) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c * 64), r0);
+          tmem_ld_32x32(t_row + (uint32_t)(c * 64 + 32), r1);
+          uint8_t* buf = stg + (c & 1) * 4096;
+          if (lane == 0) bulk_wait_read<1>();  // the store that read this buffer two steps ago is done with it
+          __syncwarp();
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint32_t* r = (j < 4) ? (r0 + 8 * j) : (r1 + 8 * (j - 4));
+            uint4 pk;
+            __nv_bfloat162 v;
+            v = __floats2bfloat162_rn(__uint_as_float(r[0]), __uint_as_float(r[1])); pk.x = *reinterpret_cast<uint32_t*>(&v);
+            v = __floats2bfloat162_rn(__uint_as_float(r[2]), __uint_as_float(r[3])); pk.y = *reinterpret_cast<uint32_t*>(&v);
+            v = __floats2bfloat162_rn(__uint_as_float(r[4]), __uint_as_float(r[5])); pk.z = *reinterpret_cast<uint32_t*>(&v);
+            v = __floats2bfloat162_rn(__uint_as_float(r[6]), __uint_as_float(r[7])); pk.w = *reinterpret_cast<uint32_t*>(&v);
+            *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) * 16)) = pk;  // SWIZZLE_128B
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmO, buf, n0 + c * 64, m0 + quad * 32);
+            bulk_commit();
+          }
+        }
+      }
+      if (EPI == 3) {
+        // fp32 tile added INTO global memory by the TMA (cp.reduce ... add): x += v without reading x on the SM
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+        uint8_t* stg = stg_base + (warp - 2) * 8192;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c++) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
+          uint8_t* buf = stg + (c & 1) * 4096;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) * 16)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmF, buf, n0 + c * 32, m0 + quad * 32);
+            bulk_commit();
+          }
+        }
+      }
       w_drain += clock64() - t1;
       tc_fence_before();
       if (TE1) {
@@ -294,6 +370,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (EPI >= 2 && lane == 0) bulk_wait<0>();
     if (threadIdx.x == 64) { dbg[blockIdx.x * 8 + 3] = w_tfull; dbg[blockIdx.x * 8 + 4] = w_drain; }
   }
   tc_fence_before();
@@ -307,13 +384,14 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 struct Bufs {
   __nv_bfloat16 *A, *W, *O;
+  float* F;
   unsigned long long* dbg;
 };
 
 template <int WAIT, int EPI, int LOAD, int STAGES, int CL4, int NOARR = 0, int TE1 = 0>
 static void run(const char* name, const Bufs& b, int M, int N, int K, int num_sms, int check) {
   auto kern = probe_kernel<WAIT, EPI, LOAD, STAGES, CL4, NOARR, TE1>;
-  const int smem = STAGES * STAGE_BYTES + 1024 + 256;
+  const int smem = STAGES * STAGE_BYTES + 1024 + 256 + (EPI >= 2 ? 32768 : 0);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   CUtensorMap tmA, tmB;
@@ -327,6 +405,25 @@ static void run(const char* name, const Bufs& b, int M, int N, int K, int num_sm
     uint32_t box[2] = {BK, (uint32_t)(CL4 ? 64 : BN_CTA)};
     if (dgs::make_tmap_bf16(&tmB, b.W, 2, dims, str, box)) { printf("tmap B failed\n"); exit(1); }
   }
+  CUtensorMap tmO, tmF;
+  {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)N * 2};
+    uint32_t box[2] = {64, 32};
+    if (dgs::make_tmap_bf16(&tmO, b.O, 2, dims, str, box)) { printf("tmap O failed\n"); exit(1); }
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)N * 4};
+    uint32_t box[2] = {32, 32};
+    dgs::g_tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const int rc = dgs::make_tmap_bf16(&tmF, b.F, 2, dims, str, box);
+    dgs::g_tmap_dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    if (rc) { printf("tmap F failed\n"); exit(1); }
+  }
+  if (EPI == 3) {
+    std::vector<float> ones((size_t)M * N, 1.0f);
+    CK(cudaMemcpy(b.F, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice));
+  }
+  if (EPI == 2) CK(cudaMemset(b.O, 0, (size_t)M * N * 2));
   constexpr int CSZ = CL4 ? 4 : 2;
   constexpr int CM = CL4 ? 512 : 256;
   const int tiles = ((M + CM - 1) / CM) * (N / BN);
@@ -354,7 +451,7 @@ static void run(const char* name, const Bufs& b, int M, int N, int K, int num_sm
   float best = 1e30f;
   for (int it = 0; it < 8; it++) {
     CK(cudaEventRecord(e0));
-    CK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, b.O, N, M, N, K, b.dbg));
+    CK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmF, b.O, N, M, N, K, b.dbg));
     CK(cudaEventRecord(e1));
     cudaError_t e = cudaEventSynchronize(e1);
     if (e != cudaSuccess) { printf("%-28s FAILED: %s\n", name, cudaGetErrorString(e)); exit(1); }
@@ -376,7 +473,24 @@ static void run(const char* name, const Bufs& b, int M, int N, int K, int num_sm
          " | producer: total %.0f wait_empty %.0f | epi: wait_tfull %.0f drain %.0f (%.0f/tile)\n",
          name, M, N, K, best * 1e3, 2.0 * M * N * K / best / 1e9, tl / nl, tot / nl, tot / nl / kblocks, mf / nl, mt / nl,
          ptot / nc, pe / nc, ef / nc, ed / nc, ed / nc / (tl / nl));
-  if (check && EPI == 0 && LOAD == 0) {
+  if (check && EPI == 3 && LOAD == 0) {
+    // F started at 1 and received 8 launches' worth of += acc
+    std::vector<__nv_bfloat16> hA((size_t)M * K), hW((size_t)N * K);
+    std::vector<float> hF((size_t)M * N);
+    CK(cudaMemcpy(hA.data(), b.A, hA.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hW.data(), b.W, hW.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hF.data(), b.F, hF.size() * 4, cudaMemcpyDeviceToHost));
+    double worst = 0;
+    for (int s = 0; s < 256; s++) {
+      const int r = (s < 4) ? (M - 1 - s) : (int)((s * 2654435761u) % (unsigned)M), c = (int)((s * 40503u + 17u * s * s) % (unsigned)N);
+      double acc = 0;
+      for (int k = 0; k < K; k++) acc += (double)__bfloat162float(hA[(size_t)r * K + k]) * (double)__bfloat162float(hW[(size_t)c * K + k]);
+      const double want = 1.0 + 8.0 * acc, err = fabs(hF[(size_t)r * N + c] - want) / (fabs(want) + 1.0);
+      if (err > worst) worst = err;
+    }
+    printf("    check (fp32 reduce-add, 8 launches): worst rel err %.3e %s\n", worst, worst < 1e-4 ? "OK" : "MISMATCH");
+  }
+  if (check && (EPI == 0 || EPI == 2) && LOAD == 0) {
     // spot check 64 entries against a host dot product
     std::vector<__nv_bfloat16> hA((size_t)M * K), hW((size_t)N * K), hO((size_t)M * N);
     CK(cudaMemcpy(hA.data(), b.A, hA.size() * 2, cudaMemcpyDeviceToHost));
@@ -384,7 +498,7 @@ static void run(const char* name, const Bufs& b, int M, int N, int K, int num_sm
     CK(cudaMemcpy(hO.data(), b.O, hO.size() * 2, cudaMemcpyDeviceToHost));
     double worst = 0;
     for (int s = 0; s < 256; s++) {
-      const int r = (int)((s * 2654435761u) % (unsigned)M), c = (int)((s * 40503u + 17u * s * s) % (unsigned)N);
+      const int r = (s < 4) ? (M - 1 - s) : (int)((s * 2654435761u) % (unsigned)M), c = (int)((s * 40503u + 17u * s * s) % (unsigned)N);
       double acc = 0;
       for (int k = 0; k < K; k++) acc += (double)__bfloat162float(hA[(size_t)r * K + k]) * (double)__bfloat162float(hW[(size_t)c * K + k]);
       const double got = __bfloat162float(hO[(size_t)r * N + c]);
@@ -438,6 +552,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&b.A, maxA * 2));
   CK(cudaMalloc(&b.W, maxW * 2));
   CK(cudaMalloc(&b.O, maxO * 2));
+  CK(cudaMalloc(&b.F, maxO * 4));
   CK(cudaMalloc(&b.dbg, 8 * 8 * 160));
   fill_kernel<<<(unsigned)((maxA + 255) / 256), 256>>>(b.A, maxA, 1u, 2.0f);
   fill_kernel<<<(unsigned)((maxW + 255) / 256), 256>>>(b.W, maxW, 2u, 0.1f);
@@ -446,20 +561,13 @@ int main(int argc, char** argv) {
     const int M = s[0], N = s[1], K = s[2];
     const int check = (M == 4098 && N == 3072);
     run_lib(b, M, N, K);
-    run<0, 0, 0, 6, 0>("pair (v1 protocol)", b, M, N, K, num_sms, 0);
-    run<0, 0, 0, 6, 0, 1, 0>("pair no-remote-arrive", b, M, N, K, num_sms, check);
-    run<0, 0, 0, 6, 0, 1, 1>("pair no-arr + 1-thr tempty", b, M, N, K, num_sms, check);
-    run<0, 1, 0, 6, 0, 1, 0>("pair no-arr no-epi", b, M, N, K, num_sms, 0);
-    run<0, 0, 0, 4, 0, 1, 1>("pair no-arr 1thr 4 stages", b, M, N, K, num_sms, 0);
-    run<0, 0, 0, 7, 0, 1, 1>("pair no-arr 1thr 7 stages", b, M, N, K, num_sms, 0);
-    run<2, 0, 0, 6, 0, 1, 1>("pair no-arr 1thr test_wait", b, M, N, K, num_sms, 0);
+    run<0, 0, 0, 6, 0, 1, 1>("pair (product protocol)", b, M, N, K, num_sms, check);
+    run<0, 0, 0, 4, 0, 1, 1>("pair 4 stages", b, M, N, K, num_sms, 0);
+    run<0, 2, 0, 4, 0, 1, 1>("pair 4st bf16 TMA-store epi", b, M, N, K, num_sms, 1);
+    run<0, 2, 0, 5, 0, 1, 1>("pair 5st bf16 TMA-store epi", b, M, N, K, num_sms, 0);
+    run<0, 3, 0, 4, 0, 1, 1>("pair 4st f32 TMA-reduce epi", b, M, N, K, num_sms, 1);
+    run<0, 3, 0, 5, 0, 1, 1>("pair 5st f32 TMA-reduce epi", b, M, N, K, num_sms, 0);
     printf("\n");
-    fflush(stdout);
-  }
-  for (auto& s : shapes) {
-    const int M = s[0], N = s[1], K = s[2];
-    const int check = (M == 4098 && N == 3072);
-    run<0, 0, 0, 6, 1, 1, 1>("quad(B mc) no-arr 1thr", b, M, N, K, num_sms, check);
     fflush(stdout);
   }
   return 0;
