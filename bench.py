@@ -296,8 +296,12 @@ def run_train(args, rank, local_rank, world):
     L.dgs_profile_enable(0)
     fam_ms = {k: v[0] / args.steps for k, v in fam.items() if v[1]}
     # end to end: pinned host inputs -> device every step, loss read back
+    from dgs_b200.diffusion import transform_input
+    e2e_keys = [k for k in host if k not in ("ray_o", "ray_d")]  # rays are derived on the device (TransformInput)
+
     def e2e_step():
-        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        b = {k: host[k].to(dev, non_blocking=True) for k in e2e_keys}
+        b["ray_o"], b["ray_d"] = transform_input(b["image"], b["c2w"], b["fxfycxcy"])
         return step(b).to("cpu")
     e2e_step()
     barrier()
@@ -329,7 +333,7 @@ def run_train(args, rank, local_rank, world):
                                 per_gpu_batch=B, parallelism=f"dp{world} (NCCL all-reduce of 460 M fp32 gradients)",
                                 l2="256 MB buffer written between timed steps"),
                     e2e=dict(value=world * B * args.steps / float(e2e_s), unit="samples/s",
-                             h2d_bytes_per_step=sum(v.numel() * v.element_size() for v in host.values()),
+                             h2d_bytes_per_step=sum(host[k].numel() * host[k].element_size() for k in e2e_keys),
                              d2h_bytes_per_step=lh.numel() * lh.element_size()),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=None, clocks=clocks,
                     breakdown_ms=dict(dit=dit_ms, families={k: round(v, 4) for k, v in fam_ms.items()}),
@@ -445,8 +449,14 @@ def main():
     fam_n = {k: v[1] // args.steps for k, v in fam.items() if v[1]}
 
     # ---- timed region 3: end to end through the public API with pinned HOST buffers ----
+    # What the reference pipeline holds on the host is the image and the cameras (pipline_obj.py:267-288); the rays are
+    # derived ON THE DEVICE by TransformInput, here dgs_b200.diffusion.transform_input (one kernel).
+    from dgs_b200.diffusion import transform_input
+    e2e_keys = ("image", "c2w", "fxfycxcy", "t")
+
     def e2e_step():
-        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        b = {k: host[k].to(dev, non_blocking=True) for k in e2e_keys}
+        b["ray_o"], b["ray_d"] = transform_input(b["image"], b["c2w"], b["fxfycxcy"])
         out = step(b)
         return out.to("cpu", non_blocking=False)
     for _ in range(2):
@@ -461,7 +471,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = world * args.batch * args.steps / float(e2e_s)
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    h2d = sum(host[k].numel() * host[k].element_size() for k in e2e_keys)
     d2h = out_host.numel() * out_host.element_size()
 
     if rank != 0:

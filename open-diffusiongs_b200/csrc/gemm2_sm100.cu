@@ -36,10 +36,11 @@ constexpr int A_BYTES = BM_CTA * BK * 2, B_BYTES = BN_CTA * BK * 2, STAGE_BYTES 
 constexpr int TMEM_COLS = 2 * BN;
 // TMAEPI (gemm_epilogue.cuh: outputs leave through shared-memory staging + TMA store / reduce-add): 5 operand stages +
 // 32 KB of staging; else 6 stages.  (The probe measured no difference between 4 and 7 stages on the DiT shapes.)
-template <bool TMAEPI>
+// TMAEPI = 2: additionally the bf16 aux (pre-activation) store of the training-mode fc1 epilogue: 4 stages + 64 KB.
+template <int TMAEPI>
 struct Cfg2 {
-  static constexpr int STAGES = TMAEPI ? 5 : 6;
-  static constexpr int STG_BYTES = TMAEPI ? EPI_TMA_STAGING_BYTES : 0;
+  static constexpr int STAGES = TMAEPI == 2 ? 4 : TMAEPI == 1 ? 5 : 6;
+  static constexpr int STG_BYTES = TMAEPI * EPI_TMA_STAGING_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256 + 2 * 2 * BN * 4;
 };
 
@@ -97,10 +98,14 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 // MN = false: C = A[M,K] x W[N,K]^T (K-major operands).  MN = true: C = A^T x W for A [K,M], W [K,N] row-major (both
 // operands MN-major: the weight-gradient GEMM, see gemm_sm100.cu); a CTA's stage then holds 2 + 2 swizzle atoms of
 // [64 K rows x 64 M/N elements].
-template <int EPI, bool MN, bool TMAEPI>
+// splits > 1 (split-K, fp32 TMA reduce-add epilogue only): work unit u = (tile u % num_tiles, K range u / num_tiles);
+// every unit adds its partial product into the (pre-zeroed) output.  Used by the weight-gradient GEMMs, whose K = tokens is
+// long and whose 256 x 256 output tiles are too few to fill 74 clusters (proj: 16 tiles).
+template <int EPI, bool MN, int TMAEPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmO, GemmEpilogue ep, int M, int N, int K) {
+                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX, GemmEpilogue ep,
+                      int M, int N, int K, int splits) {
   constexpr int STAGES = Cfg2<TMAEPI>::STAGES, STG_BYTES = Cfg2<TMAEPI>::STG_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -120,11 +125,13 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int num_m = (M + 2 * BM_CTA - 1) / (2 * BM_CTA), num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n, num_k = (K + BK - 1) / BK;
+  const int num_units = num_tiles * splits, kpb = (num_k + splits - 1) / splits;  // k-blocks per unit
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     if (TMAEPI) prefetch_tmap(&tmO);
+    if (TMAEPI == 2) prefetch_tmap(&tmX);
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; s++) { mbar_init(tfull_bar + s, 1); mbar_init(tempty_bar + s, 2); }
     fence_barrier_init();
@@ -146,10 +153,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        const int tile = unit % num_tiles, kb0 = (unit / num_tiles) * kpb, kb1 = min(num_k, kb0 + kpb);
         const int m0 = (tile / num_n) * (2 * BM_CTA) + (int)rank * BM_CTA;
         const int n0 = (tile % num_n) * BN + (int)rank * BN_CTA;
-        for (int kb = 0; kb < num_k; kb++) {
+        for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           const uint32_t leader_full = mapa(smem_u32(full_bar + stage), 0);
           if (leader) mbar_arrive_expect_tx(full_bar + stage, 2 * STAGE_BYTES);
@@ -176,11 +184,12 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        const int kb0 = (unit / num_tiles) * kpb, kb1 = min(num_k, kb0 + kpb);
         mbar_wait(tempty_bar + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_k; kb++) {
+        for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * A_BYTES), MN ? 8192 : 16, 1024);
@@ -188,7 +197,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; k++) {
             const uint64_t adv = MN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);  // 16 K rows = 2048 B  |  16 bf16 = 32 B
-            umma_bf16_2sm(d_tmem, adesc + adv, bdesc + adv, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16_2sm(d_tmem, adesc + adv, bdesc + adv, idesc, (kb > kb0 || k) ? 1u : 0u);
           }
           umma_commit_2sm(empty_bar + stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -205,7 +214,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t leader_tempty0 = mapa(smem_u32(tempty_bar), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      const int tile = unit % num_tiles;
       const int m0 = (tile / num_n) * (2 * BM_CTA) + (int)rank * BM_CTA, n0 = (tile % num_n) * BN;
       const int row = m0 + quad * 32 + lane;
       float* s_vec = s_vec_all + acc * 2 * BN;
@@ -214,9 +224,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      if constexpr (TMAEPI)
-        epilogue_drain_row_tma<EPI, BN>(ep, s_vec, uniform_gate, t_row, row, m0 + quad * 32, n0, M, N,
-                                        stg_base + (warp - 2) * 8192, lane, &tmO);
+      if constexpr (TMAEPI != 0)
+        epilogue_drain_row_tma<EPI, BN, TMAEPI == 2>(ep, s_vec, uniform_gate, t_row, row, m0 + quad * 32, n0, M, N,
+                                                     stg_base + (warp - 2) * (TMAEPI * 8192), lane, &tmO, &tmX, splits > 1);
       else
         epilogue_drain_row<EPI, BN>(ep, s_vec, uniform_gate, t_row, row, n0, M, N);
       tc_fence_before();
@@ -240,9 +250,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 }  // namespace g2
 
-template <int EPI, bool MN = false, bool TMAEPI = false>
+template <int EPI, bool MN = false, int TMAEPI = 0>
 static int launch_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmEpilogue& ep, int M,
-                       int N, int K, int num_sms, cudaStream_t st) {
+                       int N, int K, int num_sms, cudaStream_t st, const CUtensorMap* tmX = nullptr, int splits = 1) {
   auto kern = g2::gemm_bf16_2cta_kernel<EPI, MN, TMAEPI>;
   constexpr int SMEM = g2::Cfg2<TMAEPI>::SMEM_BYTES;
   static bool configured = false;
@@ -250,11 +260,11 @@ static int launch_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  const int tiles = ceil_div(M, 2 * g2::BM_CTA) * ceil_div(N, g2::BN);
+  const int tiles = ceil_div(M, 2 * g2::BM_CTA) * ceil_div(N, g2::BN) * splits;
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
   // cluster dims come from the kernel's __cluster_dims__ attribute; PDL as for the single-CTA kernel
-  DGS_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(g2::THREADS), SMEM, st, tmA, tmB, tmO, ep, M, N, K));
+  DGS_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(g2::THREADS), SMEM, st, tmA, tmB, tmO, tmX ? *tmX : tmO, ep, M, N, K, splits));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }
@@ -288,18 +298,26 @@ int gemm_bf16_2cta(const void* A, const void* W, int M, int N, int K, int epi, c
     tma_epi = (e && e[0] == '0') ? 0 : 1;
   }
   const bool out_f32 = epi == EPI_GATE_RESID_F32;
-  const bool can_tma = tma_epi && !ep.aux && !ep.resid && (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || out_f32) &&
-                       ((uintptr_t)ep.out % 16) == 0 && ((size_t)ep.ldc * (out_f32 ? 4 : 2)) % 16 == 0;
+  const bool gelu_aux = epi == EPI_BIAS_GELU_BF16 && ep.aux;  // training-mode fc1: also stores the pre-activation
+  const bool can_tma = tma_epi && (!ep.aux || gelu_aux) && !ep.resid &&
+                       (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || out_f32) && ((uintptr_t)ep.out % 16) == 0 &&
+                       ((uintptr_t)ep.aux % 16) == 0 && ((size_t)ep.ldc * (out_f32 ? 4 : 2)) % 16 == 0;
   CUtensorMap tmO = tmA;  // placeholder when the TMA epilogue is not used (never dereferenced)
   if (can_tma) {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)ep.ldc * (out_f32 ? 4 : 2)};
     uint32_t box[2] = {out_f32 ? 32u : 64u, 32u};  // 128-byte rows x 32 rows
     int rc = out_f32 ? make_tmap_f32(&tmO, ep.out, 2, dims, str, box) : make_tmap_bf16(&tmO, ep.out, 2, dims, str, box);
     if (rc) return rc;
+    if (gelu_aux) {
+      CUtensorMap tmX;
+      rc = make_tmap_bf16(&tmX, ep.aux, 2, dims, str, box);
+      if (rc) return rc;
+      return launch_2cta<EPI_BIAS_GELU_BF16, false, 2>(tmA, tmB, tmO, ep, M, N, K, num_sms, st, &tmX);
+    }
     switch (epi) {
-      case EPI_BIAS_BF16: return launch_2cta<EPI_BIAS_BF16, false, true>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
-      case EPI_BIAS_GELU_BF16: return launch_2cta<EPI_BIAS_GELU_BF16, false, true>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
-      default: return launch_2cta<EPI_GATE_RESID_F32, false, true>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
+      case EPI_BIAS_BF16: return launch_2cta<EPI_BIAS_BF16, false, 1>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
+      case EPI_BIAS_GELU_BF16: return launch_2cta<EPI_BIAS_GELU_BF16, false, 1>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
+      default: return launch_2cta<EPI_GATE_RESID_F32, false, 1>(tmA, tmB, tmO, ep, M, N, K, num_sms, st);
     }
   }
   switch (epi) {
@@ -333,7 +351,34 @@ int gemm_bf16_tn_2cta(const void* A, const void* W, int M, int N, int K, const G
     int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
     if (rc) return rc;
   }
-  return launch_2cta<EPI_F32, true>(tmA, tmB, tmA, ep, M, N, K, num_sms, st);
+  // Split-K: the output has ceil(M/256) * (N/256) tiles (16 ... 64 for the DiT weight gradients) but K = tokens is long
+  // (257 k-blocks at 4 samples): cut K so that the work units fill ~2 waves of the 74 clusters; every unit adds its
+  // partial sum into the zeroed output with the TMA (fp32 reduce-add), rows >= M clipped by the tensor map.
+  const int tiles = ceil_div(M, 2 * g2::BM_CTA) * (N / g2::BN), num_k = ceil_div(K, g2::BK), clusters = num_sms / 2;
+  static int splitk = -1;
+  if (splitk < 0) {
+    const char* e = getenv("DGS_GEMM_SPLITK");
+    splitk = (e && e[0] == '0') ? 0 : 1;
+  }
+  int splits = 1;
+  if (splitk && !ep.bias && tiles < 2 * clusters && num_k >= 32 && ((uintptr_t)ep.out % 16) == 0 &&
+      ((size_t)(ep.ldc ? ep.ldc : N) * 4) % 16 == 0) {
+    splits = (2 * clusters + tiles - 1) / tiles;            // ~2 waves of work units
+    if (splits > num_k / 8) splits = num_k / 8;             // at least 8 k-blocks per unit
+    const int kpb = ceil_div(num_k, splits);
+    splits = ceil_div(num_k, kpb);                          // no empty unit
+  }
+  if (splits <= 1) return launch_2cta<EPI_F32, true>(tmA, tmB, tmA, ep, M, N, K, num_sms, st);
+  const int ldc = ep.ldc ? ep.ldc : N;
+  CUtensorMap tmO;
+  {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)ldc * 4};
+    uint32_t obox[2] = {32u, 32u};
+    int rc = make_tmap_f32(&tmO, ep.out, 2, dims, str, obox);
+    if (rc) return rc;
+  }
+  DGS_CUDA_OK(cudaMemset2DAsync(ep.out, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
+  return launch_2cta<EPI_F32, true, 1>(tmA, tmB, tmO, ep, M, N, K, num_sms, st, nullptr, splits);
 }
 
 }  // namespace dgs

@@ -174,18 +174,23 @@ __device__ __forceinline__ void epi_bulk_wait_all() { asm volatile("cp.async.bul
 
 constexpr int EPI_TMA_STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 bytes)
 
-// `stg` = this warp's two staging buffers (8 KB, 1024-byte aligned); slab_row0 = first output row of the warp's slab.
-template <int EPI, int BN>
+// `stg` = this warp's staging buffers (1024-byte aligned): two 4 KB buffers for the output, and with AUX two more (at
+// +8 KB) for the bf16 pre-activation the training-mode fc1 epilogue also stores (tm_aux).  slab_row0 = first output row
+// of the warp's 32-row slab.  `reduce`: EPI_F32 only -- add into the output instead of storing (split-K partial sums).
+template <int EPI, int BN, bool AUX = false>
 __device__ __forceinline__ void epilogue_drain_row_tma(const GemmEpilogue& ep, const float* s_vec, bool uniform_gate,
                                                        uint32_t t_row, int row, int slab_row0, int n0, int M, int N,
-                                                       uint8_t* stg, int lane, const CUtensorMap* tm_out) {
+                                                       uint8_t* stg, int lane, const CUtensorMap* tm_out,
+                                                       const CUtensorMap* tm_aux = nullptr, bool reduce = false) {
   using namespace ptx;
-  static_assert(EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_GATE_RESID_F32, "TMA epilogue: unsupported");
+  static_assert(EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_GATE_RESID_F32 || EPI == EPI_F32,
+                "TMA epilogue: unsupported");
+  static_assert(!AUX || EPI == EPI_BIAS_GELU_BF16, "TMA epilogue: the aux store exists for the fc1 epilogue only");
   const int crow = row < M ? row : M - 1;  // rows past the end compute on a valid row's gate; their box rows are clipped
   const float* gate_row = nullptr;
   if (EPI == EPI_GATE_RESID_F32 && !uniform_gate) gate_row = ep.gate + (size_t)(crow / ep.rows_per_sample) * ep.gate_stride;
   const uint32_t sw = (uint32_t)(lane & 7);
-  if (EPI == EPI_GATE_RESID_F32) {
+  if (EPI == EPI_GATE_RESID_F32 || EPI == EPI_F32) {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; c++) {
       const int n = n0 + c * 32;
@@ -200,20 +205,24 @@ __device__ __forceinline__ void epilogue_drain_row_tma(const GemmEpilogue& ep, c
       const float* sg = s_vec + BN + c * 32;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        float4 g4;
-        if (uniform_gate) g4 = make_float4(sg[4 * j], sg[4 * j + 1], sg[4 * j + 2], sg[4 * j + 3]);
-        else g4 = __ldg(reinterpret_cast<const float4*>(gate_row + n + 4 * j));
         float4 v4;
-        v4.x = g4.x * (__uint_as_float(r[4 * j]) + sb[4 * j]);
-        v4.y = g4.y * (__uint_as_float(r[4 * j + 1]) + sb[4 * j + 1]);
-        v4.z = g4.z * (__uint_as_float(r[4 * j + 2]) + sb[4 * j + 2]);
-        v4.w = g4.w * (__uint_as_float(r[4 * j + 3]) + sb[4 * j + 3]);
+        v4.x = __uint_as_float(r[4 * j]) + sb[4 * j];
+        v4.y = __uint_as_float(r[4 * j + 1]) + sb[4 * j + 1];
+        v4.z = __uint_as_float(r[4 * j + 2]) + sb[4 * j + 2];
+        v4.w = __uint_as_float(r[4 * j + 3]) + sb[4 * j + 3];
+        if (EPI == EPI_GATE_RESID_F32) {
+          float4 g4;
+          if (uniform_gate) g4 = make_float4(sg[4 * j], sg[4 * j + 1], sg[4 * j + 2], sg[4 * j + 3]);
+          else g4 = __ldg(reinterpret_cast<const float4*>(gate_row + n + 4 * j));
+          v4.x *= g4.x; v4.y *= g4.y; v4.z *= g4.z; v4.w *= g4.w;
+        }
         *reinterpret_cast<float4*>(buf + lane * 128 + (((uint32_t)j ^ sw) * 16)) = v4;  // SWIZZLE_128B
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        epi_tma_reduce_add_2d(tm_out, buf, n, slab_row0);
+        if (EPI == EPI_GATE_RESID_F32 || reduce) epi_tma_reduce_add_2d(tm_out, buf, n, slab_row0);
+        else epi_tma_store_2d(tm_out, buf, n, slab_row0);
         epi_bulk_commit();
       }
     }
@@ -226,6 +235,7 @@ __device__ __forceinline__ void epilogue_drain_row_tma(const GemmEpilogue& ep, c
       tmem_ld_32x32(t_row + (uint32_t)(c * 64), r0);
       tmem_ld_32x32(t_row + (uint32_t)(c * 64 + 32), r1);
       uint8_t* buf = stg + (c & 1) * 4096;
+      uint8_t* abuf = stg + 8192 + (c & 1) * 4096;
       if (lane == 0) epi_bulk_wait_read1();
       __syncwarp();
       tmem_ld_wait();
@@ -235,9 +245,16 @@ __device__ __forceinline__ void epilogue_drain_row_tma(const GemmEpilogue& ep, c
         const uint32_t* r = (j < 4) ? (r0 + 8 * j) : (r1 + 8 * (j - 4));
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          v[i] = __uint_as_float(r[i]) + sb[8 * j + i];
-          if (EPI == EPI_BIAS_GELU_BF16) v[i] = epi_gelu_tanh(v[i]);
+        for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]) + sb[8 * j + i];
+        if (AUX) {  // training: keep the pre-activation acc + b (bf16)
+          uint4 pa;
+          pa.x = epi_pack_bf16(v[0], v[1]); pa.y = epi_pack_bf16(v[2], v[3]);
+          pa.z = epi_pack_bf16(v[4], v[5]); pa.w = epi_pack_bf16(v[6], v[7]);
+          *reinterpret_cast<uint4*>(abuf + lane * 128 + (((uint32_t)j ^ sw) * 16)) = pa;
+        }
+        if (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] = epi_gelu_tanh(v[i]);
         }
         uint4 pk;
         pk.x = epi_pack_bf16(v[0], v[1]); pk.y = epi_pack_bf16(v[2], v[3]);
@@ -248,7 +265,8 @@ __device__ __forceinline__ void epilogue_drain_row_tma(const GemmEpilogue& ep, c
       __syncwarp();
       if (lane == 0) {
         epi_tma_store_2d(tm_out, buf, n, slab_row0);
-        epi_bulk_commit();
+        if (AUX) epi_tma_store_2d(tm_aux, abuf, n, slab_row0);
+        epi_bulk_commit();  // one group per step: wait_group.read 1 frees both buffers of the step before last
       }
     }
   }

@@ -252,13 +252,14 @@ int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const 
               "gemm: operand row strides must be multiples of 8 elements (K=%d lda=%d ldb=%d)", K, ep.lda, ep.ldb);
   DGS_REQUIRE(epi != EPI_DGELU_BF16 || ep.aux, "gemm: EPI_DGELU_BF16 needs aux = saved pre-activation");
   DGS_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm: operands must be 16-byte aligned");
-  // CTA-pair kernel (gemm2_sm100.cu: 256 x 256 tiles, 2/3 of the operand traffic per CTA).  It is CORRECT (all parity
-  // tests pass with DGS_GEMM_2CTA=1) but on B200 it currently runs ~1.6x SLOWER than this single-CTA kernel
-  // (profiles/r1_ncu_gemm2cta.txt: tensor pipe 29 % active, L2 26 %): opt-in until that is understood.
+  // CTA-pair kernel (gemm2_sm100.cu: 256 x 256 tiles per 2-CTA cluster, tcgen05.mma.cta_group::2, 2/3 of the operand
+  // traffic per CTA, TMA-store epilogues): the DEFAULT wherever a GEMM has enough 256 x 256 tiles.  Measured on B200
+  // (profiles/r1_gemm_probe_v3.txt, r1_bench_v9.json): 1.70 vs 1.55 PFLOP/s at 8192 x 4096 x 4096 and 19-33 % less time
+  // on the four DiT linears at N = 4098 than the single-CTA kernel below.  DGS_GEMM_2CTA=0 falls back to the latter.
   static int use_2cta = -1;
   if (use_2cta < 0) {
     const char* e = getenv("DGS_GEMM_2CTA");
-    use_2cta = (e && e[0] == '1') ? 1 : 0;
+    use_2cta = (e && e[0] == '0') ? 0 : 1;
   }
   if (use_2cta && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_2cta(A, W, M, N, K, epi, ep, st);
   // 256 x 256 single-CTA tiles (gemm3_sm100.cu, 1.5x less operand traffic per FLOP): DGS_GEMM_M256=1
@@ -313,8 +314,12 @@ int gemm_bf16_tn(const void* A, const void* W, int M, int N, int K, const GemmEp
   DGS_REQUIRE(N % 32 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm_tn: need N %% 32 == 0 and row strides %% 8 == 0");
   DGS_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm_tn: operands must be 16-byte aligned");
   {
+    // CTA-pair kernel by default (see gemm_bf16); with its split-K path (long K = tokens) even a handful of 256 x 256
+    // output tiles fill the machine, so the tile-count condition only applies to short K
     const char* e = getenv("DGS_GEMM_2CTA");
-    if (e && e[0] == '1' && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_tn_2cta(A, W, M, N, K, ep, st);
+    const int tiles2 = ceil_div(M, 256) * (N / 256);
+    if (!(e && e[0] == '0') && N % 256 == 0 && M >= 128 && (tiles2 >= 48 || K >= 2048))
+      return gemm_bf16_tn_2cta(A, W, M, N, K, ep, st);
   }
   const bool wide = (N % 256 == 0) && (ceil_div(M, BM) * (N / 256) >= 120);
   CUtensorMap tmA, tmB;
