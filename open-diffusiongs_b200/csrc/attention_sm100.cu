@@ -31,26 +31,7 @@ namespace dgs {
 
 using namespace ptx;
 
-// Tail split (wave quantisation).  A (128-query block, head, sample) unit is one CTA and 2 * 148 = 296 CTAs are resident;
-// at N = 4098 there are 33 * 16 = 528 units = 1.78 waves, so the second wave leaves 22 % of the slots idle and the kernel
-// takes the time of 2.0 waves (582 vs 733 TFLOP/s at N = 16,386 where 2064 units = 6.97 waves).  The units of the last,
-// partial wave are therefore cut along the KEY axis into pieces that are separate CTAs (launched after all whole units:
-// CTAs start in block-index order): a piece runs the same loop over its key-block range and leaves an UNNORMALISED partial
-// (O, running max, row sum) per query row in a scratch buffer; the piece that arrives last at a row's counter merges the
-// row's partials (rescaled to the common max -- exact, it is the same online-softmax identity the in-kernel rescale uses)
-// and writes the output.  Counters are reset by the merger, so they are zero between launches.
 constexpr int ATT_BM = 128, ATT_BN = 64, ATT_HD = 64, ATT_KV_STAGES = 4, ATT_THREADS = 192;
-constexpr int ATT_MAX_PIECES = 8;
-constexpr int ATT_PART_FLOATS = 68;  // per query row: 64 x O, running max, row sum, 2 x pad (16-byte rows)
-struct AttSched {
-  int n_whole;                      // CTAs [0, n_whole) process whole units
-  int n_tail;                       // units of the split tail wave; CTA n_whole + piece * n_tail + t = piece of unit n_whole + t
-  int pieces;                       // pieces per tail unit (0 = no split)
-  int bound[ATT_MAX_PIECES + 1];    // piece i covers key blocks [bound[i], bound[i + 1])
-  int nq;                           // query blocks per (sample, head)
-  float* scratch;                   // [n_tail * pieces][128][ATT_PART_FLOATS]
-  int* counters;                    // [n_tail][128], zero between launches
-};
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_HD * 2;    // [128 x 64] bf16 (Q, and one P buffer: 128 rows x 64 keys)
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_HD * 2;   // [64 x 64] bf16 (one K or V block)
 constexpr int ATT_ONES_BYTES = 16 * 128;           // [16 x 64] bf16 ones, K-major (B operand of the row-sum MMA)
@@ -73,7 +54,7 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 template <int POLY_OF_8>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                     __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int Np, int N, int H, AttSched sched) {
+                     __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int Np, int N, int H) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -92,18 +73,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // work item of this CTA: a whole unit, or one key-range piece of a tail unit
-  int unit = (int)blockIdx.x, piece = -1, tail_idx = 0, j0 = 0, j1 = (N + ATT_BN - 1) / ATT_BN;
-  if (unit >= sched.n_whole) {
-    const int t = unit - sched.n_whole;
-    piece = t / sched.n_tail;
-    tail_idx = t - piece * sched.n_tail;
-    unit = sched.n_whole + tail_idx;
-    j0 = sched.bound[piece];
-    j1 = sched.bound[piece + 1];
-  }
-  const int q0 = (unit % sched.nq) * ATT_BM, h = (unit / sched.nq) % H, b = unit / (sched.nq * H);
-  const int n_blocks = j1 - j0;  // key blocks of THIS CTA: j = j0 + jj; all pipeline bookkeeping runs on the local jj
+  const int q0 = blockIdx.x * ATT_BM, h = blockIdx.y, b = blockIdx.z;
+  const int n_blocks = (N + ATT_BN - 1) / ATT_BN;
   const int D = H * ATT_HD;
 
   if (warp == 0 && lane == 0) {
@@ -137,9 +108,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t use = (uint32_t)(j / ATT_KV_STAGES);
         mbar_wait(kv_empty + s, (use & 1) ^ 1);
         mbar_arrive_expect_tx(k_full + s, ATT_KV_BYTES);
-        tma_load_3d(sK + s * ATT_KV_BYTES, &tm_kv, k_full + s, D + h * ATT_HD, (j0 + j) * ATT_BN, b);
+        tma_load_3d(sK + s * ATT_KV_BYTES, &tm_kv, k_full + s, D + h * ATT_HD, j * ATT_BN, b);
         mbar_arrive_expect_tx(v_full + s, ATT_KV_BYTES);
-        tma_load_3d(sV + s * ATT_KV_BYTES, &tm_kv, v_full + s, 2 * D + h * ATT_HD, (j0 + j) * ATT_BN, b);
+        tma_load_3d(sV + s * ATT_KV_BYTES, &tm_kv, v_full + s, 2 * D + h * ATT_HD, j * ATT_BN, b);
       }
     }
   } else if (warp == 1) {
@@ -197,7 +168,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_wait(s_full + buf, (uint32_t)(j >> 1) & 1);
       tc_fence_after();
       const uint32_t t_s = t_lane + TMEM_S + (uint32_t)(buf * ATT_BN);
-      const int kv_valid = N - (j0 + j) * ATT_BN;  // >= 1; < ATT_BN only in the last block of the sequence
+      const int kv_valid = N - j * ATT_BN;  // >= 1; < ATT_BN only in the last block
       uint32_t r0[32], r1[32];
       tmem_ld_32x32(t_s, r0);
       tmem_ld_32x32(t_s + 32u, r1);
@@ -269,71 +240,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       tc_fence_before();  // our tcgen05.ld of S_j / O and the store of P_j are complete before the issuer proceeds
       mbar_arrive(p_full + buf);
     }
-    {  // all blocks of this CTA accumulated -> (merge the unit's pieces,) normalise and store
+    {  // all blocks accumulated -> normalise and store
       const int last = n_blocks - 1;
       mbar_wait(pv_full + (last & 1), (uint32_t)(last >> 1) & 1);
       tc_fence_after();
       uint32_t q0r[32], q1r[32];
       tmem_ld_32x32(t_o, q0r);
       tmem_ld_32x32(t_o + 32u, q1r);
-      uint32_t lsum = tmem_ld_32x1(t_l);
+      const uint32_t lsum = tmem_ld_32x1(t_l);
       tmem_ld_wait();
-      bool write_out = q0 + row < N;
-      if (piece >= 0 && write_out) {
-        // leave this piece's partial row, then see whether the unit's other pieces are already there
-        float* prow = sched.scratch + (((size_t)tail_idx * sched.pieces + piece) * ATT_BM + row) * ATT_PART_FLOATS;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          *reinterpret_cast<uint4*>(prow + i) = make_uint4(q0r[i], q0r[i + 1], q0r[i + 2], q0r[i + 3]);
-          *reinterpret_cast<uint4*>(prow + 32 + i) = make_uint4(q1r[i], q1r[i + 1], q1r[i + 2], q1r[i + 3]);
-        }
-        *reinterpret_cast<float4*>(prow + 64) = make_float4(m_run, __uint_as_float(lsum), 0.f, 0.f);
-        __threadfence();  // partial visible device-wide before the arrival is
-        int* cnt = sched.counters + (size_t)tail_idx * ATT_BM + row;
-        const int arrived = atomicAdd(cnt, 1);
-        write_out = arrived == sched.pieces - 1;
-        if (write_out) {
-          __threadfence();
-          // common max of all pieces, then rescale and add (own values are in registers)
-          float m_all = m_run;
-          for (int pc = 0; pc < sched.pieces; pc++) {
-            if (pc == piece) continue;
-            const float* orow = sched.scratch + (((size_t)tail_idx * sched.pieces + pc) * ATT_BM + row) * ATT_PART_FLOATS;
-            m_all = fmaxf(m_all, __ldcg(orow + 64));
-          }
-          const float w_own = ex2_approx((m_run - m_all) * sl2);
-#pragma unroll
-          for (int i = 0; i < 32; i++) {  // accumulate in place (registers are tight: 168 per thread at 2 CTAs/SM)
-            q0r[i] = __float_as_uint(__uint_as_float(q0r[i]) * w_own);
-            q1r[i] = __float_as_uint(__uint_as_float(q1r[i]) * w_own);
-          }
-          float l_all = __uint_as_float(lsum) * w_own;
-          for (int pc = 0; pc < sched.pieces; pc++) {
-            if (pc == piece) continue;
-            const float* orow = sched.scratch + (((size_t)tail_idx * sched.pieces + pc) * ATT_BM + row) * ATT_PART_FLOATS;
-            const float4 ml = __ldcg(reinterpret_cast<const float4*>(orow + 64));
-            const float w = ex2_approx((ml.x - m_all) * sl2);
-            l_all = fmaf(ml.y, w, l_all);
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 a = __ldcg(reinterpret_cast<const float4*>(orow + i));
-              const float4 c = __ldcg(reinterpret_cast<const float4*>(orow + 32 + i));
-              q0r[i] = __float_as_uint(fmaf(a.x, w, __uint_as_float(q0r[i])));
-              q0r[i + 1] = __float_as_uint(fmaf(a.y, w, __uint_as_float(q0r[i + 1])));
-              q0r[i + 2] = __float_as_uint(fmaf(a.z, w, __uint_as_float(q0r[i + 2])));
-              q0r[i + 3] = __float_as_uint(fmaf(a.w, w, __uint_as_float(q0r[i + 3])));
-              q1r[i] = __float_as_uint(fmaf(c.x, w, __uint_as_float(q1r[i])));
-              q1r[i + 1] = __float_as_uint(fmaf(c.y, w, __uint_as_float(q1r[i + 1])));
-              q1r[i + 2] = __float_as_uint(fmaf(c.z, w, __uint_as_float(q1r[i + 2])));
-              q1r[i + 3] = __float_as_uint(fmaf(c.w, w, __uint_as_float(q1r[i + 3])));
-            }
-          }
-          lsum = __float_as_uint(l_all);
-          m_run = m_all;
-          *cnt = 0;  // every piece of this row has arrived: leave the counter ready for the next launch
-        }
-      }
-      if (write_out) {
+      if (q0 + row < N) {
         // training: log2-domain log-sum-exp of the scaled scores (the stale max is exact here: l was accumulated
         // against the same m_run), consumed by attention_bwd_sm100.cu
         if (lse2) lse2[((size_t)b * H + h) * Np + q0 + row] = fmaf(m_run, sl2, log2f(__uint_as_float(lsum)));
@@ -368,65 +284,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   }
 }
 
-// Work schedule (see "Tail split" at the top): whole units first, then the pieces of the last partial wave.
-//   f = (units in the partial wave) / (resident CTAs).  f >= 0.5: two pieces per tail unit, a long one [0, a) -- one per
-//   slot -- and a short one [a, nb) -- the ~1/(1-f) short pieces that share each remaining slot take as long as one long
-//   piece (per-CTA start-up counted as ATT_PIECE_OVERHEAD key blocks).  f < 0.5: floor(1/f) <= 8 equal pieces.
-constexpr int ATT_PIECE_OVERHEAD = 4;
-static AttSched make_att_sched(int units, int nq, int nb, int slots) {
-  AttSched sc = {};
-  sc.nq = nq;
-  sc.n_whole = units;
-  static int split = -1;
-  if (split < 0) {
-    const char* e = getenv("DGS_ATT_SPLIT");
-    split = (e && e[0] == '0') ? 0 : 1;
-  }
-  const int tail = units % slots;
-  if (!split || tail == 0 || nb < 16) return sc;
-  const double f = (double)tail / slots;
-  if (f > 0.9) return sc;
-  int pieces, bound[ATT_MAX_PIECES + 1];
-  if (f >= 0.5) {
-    // a = r (b + o), a + b = nb, r = tail / (slots - tail) short pieces per remaining slot
-    const double r = (double)tail / (slots - tail), o = ATT_PIECE_OVERHEAD;
-    int bshort = (int)((nb - r * o) / (1.0 + r) + 0.5);
-    if (bshort < 4) return sc;
-    pieces = 2;
-    bound[0] = 0; bound[1] = nb - bshort; bound[2] = nb;
-  } else {
-    pieces = (int)(1.0 / f);
-    if (pieces > ATT_MAX_PIECES) pieces = ATT_MAX_PIECES;
-    while (pieces > 1 && nb / pieces < 6) pieces--;  // pieces of at least 6 key blocks
-    if (pieces < 2) return sc;
-    const int ps = (nb + pieces - 1) / pieces;
-    pieces = (nb + ps - 1) / ps;                     // no empty piece
-    for (int i = 0; i <= pieces; i++) bound[i] = i * ps < nb ? i * ps : nb;
-  }
-  sc.n_whole = units - tail;
-  sc.n_tail = tail;
-  sc.pieces = pieces;
-  for (int i = 0; i <= pieces; i++) sc.bound[i] = bound[i];
-  return sc;
-}
-
-// scratch of the tail split: at most 2 * slots pieces of 128 rows, allocated once per device
-static int att_scratch(int dev, int slots, float** scratch, int** counters) {
-  static float* s_scratch[64] = {};
-  static int* s_counters[64] = {};
-  DGS_REQUIRE(dev >= 0 && dev < 64, "attention: device index %d out of range", dev);
-  if (!s_scratch[dev]) {
-    const size_t sbytes = (size_t)2 * slots * ATT_BM * ATT_PART_FLOATS * sizeof(float);
-    const size_t cbytes = (size_t)slots * ATT_BM * sizeof(int);
-    DGS_CUDA_OK(cudaMalloc(&s_scratch[dev], sbytes));
-    DGS_CUDA_OK(cudaMalloc(&s_counters[dev], cbytes));
-    DGS_CUDA_OK(cudaMemset(s_counters[dev], 0, cbytes));
-  }
-  *scratch = s_scratch[dev];
-  *counters = s_counters[dev];
-  return DGS_OK;
-}
-
 int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st) {
   DGS_REQUIRE(B > 0 && N > 0 && H > 0, "attention: bad shape B=%d N=%d H=%d", B, N, H);
   const int D = H * ATT_HD;
@@ -440,10 +297,6 @@ int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, 
   rc = make_tmap_bf16(&tm_kv, qkv, 3, dims, str, box_kv);
   if (rc) return rc;
   static int poly = -1;
-  static int num_sms[64] = {};
-  int dev = 0;
-  DGS_CUDA_OK(cudaGetDevice(&dev));
-  DGS_REQUIRE(dev >= 0 && dev < 64, "attention: device index %d out of range", dev);
   if (poly < 0) {
     const char* e = getenv("DGS_ATT_POLY");
     poly = e ? atoi(e) : ATT_POLY_DEFAULT;
@@ -452,20 +305,11 @@ int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, 
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
   }
-  if (!num_sms[dev]) DGS_CUDA_OK(cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev));
-  const int nq = ceil_div(N, ATT_BM), nb = ceil_div(N, ATT_BN), slots = 2 * num_sms[dev];  // 2 CTAs resident per SM
-  DGS_REQUIRE((long long)nq * H * B < (1ll << 30), "attention: too many (query block, head, sample) units");
-  const int units = nq * H * B;
-  AttSched sc = make_att_sched(units, nq, nb, slots);
-  if (sc.pieces) {
-    rc = att_scratch(dev, slots, &sc.scratch, &sc.counters);
-    if (rc) return rc;
-  }
-  dim3 grid((unsigned)(sc.n_whole + sc.n_tail * sc.pieces));
+  dim3 grid(ceil_div(N, ATT_BM), H, B);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   auto kern = poly == 1 ? attention_fwd_kernel<1> : poly == 2 ? attention_fwd_kernel<2> : poly >= 3 ? attention_fwd_kernel<3>
                                                                                                    : attention_fwd_kernel<0>;
-  DGS_CUDA_OK(launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tm_q, tm_kv, o, lse2, Np, N, H, sc));
+  DGS_CUDA_OK(launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tm_q, tm_kv, o, lse2, Np, N, H));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }

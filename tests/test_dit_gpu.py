@@ -90,8 +90,7 @@ def test_gemm_gate_residual_epilogue():
     assert rel(out, ref) < 2e-5
 
 
-# (1, 2050, 20) / (1, 1500, 16) / (3, 4098, 16): 5-way, two-piece-without-a-whole-wave and 2-way key-axis tail splits of the
-# forward kernel (attention_sm100.cu "Tail split"; (1, 4098, 16) itself is the two-piece case of the bench workload)
+# (1, 2050, 20) / (1, 1500, 16) / (3, 4098, 16): ragged query/key tails at other head counts and batch sizes
 # (1, 16386, 2): the 512x512 configurations (obj-512 / scene-512 / the pipline_obj.py demo), two heads bound the fp32 reference
 @pytest.mark.parametrize("B,N,H", [(1, 4098, 16), (2, 1026, 16), (1, 128, 2), (1, 130, 1), (2, 77, 4), (1, 1, 1), (1, 16386, 2),
                                    (1, 2050, 20), (1, 1500, 16), (3, 4098, 16)])
