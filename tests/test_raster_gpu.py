@@ -286,6 +286,47 @@ def test_batched_renderer_vs_oracle_renderer():
         assert e < TOL, k
 
 
+def test_view_chunked_render_equals_single_batch(monkeypatch):
+    """The > 2^31-1 instances fallback (dgs_b200/raster.py: views rendered in halves, gradients summed over the chunks)
+    on the real kernels: the overflow status is injected for every call with more than 2 views, so a 5-view batch runs as
+    chunks of (1, 1) and (1, 2) views; images must be bit-identical to the one-batch render (each view's blend is
+    independent) and the per-Gaussian gradients equal up to the order of the cross-view sums."""
+    from dgs_b200 import raster
+    from dgs_b200._lib import DgsError
+    from dgs_b200.renderer import Renderer
+    B, V, P, W, H = 2, 5, 1200, 64, 48
+    raw, c2w, fx = _batch_inputs(B, V, P, W, H)
+    names = ("xyz", "features", "scaling", "rotation", "opacity")
+    dimg = T(np.random.default_rng(5).normal(0, 1, (B, V, 3, H, W)).astype(np.float32))
+
+    class Cfg:
+        gaussians_sh_degree = 0
+        use_gssplat = False
+
+    def run():
+        g = [T(raw[k]).requires_grad_() for k in names]
+        img = Renderer(Cfg())(*g, H, W, T(c2w), T(fx))
+        img.backward(dimg)
+        return img.detach(), [t.grad for t in g]
+    img1, grads1 = run()
+    real = raster._render_batch_forward_one
+    calls = []
+
+    def overflowing(xyz, features, scaling, rotation, opacity, Hh, Ww, C2W, fxf, *a, **k):
+        calls.append(C2W.shape[1])
+        if C2W.shape[1] > 2:
+            raise DgsError("libdgs_b200 status 4: instance count 3000000000 exceeds 2^31-1 (render the views in smaller batches)")
+        return real(xyz, features, scaling, rotation, opacity, Hh, Ww, C2W, fxf, *a, **k)
+    monkeypatch.setattr(raster, "_render_batch_forward_one", overflowing)
+    img2, grads2 = run()
+    assert calls == [5, 2, 3, 1, 2]
+    assert torch.equal(img1, img2)
+    for k, a, b in zip(names, grads1, grads2):
+        e = rel_l2(b.cpu().numpy(), a.cpu().numpy())
+        print(f"  chunked d{k}: rel_l2={e:.3e}")
+        assert e < 1e-5, k
+
+
 def test_full_size_properties_obj256():
     """BASELINE configs[1] shape: P = 2 + 4*256*256 init-like Gaussians, 4 views at 256x256.
     Size-independent properties: partition of unity, (tile, depth) sortedness with stable ties,
