@@ -302,20 +302,42 @@ __global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const float* __restric
 }
 
 // colsum[c] += sum_m in[m, c]  (bias gradient of a linear whose output gradient `in` is [M, C] bf16)
+// A CTA owns 256 columns x COLSUM_ROWS rows: every lane reads 8 consecutive columns with ONE 16-byte load (512 contiguous
+// bytes per warp and row; the first version read 2 bytes per thread = 64 bytes per warp instruction and ran at 30 % of the
+// HBM bandwidth: 61 us for the [16392, 3072] qkv gradient), the 8 warps take rows r0 + warp, r0 + warp + 8, ...
+constexpr int COLSUM_ROWS = 512;
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ in, int M, int C,
                                                      float* __restrict__ colsum) {
-  __shared__ float red[4 * 64];
+  __shared__ float red[8][256];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: launched via launch_pdl
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63), rq = threadIdx.x >> 6;
-  const int r0 = blockIdx.y * 256, r_end = min(M, r0 + 256);
-  float a = 0.f;
-#pragma unroll 8
-  for (int r = r0 + rq; r < r_end; r += 4) a += __bfloat162float(in[(size_t)r * C + c]);
-  red[rq * 64 + (threadIdx.x & 63)] = a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * COLSUM_ROWS, r_end = min(M, r0 + COLSUM_ROWS);
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < C) {  // C % 64 == 0 and 8 columns per lane: a lane is either fully inside or fully outside
+#pragma unroll 4
+    for (int r = r0 + warp; r < r_end; r += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(in + (size_t)r * C + c0);
+      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float2 f = __bfloat1622float2(p[i]);
+        a[2 * i] += f.x;
+        a[2 * i + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) red[warp][lane * 8 + i] = a[i];
   __syncthreads();
-  if (threadIdx.x < 64) atomicAdd(colsum + blockIdx.x * 64 + threadIdx.x, red[threadIdx.x] + red[64 + threadIdx.x] +
-                                                                               red[128 + threadIdx.x] + red[192 + threadIdx.x]);
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += red[w][threadIdx.x];
+    atomicAdd(colsum + c, t);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -559,7 +581,8 @@ int gate_bwd(const float* dx, const __nv_bfloat16* y, const float* gate, int gat
 
 int colsum_bf16(const __nv_bfloat16* in, int M, int C, float* colsum, cudaStream_t st) {
   DGS_REQUIRE(C % 64 == 0, "colsum: need C %% 64 == 0");
-  DGS_CUDA_OK(launch_pdl(colsum_kernel, dim3(C / 64, ceil_div(M, 256)), dim3(256), 0, st, in, M, C, colsum));
+  DGS_REQUIRE(((uintptr_t)in % 16) == 0, "colsum: input must be 16-byte aligned");
+  DGS_CUDA_OK(launch_pdl(colsum_kernel, dim3(ceil_div(C, 256), ceil_div(M, COLSUM_ROWS)), dim3(256), 0, st, in, M, C, colsum));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }
