@@ -1,7 +1,8 @@
 // gemm3_sm100.cu -- 256 x 256 tile, single CTA: the operand-traffic variant of the DiT GEMM.
 //
-// The 128 x 256 kernel (gemm_sm100.cu) is bound by L2 -> SM operand delivery: 48 KB of A/B per 128x256x64 MAC block
-// (43 MAC/B) runs at ~10 TB/s aggregate, 84 % of the ~6300 B/clk L2 fabric limit, i.e. ~55 % of the tensor peak.
+// EXPERIMENT, opt-in (DGS_GEMM_M256=1), slower than both gemm_sm100.cu and the default CTA-pair kernel gemm2_sm100.cu.
+// Premise at the time: the 128 x 256 kernel moves 48 KB of A/B per 128x256x64 MAC block (43 MAC/B) and looked bound by
+// operand delivery.  (The CTA-pair kernel later showed what the single-CTA mainloop really loses: see DESIGN.md section 4.)
 // Here one CTA computes TWO 128-row halves against the SAME 256-column B block: 64 KB per 256x256x64 block = 64 MAC/B,
 // 1.5x less traffic per FLOP.  Each k-step issues two tcgen05.mma (top / bottom half) that share the B descriptor.
 // The two 128 x 256 fp32 accumulators fill all 512 TMEM columns, so the accumulator is NOT double-buffered; to keep the
