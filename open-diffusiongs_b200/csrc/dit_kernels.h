@@ -41,6 +41,8 @@ int gemm_bf16_m256(const void* A, const void* W, int M, int N, int K, int epi, c
 // lse2 (optional, training): [B, H, attention_lse_stride(N)] fp32, log2-domain log-sum-exp of the scaled scores
 int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st);
 inline int attention_lse_stride(int N) { return (N + 127) / 128 * 128; }
+// experiment (attention2_sm100.cu, DGS_ATT_TPR2=1): same contract, two softmax threads per query row
+int attention_fwd_tpr2(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st);
 // backward (attention_bwd_sm100.cu): dqkv [B, N, 3, H, 64] (bf16) from qkv, out (= O), lse2 and dout [B, N, H*64] (bf16);
 // dsum = scratch [B, H, attention_lse_stride(N)] fp32.  Fills the pad entries of lse2 (+inf) as a side effect.
 int attention_bwd(const void* qkv, const void* out, const void* dout, float* lse2, float* dsum, void* dqkv, int B, int N,
