@@ -34,8 +34,7 @@ using namespace ptx;
 constexpr int ATT_BM = 128, ATT_BN = 64, ATT_HD = 64, ATT_KV_STAGES = 4, ATT_THREADS = 192;
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_HD * 2;    // [128 x 64] bf16 (Q, and one P buffer: 128 rows x 64 keys)
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_HD * 2;   // [64 x 64] bf16 (one K or V block)
-constexpr int ATT_ONES_BYTES = 64 * 128;           // all-ones bf16 block: read as [16 x 64] K-major (B operand of the row-sum MMA)
-                                                    // or, FUSE_L, as one MN-major [64 keys x 64 cols] swizzle atom behind the V tile
+constexpr int ATT_ONES_BYTES = 16 * 128;           // [16 x 64] bf16 ones, K-major (B operand of the row-sum MMA)
 constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES + 2 * ATT_KV_STAGES * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;
 constexpr uint32_t TMEM_S = 0, TMEM_O = 2 * ATT_BN, TMEM_L = TMEM_O + ATT_HD, ATT_TMEM_COLS = 256;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;
@@ -52,11 +51,7 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 
 // POLY_OF_8: how many of every 8 exponentials are evaluated by a degree-3 polynomial on the FMA/ALU pipes instead of
 // the MUFU pipe (which is the busiest unit of this kernel: XU 58 %, 27 % of the stall samples on MUFU.EX2)
-// FUSE_L (experiment, DGS_ATT_FUSEL=1): the row sums come out of the P V MMA itself.  V is an MN-major B operand whose N
-// extent is cut into 64-column swizzle atoms LBO bytes apart; with N = 80 the MMA reads a second atom, and the descriptor's
-// LBO is set so that this atom is the all-ones block: D = [O | L] in one instruction (TMEM_L = TMEM_O + 64), 8 instead of
-// 12 tensor-core instructions per key block (ncu: the TC pipe is as busy as the MUFU pipe, 62 %).
-template <int POLY_OF_8, bool FUSE_L = false>
+template <int POLY_OF_8>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int Np, int N, int H) {
@@ -122,7 +117,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, false, false);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, FUSE_L ? ATT_HD + 16 : ATT_HD, false, true);   // P (K-major) x V (MN-major)
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_HD, false, true);   // P (K-major) x V (MN-major)
       constexpr uint32_t idesc_l = make_idesc_bf16(ATT_BM, 16, false, false);      // P (K-major) x ONES (K-major)
       const uint64_t odesc = make_smem_desc_sw128(smem_u32(sOnes), 16, 1024);
       const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
@@ -151,11 +146,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         for (int k = 0; k < ATT_BN / 16; k++) {
           // A = P from TMEM: 16 keys = 8 packed columns;  B = V: MN-major ([key][64 dims] rows of 128 bytes),
           // 16 keys = 2 groups of 8 rows = 2048 bytes
-          // (FUSE_L: the second 64-column atom of B = the ones block, i.e. LBO = its distance from this V tile)
-          const uint64_t vdesc = make_smem_desc_sw128(vbase + (uint32_t)(k * 2048), FUSE_L ? smem_u32(sOnes) - vbase : ATT_KV_BYTES, 1024);
-          umma_bf16_ts(d, p_tmem + (uint32_t)(k * 8), vdesc, idesc_pv, (j | k) ? 1u : 0u);  // O += P_j V_j  (FUSE_L: [O | L])
-          if (!FUSE_L)
-            umma_bf16_ts(tmem_base + TMEM_L, p_tmem + (uint32_t)(k * 8), odesc + (uint64_t)(2 * k), idesc_l, (j | k) ? 1u : 0u);
+          const uint64_t vdesc = make_smem_desc_sw128(vbase + (uint32_t)(k * 2048), ATT_KV_BYTES, 1024);
+          umma_bf16_ts(d, p_tmem + (uint32_t)(k * 8), vdesc, idesc_pv, (j | k) ? 1u : 0u);  // O += P_j V_j
+          umma_bf16_ts(tmem_base + TMEM_L, p_tmem + (uint32_t)(k * 8), odesc + (uint64_t)(2 * k), idesc_l, (j | k) ? 1u : 0u);
         }
         umma_commit(pv_full + (j & 1));
         umma_commit(kv_empty + s);
@@ -293,7 +286,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
 int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st) {
   DGS_REQUIRE(B > 0 && N > 0 && H > 0, "attention: bad shape B=%d N=%d H=%d", B, N, H);
-  static int tpr2 = -1;  // experiment: two softmax threads per row (attention2_sm100.cu)
+  static int tpr2 = -1;  // experiment: two softmax threads per row (attention2_sm100.cu), measured slower
   if (tpr2 < 0) {
     const char* e = getenv("DGS_ATT_TPR2");
     tpr2 = (e && e[0] == '1') ? 1 : 0;
@@ -309,7 +302,7 @@ int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, 
   if (rc) return rc;
   rc = make_tmap_bf16(&tm_kv, qkv, 3, dims, str, box_kv);
   if (rc) return rc;
-  static int poly = -1, fusel = 0;
+  static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("DGS_ATT_POLY");
     poly = e ? atoi(e) : ATT_POLY_DEFAULT;
@@ -317,14 +310,11 @@ int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, 
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    const char* ef = getenv("DGS_ATT_FUSEL");
-    fusel = (ef && ef[0] == '1') ? 1 : 0;
   }
   dim3 grid(ceil_div(N, ATT_BM), H, B);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  auto kern = fusel ? attention_fwd_kernel<0, true> : poly == 1 ? attention_fwd_kernel<1> : poly == 2 ? attention_fwd_kernel<2>
-                    : poly >= 3 ? attention_fwd_kernel<3> : attention_fwd_kernel<0>;
+  auto kern = poly == 1 ? attention_fwd_kernel<1> : poly == 2 ? attention_fwd_kernel<2> : poly >= 3 ? attention_fwd_kernel<3>
+                                                                                                   : attention_fwd_kernel<0>;
   DGS_CUDA_OK(launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tm_q, tm_kv, o, lse2, Np, N, H));
   DGS_POST_LAUNCH();
   return DGS_OK;
