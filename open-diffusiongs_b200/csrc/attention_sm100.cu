@@ -31,6 +31,24 @@ namespace dgs {
 
 using namespace ptx;
 
+// Timeline probe (scripts/att_probe.cu defines DGS_ATT_PROBE and includes this file): every role accumulates the cycles it
+// spends waiting on each barrier; with the macro undefined (the product build) these lines do not exist.
+#ifdef DGS_ATT_PROBE
+__device__ unsigned long long* g_att_dbg = nullptr;  // [CTAs][16]
+#define ATT_PROBE_DECL(n) unsigned long long probe_acc[n] = {}
+#define ATT_PROBE_T0() const long long probe_t0 = clock64()
+#define ATT_PROBE_ACC(i) probe_acc[i] += (unsigned long long)(clock64() - probe_t0)
+#define ATT_PROBE_OUT(slot, i)                                                                                     \
+  do {                                                                                                             \
+    if (g_att_dbg) g_att_dbg[(size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = probe_acc[i]; \
+  } while (0)
+#else
+#define ATT_PROBE_DECL(n)
+#define ATT_PROBE_T0()
+#define ATT_PROBE_ACC(i)
+#define ATT_PROBE_OUT(slot, i)
+#endif
+
 constexpr int ATT_BM = 128, ATT_BN = 64, ATT_HD = 64, ATT_KV_STAGES = 4, ATT_THREADS = 192;
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_HD * 2;    // [128 x 64] bf16 (Q, and one P buffer: 128 rows x 64 keys)
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_HD * 2;   // [64 x 64] bf16 (one K or V block)
@@ -101,17 +119,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      ATT_PROBE_DECL(1);
       mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
       tma_load_3d(sQ, &tm_q, q_full, h * ATT_HD, q0, b);
       for (int j = 0; j < n_blocks; j++) {
         const int s = j % ATT_KV_STAGES;
         const uint32_t use = (uint32_t)(j / ATT_KV_STAGES);
-        mbar_wait(kv_empty + s, (use & 1) ^ 1);
+        {
+          ATT_PROBE_T0();
+          mbar_wait(kv_empty + s, (use & 1) ^ 1);
+          ATT_PROBE_ACC(0);
+        }
         mbar_arrive_expect_tx(k_full + s, ATT_KV_BYTES);
         tma_load_3d(sK + s * ATT_KV_BYTES, &tm_kv, k_full + s, D + h * ATT_HD, j * ATT_BN, b);
         mbar_arrive_expect_tx(v_full + s, ATT_KV_BYTES);
         tma_load_3d(sV + s * ATT_KV_BYTES, &tm_kv, v_full + s, 2 * D + h * ATT_HD, j * ATT_BN, b);
       }
+      ATT_PROBE_OUT(0, 0);  // producer: cycles waiting for a free K/V stage
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
@@ -121,9 +145,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       constexpr uint32_t idesc_l = make_idesc_bf16(ATT_BM, 16, false, false);      // P (K-major) x ONES (K-major)
       const uint64_t odesc = make_smem_desc_sw128(smem_u32(sOnes), 16, 1024);
       const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      ATT_PROBE_DECL(4);
       auto issue_s = [&](int j) {
         const int s = j % ATT_KV_STAGES;
-        mbar_wait(k_full + s, (uint32_t)(j / ATT_KV_STAGES) & 1);
+        {
+          ATT_PROBE_T0();
+          mbar_wait(k_full + s, (uint32_t)(j / ATT_KV_STAGES) & 1);
+          ATT_PROBE_ACC(0);
+        }
         tc_fence_after();
         const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s * ATT_KV_BYTES), 16, 1024);
         const uint32_t d = tmem_base + TMEM_S + (uint32_t)((j & 1) * ATT_BN);
@@ -136,8 +165,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       for (int j = 0; j < n_blocks; j++) {
         if (j + 1 < n_blocks) issue_s(j + 1);
         const int s = j % ATT_KV_STAGES;
-        mbar_wait(p_full + (j & 1), (uint32_t)(j >> 1) & 1);
-        mbar_wait(v_full + s, (uint32_t)(j / ATT_KV_STAGES) & 1);
+        {
+          ATT_PROBE_T0();
+          mbar_wait(p_full + (j & 1), (uint32_t)(j >> 1) & 1);
+          ATT_PROBE_ACC(1);
+        }
+        {
+          ATT_PROBE_T0();
+          mbar_wait(v_full + s, (uint32_t)(j / ATT_KV_STAGES) & 1);
+          ATT_PROBE_ACC(2);
+        }
         tc_fence_after();
         const uint32_t p_tmem = tmem_base + TMEM_S + (uint32_t)((j & 1) * ATT_BN);  // P_j: packed bf16 over S_j
         const uint32_t vbase = smem_u32(sV + s * ATT_KV_BYTES);
@@ -153,6 +190,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         umma_commit(pv_full + (j & 1));
         umma_commit(kv_empty + s);
       }
+      ATT_PROBE_OUT(1, 0);  // MMA issuer: waiting for K
+      ATT_PROBE_OUT(2, 1);  //             waiting for P (the softmax of the block)
+      ATT_PROBE_OUT(3, 2);  //             waiting for V
     }
   } else {
     // ===================== softmax / output (warps 2..5): one query row per thread =====================
@@ -162,17 +202,29 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     const uint32_t t_o = t_lane + TMEM_O, t_l = t_lane + TMEM_L;
     float m_run = -INFINITY;
+    ATT_PROBE_DECL(5);
+#ifdef DGS_ATT_PROBE
+    const long long probe_begin = clock64();
+#endif
 
     for (int j = 0; j < n_blocks; j++) {
       const int buf = j & 1;
-      mbar_wait(s_full + buf, (uint32_t)(j >> 1) & 1);
+      {
+        ATT_PROBE_T0();
+        mbar_wait(s_full + buf, (uint32_t)(j >> 1) & 1);
+        ATT_PROBE_ACC(0);
+      }
       tc_fence_after();
       const uint32_t t_s = t_lane + TMEM_S + (uint32_t)(buf * ATT_BN);
       const int kv_valid = N - j * ATT_BN;  // >= 1; < ATT_BN only in the last block
       uint32_t r0[32], r1[32];
-      tmem_ld_32x32(t_s, r0);
-      tmem_ld_32x32(t_s + 32u, r1);
-      tmem_ld_wait();
+      {
+        ATT_PROBE_T0();
+        tmem_ld_32x32(t_s, r0);
+        tmem_ld_32x32(t_s + 32u, r1);
+        tmem_ld_wait();
+        ATT_PROBE_ACC(1);
+      }
       if (kv_valid < ATT_BN) {  // warp-uniform: mask the zero-filled tail keys
 #pragma unroll
         for (int i = 0; i < 32; i++) {
@@ -198,7 +250,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       // through s_full -- was written after P V(j-2) had read P_{j-2} from the same columns: nothing to wait for.)
       // For a rescale O must hold every earlier block:
       if (j >= 1 && __any_sync(0xffffffffu, grow)) {
+        ATT_PROBE_T0();
         mbar_wait(pv_full + (buf ^ 1), (uint32_t)((j - 1) >> 1) & 1);
+        ATT_PROBE_ACC(2);
         tc_fence_after();
         uint32_t q0r[32], q1r[32];
         tmem_ld_32x32(t_o, q0r);
@@ -235,11 +289,25 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const float p1 = (((2 * i + 1) & 7) < POLY_OF_8) ? ex2_poly3(x1) : ex2_approx(x1);
         pk[16 + i] = pack2_bf16(p0, p1);
       }
-      tmem_st_32x32(t_s, pk);
-      tmem_st_wait();
+      {
+        ATT_PROBE_T0();
+        tmem_st_32x32(t_s, pk);
+        tmem_st_wait();
+        ATT_PROBE_ACC(3);
+      }
       tc_fence_before();  // our tcgen05.ld of S_j / O and the store of P_j are complete before the issuer proceeds
       mbar_arrive(p_full + buf);
     }
+#ifdef DGS_ATT_PROBE
+    probe_acc[4] = (unsigned long long)(clock64() - probe_begin);
+    if (threadIdx.x == 64) {
+      ATT_PROBE_OUT(4, 0);  // softmax thread (warp 2, lane 0): waiting for S
+      ATT_PROBE_OUT(5, 1);  //   TMEM load of S (issue -> wait::ld)
+      ATT_PROBE_OUT(6, 2);  //   waiting for the previous P V before a rescale
+      ATT_PROBE_OUT(7, 3);  //   TMEM store of P (issue -> wait::st)
+      ATT_PROBE_OUT(8, 4);  //   whole key-block loop
+    }
+#endif
     {  // all blocks accumulated -> normalise and store
       const int last = n_blocks - 1;
       mbar_wait(pv_full + (last & 1), (uint32_t)(last >> 1) & 1);
