@@ -145,7 +145,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       constexpr uint32_t idesc_l = make_idesc_bf16(ATT_BM, 16, false, false);      // P (K-major) x ONES (K-major)
       const uint64_t odesc = make_smem_desc_sw128(smem_u32(sOnes), 16, 1024);
       const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-      ATT_PROBE_DECL(4);
+      ATT_PROBE_DECL(6);
+#ifdef DGS_ATT_PROBE
+      const long long probe_mma_begin = clock64();
+#endif
       auto issue_s = [&](int j) {
         const int s = j % ATT_KV_STAGES;
         {
@@ -156,9 +159,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tc_fence_after();
         const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s * ATT_KV_BYTES), 16, 1024);
         const uint32_t d = tmem_base + TMEM_S + (uint32_t)((j & 1) * ATT_BN);
+        ATT_PROBE_T0();
 #pragma unroll
         for (int k = 0; k < ATT_HD / 16; k++) umma_bf16(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
         umma_commit(s_full + (j & 1));
+        ATT_PROBE_ACC(3);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -179,6 +184,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t p_tmem = tmem_base + TMEM_S + (uint32_t)((j & 1) * ATT_BN);  // P_j: packed bf16 over S_j
         const uint32_t vbase = smem_u32(sV + s * ATT_KV_BYTES);
         const uint32_t d = tmem_base + TMEM_O;
+        ATT_PROBE_T0();
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; k++) {
           // A = P from TMEM: 16 keys = 8 packed columns;  B = V: MN-major ([key][64 dims] rows of 128 bytes),
@@ -189,7 +195,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
         umma_commit(pv_full + (j & 1));
         umma_commit(kv_empty + s);
+        ATT_PROBE_ACC(4);
       }
+#ifdef DGS_ATT_PROBE
+      probe_acc[5] = (unsigned long long)(clock64() - probe_mma_begin);
+#endif
+      ATT_PROBE_OUT(9, 5);   //             whole loop
+      ATT_PROBE_OUT(10, 3);  //             issuing the 4 S MMAs + commit
+      ATT_PROBE_OUT(11, 4);  //             issuing the 8 P V / row-sum MMAs + 2 commits
       ATT_PROBE_OUT(1, 0);  // MMA issuer: waiting for K
       ATT_PROBE_OUT(2, 1);  //             waiting for P (the softmax of the block)
       ATT_PROBE_OUT(3, 2);  //             waiting for V

@@ -68,7 +68,8 @@ int main(int argc, char** argv) {
          N, H, B, best * 1e3, 4.0 * N * N * D * B / best / 1e9, ctas, nb);
   printf("  softmax thread  loop total %.0f (%.0f per block)   wait S %.0f   TMEM ld S %.0f   wait prev PV (rescale) %.0f   TMEM st P %.0f   => math+other %.0f\n",
          s[8], s[8] / nb, s[4], s[5], s[6], s[7], s[8] - s[4] - s[5] - s[6] - s[7]);
-  printf("  MMA issuer      wait K %.0f   wait P %.0f   wait V %.0f\n", s[1], s[2], s[3]);
+  printf("  MMA issuer      loop total %.0f   wait K %.0f   wait P %.0f   wait V %.0f   issuing S (4 MMA + commit) %.0f (%.0f per block)   issuing PV+L (8 MMA + 2 commits) %.0f (%.0f per block)\n",
+         s[9], s[1], s[2], s[3], s[10], s[10] / nb, s[11], s[11] / nb);
   printf("  TMA producer    wait free K/V stage %.0f\n", s[0]);
   return 0;
 }
