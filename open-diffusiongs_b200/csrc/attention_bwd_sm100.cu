@@ -86,6 +86,8 @@ constexpr int DQ_STAGES = 3;
 constexpr int DQ_SMEM = 2 * AB_T128 /*Q, dO*/ + 2 * DQ_STAGES * AB_T64 /*K, V*/ + 1024 + 256;
 constexpr uint32_t DQ_TM_S = 0 /* 2 buffers x 64 */, DQ_TM_DP = 128, DQ_TM_DQ = 192, DQ_TMEM_COLS = 256;
 
+// UNI (experiment, DGS_ATT_UNI=1): MMA issue by the converged warp under elect.sync (see attention_sm100.cu / sm100_ptx.cuh)
+template <bool UNI>
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_kv64,
                    const __grid_constant__ CUtensorMap tm_do128, const float* __restrict__ lse2,
@@ -147,7 +149,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (UNI || lane == 0) {
       constexpr uint32_t idesc_kk = make_idesc_bf16(128, 64, false, false);  // A K-major x B K-major
       constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 64, false, true);  // A K-major x B MN-major
       const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
@@ -160,16 +162,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
         tc_fence_after();
         const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s * AB_T64), 16, 1024);
         const uint32_t d = tmem_base + DQ_TM_S + (uint32_t)((j & 1) * 64);
+        if (!UNI || elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) umma_bf16(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
-        umma_commit(s_full + (j & 1));
+          for (int k = 0; k < 4; k++) umma_bf16(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+          umma_commit(s_full + (j & 1));
+        }
       };
       auto issue_dp = [&](int j) {  // kv_full(j) already observed by issue_s(j)
         const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + (j % DQ_STAGES) * AB_T64), 16, 1024);
+        if (!UNI || elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          umma_bf16(tmem_base + DQ_TM_DP, dodesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
-        umma_commit(dp_full);
+          for (int k = 0; k < 4; k++)
+            umma_bf16(tmem_base + DQ_TM_DP, dodesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+          umma_commit(dp_full);
+        }
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -181,6 +187,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
         mbar_wait(ds_full + (j & 1), (uint32_t)(j >> 1) & 1);
         tc_fence_after();
         const uint32_t kbase = smem_u32(sK + s * AB_T64);
+        if (!UNI || elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           // A = dS_j from TENSOR MEMORY: packed bf16 pairs written by the softmax threads over their own dP columns --
@@ -192,6 +199,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
         }
         umma_commit(dq_done + (j & 1));
         umma_commit(kv_empty + s);
+        }
         if (j + 1 < n_blocks) issue_dp(j + 1);  // dP(j) has been read (ds_full(j))
       }
     }
@@ -289,6 +297,7 @@ constexpr int DKV_SMEM = 2 * AB_T128 /*K, V*/ + 2 * DKV_STAGES * AB_T64 /*Q, dO*
                          2 * 128 * 4 /*lse2 | Dsum of a query block, x2*/ + 1024 + 256;
 constexpr uint32_t DKV_TM_ST = 0, DKV_TM_DPT = 64, DKV_TM_DV = 128, DKV_TM_DK = 192, DKV_TMEM_COLS = 256;
 
+template <bool UNI>
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_constant__ CUtensorMap tm_q64,
                     const __grid_constant__ CUtensorMap tm_do64, const float* __restrict__ lse2,
@@ -353,7 +362,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (UNI || lane == 0) {
       constexpr uint32_t idesc_kk = make_idesc_bf16(128, 64, false, false);
       constexpr uint32_t idesc_kmn = make_idesc_bf16(128, 64, false, true);
       const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
@@ -366,17 +375,21 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
         mbar_wait(q_full + s, (uint32_t)(i / DKV_STAGES) & 1);
         tc_fence_after();
         const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + s * AB_T64), 16, 1024);
+        if (!UNI || elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; k++)  // S^T = K Q_i^T : [128 keys x 64 queries]
-          umma_bf16(tmem_base + DKV_TM_ST, kdesc + (uint64_t)(2 * k), qdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
-        umma_commit(st_full);
+          for (int k = 0; k < 4; k++)  // S^T = K Q_i^T : [128 keys x 64 queries]
+            umma_bf16(tmem_base + DKV_TM_ST, kdesc + (uint64_t)(2 * k), qdesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+          umma_commit(st_full);
+        }
       };
       auto issue_dpt = [&](int i) {
         const uint64_t dodesc = make_smem_desc_sw128(smem_u32(sdO + (i % DKV_STAGES) * AB_T64), 16, 1024);
+        if (!UNI || elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < 4; k++)  // dP^T = V dO_i^T
-          umma_bf16(tmem_base + DKV_TM_DPT, vdesc + (uint64_t)(2 * k), dodesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
-        umma_commit(dpt_full);
+          for (int k = 0; k < 4; k++)  // dP^T = V dO_i^T
+            umma_bf16(tmem_base + DKV_TM_DPT, vdesc + (uint64_t)(2 * k), dodesc + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+          umma_commit(dpt_full);
+        }
       };
       mbar_wait(kv_full, 0);
       issue_st(0);
@@ -387,6 +400,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
         tc_fence_after();
         if (i + 1 < n_blocks) issue_st(i + 1);
         const uint32_t qbase = smem_u32(sQ + s * AB_T64), dobase = smem_u32(sdO + s * AB_T64);
+        if (!UNI || elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {  // reduction over the 64 queries of the block, 16 per instruction
           // P^T and dS^T come from TENSOR MEMORY: packed bf16 pairs written by the softmax threads over their own
@@ -400,6 +414,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
         }
         umma_commit(acc_done);
         umma_commit(q_empty + s);
+        }
         if (i + 1 < n_blocks) issue_dpt(i + 1);
       }
     }
@@ -536,20 +551,25 @@ int attention_bwd(const void* qkv, const void* out, const void* dout, float* lse
     if (rc) return rc;
   }
   static bool configured = false;
+  static int uni = 0;
   if (!configured) {
-    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
-    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    const char* eu = getenv("DGS_ATT_UNI");
+    uni = (eu && eu[0] == '1') ? 1 : 0;
     configured = true;
   }
   DGS_CUDA_OK(launch_pdl(attn_bwd_prep_kernel, dim3(Np, B), dim3(H * 16 < 32 ? 32 : H * 16), 0, st,
                          (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse2, dsum, N, Np, H));
   DGS_POST_LAUNCH();
   dim3 grid(ceil_div(N, 128), H, B);
-  DGS_CUDA_OK(launch_pdl(attn_bwd_dq_kernel, grid, dim3(AB_THREADS), DQ_SMEM, st, tm_qkv128, tm_qkv64, tm_do128,
-                         (const float*)lse2, (const float*)dsum, (__nv_bfloat16*)dqkv, N, Np, H));
+  DGS_CUDA_OK(launch_pdl(uni ? attn_bwd_dq_kernel<true> : attn_bwd_dq_kernel<false>, grid, dim3(AB_THREADS), DQ_SMEM, st, tm_qkv128,
+                         tm_qkv64, tm_do128, (const float*)lse2, (const float*)dsum, (__nv_bfloat16*)dqkv, N, Np, H));
   DGS_POST_LAUNCH();
-  DGS_CUDA_OK(launch_pdl(attn_bwd_dkv_kernel, grid, dim3(AB_THREADS), DKV_SMEM, st, tm_qkv128, tm_qkv64, tm_do64,
-                         (const float*)lse2, (const float*)dsum, (__nv_bfloat16*)dqkv, N, Np, H));
+  DGS_CUDA_OK(launch_pdl(uni ? attn_bwd_dkv_kernel<true> : attn_bwd_dkv_kernel<false>, grid, dim3(AB_THREADS), DKV_SMEM, st,
+                         tm_qkv128, tm_qkv64, tm_do64, (const float*)lse2, (const float*)dsum, (__nv_bfloat16*)dqkv, N, Np, H));
   DGS_POST_LAUNCH();
   return DGS_OK;
 }

@@ -69,7 +69,10 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 
 // POLY_OF_8: how many of every 8 exponentials are evaluated by a degree-3 polynomial on the FMA/ALU pipes instead of
 // the MUFU pipe (which is the busiest unit of this kernel: XU 58 %, 27 % of the stall samples on MUFU.EX2)
-template <int POLY_OF_8>
+// UNI (experiment, DGS_ATT_UNI=1): the MMA-issuing warp runs fully converged and issues under elect.sync instead of
+// `lane == 0` (see elect_one_sync in sm100_ptx.cuh): the probe has this thread as the pacing role (~1140 clk per key block
+// for 12 small MMAs + 3 commits).
+template <int POLY_OF_8, bool UNI = false>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse2, int Np, int N, int H) {
@@ -138,8 +141,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       ATT_PROBE_OUT(0, 0);  // producer: cycles waiting for a free K/V stage
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (one thread; UNI: the converged warp, instructions under elect.sync) ============
+    if (UNI || lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, false, false);   // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_HD, false, true);   // P (K-major) x V (MN-major)
       constexpr uint32_t idesc_l = make_idesc_bf16(ATT_BM, 16, false, false);      // P (K-major) x ONES (K-major)
@@ -160,9 +163,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + s * ATT_KV_BYTES), 16, 1024);
         const uint32_t d = tmem_base + TMEM_S + (uint32_t)((j & 1) * ATT_BN);
         ATT_PROBE_T0();
+        if (!UNI || elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < ATT_HD / 16; k++) umma_bf16(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
-        umma_commit(s_full + (j & 1));
+          for (int k = 0; k < ATT_HD / 16; k++) umma_bf16(d, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
+          umma_commit(s_full + (j & 1));
+        }
         ATT_PROBE_ACC(3);
       };
       mbar_wait(q_full, 0);
@@ -185,16 +190,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t vbase = smem_u32(sV + s * ATT_KV_BYTES);
         const uint32_t d = tmem_base + TMEM_O;
         ATT_PROBE_T0();
+        if (!UNI || elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < ATT_BN / 16; k++) {
-          // A = P from TMEM: 16 keys = 8 packed columns;  B = V: MN-major ([key][64 dims] rows of 128 bytes),
-          // 16 keys = 2 groups of 8 rows = 2048 bytes
-          const uint64_t vdesc = make_smem_desc_sw128(vbase + (uint32_t)(k * 2048), ATT_KV_BYTES, 1024);
-          umma_bf16_ts(d, p_tmem + (uint32_t)(k * 8), vdesc, idesc_pv, (j | k) ? 1u : 0u);  // O += P_j V_j
-          umma_bf16_ts(tmem_base + TMEM_L, p_tmem + (uint32_t)(k * 8), odesc + (uint64_t)(2 * k), idesc_l, (j | k) ? 1u : 0u);
+          for (int k = 0; k < ATT_BN / 16; k++) {
+            // A = P from TMEM: 16 keys = 8 packed columns;  B = V: MN-major ([key][64 dims] rows of 128 bytes),
+            // 16 keys = 2 groups of 8 rows = 2048 bytes
+            const uint64_t vdesc = make_smem_desc_sw128(vbase + (uint32_t)(k * 2048), ATT_KV_BYTES, 1024);
+            umma_bf16_ts(d, p_tmem + (uint32_t)(k * 8), vdesc, idesc_pv, (j | k) ? 1u : 0u);  // O += P_j V_j
+            umma_bf16_ts(tmem_base + TMEM_L, p_tmem + (uint32_t)(k * 8), odesc + (uint64_t)(2 * k), idesc_l, (j | k) ? 1u : 0u);
+          }
+          umma_commit(pv_full + (j & 1));
+          umma_commit(kv_empty + s);
         }
-        umma_commit(pv_full + (j & 1));
-        umma_commit(kv_empty + s);
         ATT_PROBE_ACC(4);
       }
 #ifdef DGS_ATT_PROBE
@@ -383,7 +390,7 @@ int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, 
   if (rc) return rc;
   rc = make_tmap_bf16(&tm_kv, qkv, 3, dims, str, box_kv);
   if (rc) return rc;
-  static int poly = -1;
+  static int poly = -1, uni = 0;
   if (poly < 0) {
     const char* e = getenv("DGS_ATT_POLY");
     poly = e ? atoi(e) : ATT_POLY_DEFAULT;
@@ -391,11 +398,14 @@ int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, 
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    const char* eu = getenv("DGS_ATT_UNI");
+    uni = (eu && eu[0] == '1') ? 1 : 0;
   }
   dim3 grid(ceil_div(N, ATT_BM), H, B);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  auto kern = poly == 1 ? attention_fwd_kernel<1> : poly == 2 ? attention_fwd_kernel<2> : poly >= 3 ? attention_fwd_kernel<3>
-                                                                                                   : attention_fwd_kernel<0>;
+  auto kern = uni ? attention_fwd_kernel<0, true> : poly == 1 ? attention_fwd_kernel<1> : poly == 2 ? attention_fwd_kernel<2>
+                  : poly >= 3 ? attention_fwd_kernel<3> : attention_fwd_kernel<0>;
   DGS_CUDA_OK(launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tm_q, tm_kv, o, lse2, Np, N, H));
   DGS_POST_LAUNCH();
   return DGS_OK;

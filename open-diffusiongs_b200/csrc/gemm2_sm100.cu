@@ -102,7 +102,10 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 // splits > 1 (split-K, fp32 TMA reduce-add epilogue only): work unit u = (tile u % num_tiles, K range u / num_tiles);
 // every unit adds its partial product into the (pre-zeroed) output.  Used by the weight-gradient GEMMs, whose K = tokens is
 // long and whose 256 x 256 output tiles are too few to fill 74 clusters (proj: 16 tiles).
-template <int EPI, bool MN, int TMAEPI>
+// UNI (experiment, DGS_GEMM_UNI=1): the TMA-producer and MMA-issuer warps run converged and issue under elect.sync instead of
+// `lane == 0` (elect_one_sync in sm100_ptx.cuh): without it ptxas wraps every TMA / tcgen05 instruction of those roles in an
+// ELECT / BRA.U.ANY serialisation loop with R2UR operand moves (99 such loops in this file's kernels).
+template <int EPI, bool MN, int TMAEPI, bool UNI = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX, GemmEpilogue ep,
@@ -151,7 +154,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer (one per CTA) =====================
-    if (lane == 0) {
+    if (UNI || lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
@@ -161,17 +164,19 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           const uint32_t leader_full = mapa(smem_u32(full_bar + stage), 0);
-          if (leader) mbar_arrive_expect_tx(full_bar + stage, 2 * STAGE_BYTES);
-          if (!MN) {
-            tma_load_2d_2sm(sA + stage * A_BYTES, &tmA, leader_full, kb * BK, m0);
-            tma_load_2d_2sm(sB + stage * B_BYTES, &tmB, leader_full, kb * BK, n0);
-          } else {
+          if (!UNI || elect_one_sync()) {
+            if (leader) mbar_arrive_expect_tx(full_bar + stage, 2 * STAGE_BYTES);
+            if (!MN) {
+              tma_load_2d_2sm(sA + stage * A_BYTES, &tmA, leader_full, kb * BK, m0);
+              tma_load_2d_2sm(sB + stage * B_BYTES, &tmB, leader_full, kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int a = 0; a < BM_CTA / 64; a++)
-              tma_load_2d_2sm(sA + stage * A_BYTES + a * 8192, &tmA, leader_full, m0 + a * 64, kb * BK);
+              for (int a = 0; a < BM_CTA / 64; a++)
+                tma_load_2d_2sm(sA + stage * A_BYTES + a * 8192, &tmA, leader_full, m0 + a * 64, kb * BK);
 #pragma unroll
-            for (int a = 0; a < BN_CTA / 64; a++)
-              tma_load_2d_2sm(sB + stage * B_BYTES + a * 8192, &tmB, leader_full, n0 + a * 64, kb * BK);
+              for (int a = 0; a < BN_CTA / 64; a++)
+                tma_load_2d_2sm(sB + stage * B_BYTES + a * 8192, &tmB, leader_full, n0 + a * 64, kb * BK);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -179,7 +184,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: one thread of the LEADER CTA =====================
-    if (leader && lane == 0) {
+    if (leader && (UNI || lane == 0)) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM_CTA, BN, MN, MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -195,15 +200,17 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tc_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * A_BYTES), MN ? 8192 : 16, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * B_BYTES), MN ? 8192 : 16, 1024);
+          if (!UNI || elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; k++) {
-            const uint64_t adv = MN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);  // 16 K rows = 2048 B  |  16 bf16 = 32 B
-            umma_bf16_2sm(d_tmem, adesc + adv, bdesc + adv, idesc, (kb > kb0 || k) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; k++) {
+              const uint64_t adv = MN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);  // 16 K rows = 2048 B  |  16 bf16 = 32 B
+              umma_bf16_2sm(d_tmem, adesc + adv, bdesc + adv, idesc, (kb > kb0 || k) ? 1u : 0u);
+            }
+            umma_commit_2sm(empty_bar + stage);
           }
-          umma_commit_2sm(empty_bar + stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(tfull_bar + acc);
+        if (!UNI || elect_one_sync()) umma_commit_2sm(tfull_bar + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -254,13 +261,17 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 template <int EPI, bool MN = false, int TMAEPI = 0>
 static int launch_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmEpilogue& ep, int M,
                        int N, int K, int num_sms, cudaStream_t st, const CUtensorMap* tmX = nullptr, int splits = 1) {
-  auto kern = g2::gemm_bf16_2cta_kernel<EPI, MN, TMAEPI>;
   constexpr int SMEM = g2::Cfg2<TMAEPI>::SMEM_BYTES;
   static bool configured = false;
+  static int uni = 0;
   if (!configured) {
-    DGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    DGS_CUDA_OK(cudaFuncSetAttribute(g2::gemm_bf16_2cta_kernel<EPI, MN, TMAEPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    DGS_CUDA_OK(cudaFuncSetAttribute(g2::gemm_bf16_2cta_kernel<EPI, MN, TMAEPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const char* eu = getenv("DGS_GEMM_UNI");
+    uni = (eu && eu[0] == '1') ? 1 : 0;
     configured = true;
   }
+  auto kern = uni ? g2::gemm_bf16_2cta_kernel<EPI, MN, TMAEPI, true> : g2::gemm_bf16_2cta_kernel<EPI, MN, TMAEPI, false>;
   const int tiles = ceil_div(M, 2 * g2::BM_CTA) * ceil_div(N, g2::BN) * splits;
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;

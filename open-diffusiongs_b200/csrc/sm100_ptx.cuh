@@ -102,6 +102,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a fully converged warp (elect.sync): code that issues tcgen05 / TMA instructions under THIS predicate stays
+// on the uniform datapath; under `lane == 0` ptxas cannot know that a single lane is active and wraps every such
+// instruction in an ELECT / BRA.U.ANY serialisation loop with R2UR operand moves (~23 loops in the attention kernel).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- tcgen05: MMA -------------------------------------------------------------------------------
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
