@@ -152,6 +152,29 @@ int dgs_render_batch_backward(const dgs_render_batch_args* args, long long R,
                               float* d_scaling, float* d_rotation, float* d_opacity,
                               dgs_alloc_fn scratch_alloc, void* scratch_user, void* stream);
 
+/* The same pair with the image-space MSE of the training loss fused in (LossComputer.forward's l2 term,
+ * diffusionGS/utils/losses.py:261-284: l2_loss[b] = mean over (v,3,h,w) of (rendering - target)^2, later averaged over b and
+ * weighted by lambda_diffusion, diffusion_gs_system.py:94-124).  Forward: the blend kernel adds sum (render - target)^2 of
+ * sample b into loss_sum[b] (caller-zeroed, fp64) while the pixel is in registers.  Backward: the blend-backward kernel forms
+ * dL/dpix = dL_dimages (may be NULL) + coef[b] * (render - target) itself, with coef[b] = dL/dl2_loss[b] * 2 / (V*3*H*W)
+ * computed by the caller on the device -- no per-element loss or gradient image exists.  mse == NULL: the plain pair. */
+typedef struct {
+  const float* target;   /* [B,V,target_channels,H,W] fp32 in (0,1)                                       */
+  int target_channels;   /* 3, or 4 = rgb + mask (the mask plane is skipped, losses.py:274-276)           */
+  double* loss_sum;      /* forward:  out [B]                                                              */
+  const float* coef;     /* backward: in  [B] (device)                                                     */
+  const float* images;   /* backward: in  the forward's out_images                                         */
+} dgs_render_mse;
+int dgs_render_batch_forward_mse(const dgs_render_batch_args* args, dgs_alloc_fn geom_alloc, void* geom_user,
+                                 dgs_alloc_fn binning_alloc, void* binning_user, dgs_alloc_fn image_alloc,
+                                 void* image_user, float* out_images, long long* num_rendered, long long* chunk_instances,
+                                 const dgs_render_mse* mse, void* stream);
+int dgs_render_batch_backward_mse(const dgs_render_batch_args* args, long long R, const long long* chunk_instances,
+                                  const void* geom_buffer, const void* binning_buffer, const void* binning_buffer_b,
+                                  const void* image_buffer, const float* dL_dimages, const dgs_render_mse* mse,
+                                  float* d_xyz, float* d_features, float* d_scaling, float* d_rotation, float* d_opacity,
+                                  dgs_alloc_fn scratch_alloc, void* scratch_user, void* stream);
+
 /* Introspection used by the parity tests: copies of per-(view, Gaussian) / per-pixel forward state
  * out of the opaque arenas into caller DEVICE buffers (any may be NULL):
  * xy [N,2], depth [N], conic_opacity [N,4], rgb [N,3], tiles_touched [N] (N = n_views*P),
@@ -197,7 +220,8 @@ typedef struct {
 typedef struct {
   int B, V, H, W;
   int plucker_mode;          /* 0 = 'relative_plk' (object model), 1 = 'plk' (scene model)            */
-  int scene_depth;           /* 0: depth=(2s-1)*1.8 + (-o.d) ; 1: depth=s*(far-near)+near             */
+  int scene_depth;           /* 0: depth=(2s-1)*1.8 + (-o.d) (object model, 'relative_plk'); 1: depth=s*(far-near)+near
+                                (scene model); 2: depth=s (object model with ray_pe_type 'plk', denoiser.py:381-388) */
   float range_near, range_far;
   const float* images;       /* [B,V,3,H,W] fp32 (view 0 clean, others noised)                        */
   const float* ray_o;        /* [B,V,3,H,W]                                                           */
@@ -210,12 +234,17 @@ typedef struct {
   float* opacity;            /* out [B,P,1]                                                           */
   float* img_aligned_xyz;    /* out [B,V,3,H,W] or NULL                                               */
   float* tokens_out;         /* optional debug out: final residual stream [B,N,width] fp32, or NULL   */
-  void* train_state;         /* NULL: inference.  Else a caller buffer of dgs_dit_train_state_bytes(): the forward
-                                keeps every activation the backward needs there (no recompute: 4 GB per sample at
-                                N=4098 -- the reference instead checkpoints each block, denoiser.py:348-354, and pays a
-                                second forward); it must stay untouched, together with `workspace`, until
-                                dgs_dit_backward has run.                                               */
+  void* train_state;         /* NULL: inference.  Else a caller buffer of dgs_dit_train_state_bytes[_ex](): what the
+                                backward needs from the forward lives there; it must stay untouched, together with
+                                `workspace`, until dgs_dit_backward has run.                              */
+  int train_mode;            /* DGS_TRAIN_STORE (0): every activation is kept (4 GB per sample at N=4098; forward + 2x
+                                backward FLOPs).  DGS_TRAIN_RECOMPUTE (1): only the fp32 residual stream entering each
+                                block is kept (0.6 GB per sample) and the backward re-runs each block's forward before
+                                differentiating it -- the reference's torch.utils.checkpoint around every block
+                                (denoiser.py:348-354; grad_checkpoint_every = 1), for the yaml batch sizes.           */
 } dgs_dit_io;
+#define DGS_TRAIN_STORE 0
+#define DGS_TRAIN_RECOMPUTE 1
 
 size_t dgs_dit_workspace_bytes(const dgs_dit_weights* w, int B, int V, int H, int W);
 int dgs_dit_forward(const dgs_dit_weights* w, const dgs_dit_io* io, void* workspace, size_t workspace_bytes,
@@ -255,11 +284,27 @@ typedef struct {  /* gradients w.r.t. the outputs of dgs_dit_forward (what dgs_r
   const float* d_xyz; const float* d_features; const float* d_scaling; const float* d_rotation; const float* d_opacity;
 } dgs_dit_out_grads;
 
-size_t dgs_dit_train_state_bytes(const dgs_dit_weights* w, int B, int V, int H, int W);
+size_t dgs_dit_train_state_bytes(const dgs_dit_weights* w, int B, int V, int H, int W); /* DGS_TRAIN_STORE */
+size_t dgs_dit_train_state_bytes_ex(const dgs_dit_weights* w, int B, int V, int H, int W, int train_mode);
 /* io / workspace / io->train_state: exactly what the matching dgs_dit_forward call was given. */
 int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, const dgs_dit_io* io,
                      const dgs_dit_out_grads* dout, const dgs_dit_grads* grads, void* workspace, size_t workspace_bytes,
                      void* stream);
+/* Same, with a completion hook for the data-parallel gradient exchange (what torch DDP's autograd hooks give the
+ * reference, diffusionGS_rel.yaml:80): block_done[l], l = layers-1 .. 0, is recorded on `stream` as soon as EVERY
+ * parameter gradient of transformer block l is final (the blocks are differentiated in reverse order), block_done[layers]
+ * when the remaining gradients (tokenizer, embedder, heads) are.  A side stream that waits on block_done[l]
+ * (dgs_stream_wait_event) can all-reduce block l's contiguous bucket while blocks l-1 .. 0 are still running.
+ * Entries may be NULL; events come from dgs_event_create. */
+typedef struct {
+  void** block_done;   /* NULL or [layers + 1] events */
+} dgs_dit_bwd_opts;
+int dgs_dit_backward_ex(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, const dgs_dit_io* io,
+                        const dgs_dit_out_grads* dout, const dgs_dit_grads* grads, const dgs_dit_bwd_opts* opts,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int dgs_event_create(void** event);                 /* cudaEventCreateWithFlags(DisableTiming) */
+int dgs_event_destroy(void* event);
+int dgs_stream_wait_event(void* stream, void* event);
 /* out[c, m] = bf16(in[m, c]) for in [M, C] (fp32 if in_is_f32 else bf16), out [C, round_up(M, 64)] zero padded;
  * colsum (optional, fp32 [C]) += column sums.  Used for the transposed weight copies and inside the backward. */
 int dgs_transpose_bf16(const void* in, int in_is_f32, int M, int C, void* out, float* colsum, void* stream);
@@ -268,6 +313,12 @@ int dgs_transpose_bf16(const void* in, int in_is_f32, int M, int C, void* out, f
 int dgs_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, const float* grad_scale_dev,
                    void* stream);
+/* Same update with the exponential moving average of the parameters folded in (the reference's EMA callback,
+ * diffusionGS/utils/ema.py:82-101 with decay 0.9999, launch.py:227): after the AdamW update of p,
+ * ema = ema_decay * ema + (1 - ema_decay) * p, in the same pass over the arena.  ema == NULL: plain dgs_adamw_step. */
+int dgs_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, size_t n, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                       const float* grad_scale_dev, float ema_decay, void* stream);
 /* weight refresh after an optimizer step: `batch` fp32 matrices [M, C] (matrix i at in + i*in_batch_stride floats) ->
  * bf16 copies [batch, M, C] (optional) and transposed bf16 copies [batch, C, M]; M, C multiples of 64 */
 int dgs_cast_transpose_f32(const float* in, long long in_batch_stride, int batch, int M, int C, void* out_bf16,

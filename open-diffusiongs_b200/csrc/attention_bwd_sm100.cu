@@ -86,7 +86,7 @@ constexpr int DQ_STAGES = 3;
 constexpr int DQ_SMEM = 2 * AB_T128 /*Q, dO*/ + 2 * DQ_STAGES * AB_T64 /*K, V*/ + 1024 + 256;
 constexpr uint32_t DQ_TM_S = 0 /* 2 buffers x 64 */, DQ_TM_DP = 128, DQ_TM_DQ = 192, DQ_TMEM_COLS = 256;
 
-// UNI (experiment, DGS_ATT_UNI=1): MMA issue by the converged warp under elect.sync (see attention_sm100.cu / sm100_ptx.cuh)
+// UNI (default; DGS_ATT_UNI=0 selects the old path): MMA issue by the converged warp under elect.sync (see attention_sm100.cu / sm100_ptx.cuh)
 template <bool UNI>
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_kv64,
@@ -558,7 +558,7 @@ int attention_bwd(const void* qkv, const void* out, const void* dout, float* lse
     DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
     const char* eu = getenv("DGS_ATT_UNI");
-    uni = (eu && eu[0] == '1') ? 1 : 0;
+    uni = (eu && eu[0] == '0') ? 0 : 1;  // default since round 2 (measured: r2 first GPU call)
     configured = true;
   }
   DGS_CUDA_OK(launch_pdl(attn_bwd_prep_kernel, dim3(Np, B), dim3(H * 16 < 32 ? 32 : H * 16), 0, st,

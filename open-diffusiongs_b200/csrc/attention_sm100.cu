@@ -69,7 +69,7 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 
 // POLY_OF_8: how many of every 8 exponentials are evaluated by a degree-3 polynomial on the FMA/ALU pipes instead of
 // the MUFU pipe (which is the busiest unit of this kernel: XU 58 %, 27 % of the stall samples on MUFU.EX2)
-// UNI (experiment, DGS_ATT_UNI=1): the MMA-issuing warp runs fully converged and issues under elect.sync instead of
+// UNI (default; DGS_ATT_UNI=0 selects the old path): the MMA-issuing warp runs fully converged and issues under elect.sync instead of
 // `lane == 0` (see elect_one_sync in sm100_ptx.cuh): the probe has this thread as the pacing role (~1140 clk per key block
 // for 12 small MMAs + 3 commits).
 template <int POLY_OF_8, bool UNI = false>
@@ -374,12 +374,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
 int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st) {
   DGS_REQUIRE(B > 0 && N > 0 && H > 0, "attention: bad shape B=%d N=%d H=%d", B, N, H);
-  static int tpr2 = -1;  // experiment: two softmax threads per row (attention2_sm100.cu), measured slower
-  if (tpr2 < 0) {
-    const char* e = getenv("DGS_ATT_TPR2");
-    tpr2 = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (tpr2) return attention_fwd_tpr2(qkv, out, lse2, B, N, H, st);
   const int D = H * ATT_HD;
   const int Np = attention_lse_stride(N);
   CUtensorMap tm_q, tm_kv;
@@ -400,11 +394,11 @@ int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, 
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     const char* eu = getenv("DGS_ATT_UNI");
-    uni = (eu && eu[0] == '1') ? 1 : 0;
+    uni = (eu && eu[0] == '0') ? 0 : 1;  // default since round 2 (measured: r2 first GPU call)
   }
   dim3 grid(ceil_div(N, ATT_BM), H, B);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  auto kern = uni ? attention_fwd_kernel<0, true> : poly == 1 ? attention_fwd_kernel<1> : poly == 2 ? attention_fwd_kernel<2>
+  auto kern = (uni && poly <= 0) ? attention_fwd_kernel<0, true> : poly == 1 ? attention_fwd_kernel<1> : poly == 2 ? attention_fwd_kernel<2>
                   : poly >= 3 ? attention_fwd_kernel<3> : attention_fwd_kernel<0>;
   DGS_CUDA_OK(launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tm_q, tm_kv, o, lse2, Np, N, H));
   DGS_POST_LAUNCH();

@@ -47,6 +47,9 @@ struct DitWorkspace {
 
 // Everything the backward needs from the forward (training mode), plus the backward's own scratch.  Per-layer tensors
 // are stacked along a leading L axis.  M = B*N rows, Mp = round_up(M, 64), Mt = B*T image-token rows.
+// Recompute mode (io->train_mode == DGS_TRAIN_RECOMPUTE; the reference's torch.utils.checkpoint around every block,
+// denoiser.py:348-354): only the residual stream entering each block (x_all) survives the forward; the per-layer tensors
+// have ONE slot that the backward refills by re-running block l's forward right before differentiating it.
 struct TrainState {
   float* x_pre;             // [M, w]      assembled tokens before the input LayerNorm
   float* x_all;             // [L+1][M, w] residual stream entering block l (x_all[L] = final)
@@ -75,15 +78,18 @@ struct TrainState {
   __nv_bfloat16* bigT0;     // [w, Mp]     transposed token gradient (tokenizer weight gradient only)
   __nv_bfloat16* bigT1;     // [w, Mp]     transposed patches        (tokenizer weight gradient only)
   size_t bytes;
-  TrainState(void* base, const dgs_dit_weights* w, int B, int V, int H, int W) {
-    const size_t T = (size_t)V * (H / w->patch) * (W / w->patch), N = T + w->n_gaussians, D = w->width, L = w->layers;
+  size_t lk;  // slots of the per-layer tensors: L (store mode) or 1 (recompute mode: only x_all is kept per layer)
+  TrainState(void* base, const dgs_dit_weights* w, int B, int V, int H, int W, int mode) {
+    const size_t T = (size_t)V * (H / w->patch) * (W / w->patch), N = T + w->n_gaussians, D = w->width;
+    const size_t Lx = w->layers, L = mode == DGS_TRAIN_RECOMPUTE ? 1 : Lx;
+    lk = L;
     const size_t M = (size_t)B * N, Mp = (M + 63) / 64 * 64, U = w->mlp_hidden;
     const size_t Np = (size_t)attention_lse_stride((int)N);
-    const size_t mod_stride = L * 6 * D + 4 * D;
+    const size_t mod_stride = Lx * 6 * D + 4 * D;
     const size_t wide = U > 3 * D ? U : 3 * D;
     Carver c(base);
     x_pre = c.take<float>(M * D);
-    x_all = c.take<float>((L + 1) * M * D);
+    x_all = c.take<float>((Lx + 1) * M * D);
     x_mid = c.take<float>(L * M * D);
     h1 = c.take<__nv_bfloat16>(L * M * D);
     h2 = c.take<__nv_bfloat16>(L * M * D);
@@ -127,6 +133,81 @@ int check_dit(const dgs_dit_weights* w, int B, int V, int H, int W) {
     if (_rc) return _rc;    \
   } while (0)
 
+// Buffers of ONE DiTBlock forward (utils_transformer.py:270-290).  Inference: every block re-uses the workspace and the
+// residual stream is updated in place (x_in == x_mid == x_out, TMA reduce-add epilogue).  Training: x_in / x_mid / x_out
+// are distinct fp32 tensors and the pre-gate branch outputs / pre-GELU values are kept for the backward.
+struct BlockBufs {
+  const float* x_in; float* x_mid; float* x_out;
+  __nv_bfloat16 *h1, *h2, *qkv, *attn, *u;
+  __nv_bfloat16 *proj_out, *fc2_out, *u_pre;  // training only (NULL: not stored)
+  float* lse;                                  // training only
+  bool distinct;                               // x_in / x_mid / x_out are separate buffers
+};
+
+int block_forward(const dgs_dit_weights* w, int l, const float* m, int mod_stride, int B, int N, const BlockBufs& b,
+                  cudaStream_t st) {
+  const int D = w->width;
+  {
+    ProfScope ps(st, PROF_DIT_LN);
+    DGS_TRY(ln_modulate(b.x_in, nullptr, m, m + D, mod_stride, b.h1, B, N, 0, N, D, 1e-6f, 0, st));
+  }
+  {
+    ProfScope ps(st, PROF_DIT_GEMM_QKV);
+    GemmEpilogue ep;
+    ep.out = b.qkv; ep.ldc = 3 * D; ep.bias = w->qkv_b + (size_t)l * 3 * D;
+    DGS_TRY(gemm_bf16(b.h1, (const __nv_bfloat16*)w->qkv_w + (size_t)l * 3 * D * D, B * N, 3 * D, D, EPI_BIAS_BF16, ep, st));
+  }
+  {
+    ProfScope ps(st, PROF_DIT_ATTN);
+    DGS_TRY(attention_fwd(b.qkv, b.attn, b.lse, B, N, w->heads, st));
+  }
+  {
+    ProfScope ps(st, PROF_DIT_GEMM_PROJ);
+    GemmEpilogue ep;
+    ep.out = b.x_mid; ep.ldc = D; ep.bias = w->proj_b + (size_t)l * D;
+    ep.gate = m + 2 * D; ep.gate_stride = mod_stride; ep.rows_per_sample = N;
+    if (b.distinct) { ep.resid = b.x_in; ep.aux = b.proj_out; }
+    DGS_TRY(gemm_bf16(b.attn, (const __nv_bfloat16*)w->proj_w + (size_t)l * D * D, B * N, D, D, EPI_GATE_RESID_F32, ep, st));
+  }
+  {
+    ProfScope ps(st, PROF_DIT_LN);
+    DGS_TRY(ln_modulate(b.x_mid, nullptr, m + 3 * D, m + 4 * D, mod_stride, b.h2, B, N, 0, N, D, 1e-6f, 0, st));
+  }
+  {
+    ProfScope ps(st, PROF_DIT_GEMM_FC1);
+    GemmEpilogue ep;
+    ep.out = b.u; ep.ldc = w->mlp_hidden; ep.bias = w->fc1_b + (size_t)l * w->mlp_hidden;
+    ep.aux = b.u_pre;
+    DGS_TRY(gemm_bf16(b.h2, (const __nv_bfloat16*)w->fc1_w + (size_t)l * w->mlp_hidden * D, B * N, w->mlp_hidden, D,
+                      EPI_BIAS_GELU_BF16, ep, st));
+  }
+  {
+    ProfScope ps(st, PROF_DIT_GEMM_FC2);
+    GemmEpilogue ep;
+    ep.out = b.x_out; ep.ldc = D; ep.bias = w->fc2_b + (size_t)l * D;
+    ep.gate = m + 5 * D; ep.gate_stride = mod_stride; ep.rows_per_sample = N;
+    if (b.distinct) { ep.resid = b.x_mid; ep.aux = b.fc2_out; }
+    DGS_TRY(gemm_bf16(b.u, (const __nv_bfloat16*)w->fc2_w + (size_t)l * D * w->mlp_hidden, B * N, D, w->mlp_hidden,
+                      EPI_GATE_RESID_F32, ep, st));
+  }
+  return DGS_OK;
+}
+
+// the training-mode buffers of block l: slice l of the stacked tensors (store mode) or the single slot (recompute mode);
+// `keep_aux` = false drops the stores only the backward reads (recompute-mode forward pass)
+BlockBufs train_bufs(const TrainState& ts, const dgs_dit_weights* w, int l, size_t MD, size_t MU, int B, int N, bool keep_aux) {
+  const size_t s = ts.lk == 1 ? 0 : (size_t)l;
+  BlockBufs b;
+  b.x_in = ts.x_all + (size_t)l * MD; b.x_mid = ts.x_mid + s * MD; b.x_out = ts.x_all + (size_t)(l + 1) * MD;
+  b.h1 = ts.h1 + s * MD; b.h2 = ts.h2 + s * MD; b.qkv = ts.qkv + s * 3 * MD; b.attn = ts.attn + s * MD; b.u = ts.u + s * MU;
+  b.proj_out = keep_aux ? ts.proj_out + s * MD : nullptr;
+  b.fc2_out = keep_aux ? ts.fc2_out + s * MD : nullptr;
+  b.u_pre = keep_aux ? ts.u_pre + s * MU : nullptr;
+  b.lse = ts.lse + s * B * w->heads * attention_lse_stride(N);
+  b.distinct = true;
+  return b;
+}
+
 }  // namespace
 
 extern "C" {
@@ -149,9 +230,11 @@ int dgs_dit_forward(const dgs_dit_weights* w, const dgs_dit_io* io, void* worksp
   DGS_REQUIRE(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
   const int mod_stride = L * 6 * D + 4 * D;
   const bool train = io->train_state != nullptr;
-  TrainState ts(io->train_state, w, B, V, H, W);
+  const bool recompute = train && io->train_mode == DGS_TRAIN_RECOMPUTE;
+  DGS_REQUIRE(io->train_mode == DGS_TRAIN_STORE || io->train_mode == DGS_TRAIN_RECOMPUTE, "bad train_mode %d", io->train_mode);
+  TrainState ts(io->train_state, w, B, V, H, W, io->train_mode);
   const size_t MD = (size_t)B * N * D, MU = (size_t)B * N * w->mlp_hidden;
-  float* x0 = train ? ts.x_all : ws.x;  // residual stream entering block 0
+  float* x0 = (train && !recompute) ? ts.x_all : ws.x;  // residual stream entering block 0
 
   // ---- input stage: posed image -> tokens -> tokenizer GEMM -> [pos tokens | image tokens] -> LayerNorm(weight) ----
   if (g_prof_on) prof_begin(st, PROF_DIT_INPUT);
@@ -176,61 +259,20 @@ int dgs_dit_forward(const dgs_dit_weights* w, const dgs_dit_io* io, void* worksp
   // ---- L x DiTBlock (utils_transformer.py:270-290) ----
   for (int l = 0; l < L; l++) {
     const float* m = ws.mod + (size_t)l * 6 * D;  // shift_msa | scale_msa | gate_msa | shift_mlp | scale_mlp | gate_mlp
-    // inference: one set of buffers, residual stream updated in place; training: per-layer slices of the train state
-    float* x_in = train ? ts.x_all + (size_t)l * MD : ws.x;
-    float* x_mid = train ? ts.x_mid + (size_t)l * MD : ws.x;
-    float* x_out = train ? ts.x_all + (size_t)(l + 1) * MD : ws.x;
-    __nv_bfloat16* h1 = train ? ts.h1 + (size_t)l * MD : ws.h;
-    __nv_bfloat16* h2 = train ? ts.h2 + (size_t)l * MD : ws.h;
-    __nv_bfloat16* qkv = train ? ts.qkv + (size_t)l * 3 * MD : ws.qkv;
-    __nv_bfloat16* attn = train ? ts.attn + (size_t)l * MD : ws.attn;
-    __nv_bfloat16* u = train ? ts.u + (size_t)l * MU : ws.u;
-    float* lse = train ? ts.lse + (size_t)l * B * w->heads * attention_lse_stride(N) : nullptr;
-    {
-      ProfScope ps(st, PROF_DIT_LN);
-      DGS_TRY(ln_modulate(x_in, nullptr, m, m + D, mod_stride, h1, B, N, 0, N, D, 1e-6f, 0, st));
+    BlockBufs bb;
+    if (train && !recompute) {
+      bb = train_bufs(ts, w, l, MD, MU, B, N, /*keep_aux=*/true);
+    } else {  // inference / recompute mode: one set of buffers, residual stream updated in place (TMA reduce-add epilogues);
+              // recompute mode snapshots the stream entering every block (all the backward keeps per layer)
+      if (recompute) DGS_CUDA_OK(cudaMemcpyAsync(ts.x_all + (size_t)l * MD, ws.x, MD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      bb.x_in = ws.x; bb.x_mid = ws.x; bb.x_out = ws.x;
+      bb.h1 = ws.h; bb.h2 = ws.h; bb.qkv = ws.qkv; bb.attn = ws.attn; bb.u = ws.u;
+      bb.proj_out = bb.fc2_out = bb.u_pre = nullptr; bb.lse = nullptr; bb.distinct = false;
     }
-    {
-      ProfScope ps(st, PROF_DIT_GEMM_QKV);
-      GemmEpilogue ep;
-      ep.out = qkv; ep.ldc = 3 * D; ep.bias = w->qkv_b + (size_t)l * 3 * D;
-      DGS_TRY(gemm_bf16(h1, (const __nv_bfloat16*)w->qkv_w + (size_t)l * 3 * D * D, B * N, 3 * D, D, EPI_BIAS_BF16, ep, st));
-    }
-    {
-      ProfScope ps(st, PROF_DIT_ATTN);
-      DGS_TRY(attention_fwd(qkv, attn, lse, B, N, w->heads, st));
-    }
-    {
-      ProfScope ps(st, PROF_DIT_GEMM_PROJ);
-      GemmEpilogue ep;
-      ep.out = x_mid; ep.ldc = D; ep.bias = w->proj_b + (size_t)l * D;
-      ep.gate = m + 2 * D; ep.gate_stride = mod_stride; ep.rows_per_sample = N;
-      if (train) { ep.resid = x_in; ep.aux = ts.proj_out + (size_t)l * MD; }
-      DGS_TRY(gemm_bf16(attn, (const __nv_bfloat16*)w->proj_w + (size_t)l * D * D, B * N, D, D, EPI_GATE_RESID_F32, ep, st));
-    }
-    {
-      ProfScope ps(st, PROF_DIT_LN);
-      DGS_TRY(ln_modulate(x_mid, nullptr, m + 3 * D, m + 4 * D, mod_stride, h2, B, N, 0, N, D, 1e-6f, 0, st));
-    }
-    {
-      ProfScope ps(st, PROF_DIT_GEMM_FC1);
-      GemmEpilogue ep;
-      ep.out = u; ep.ldc = w->mlp_hidden; ep.bias = w->fc1_b + (size_t)l * w->mlp_hidden;
-      if (train) ep.aux = ts.u_pre + (size_t)l * MU;
-      DGS_TRY(gemm_bf16(h2, (const __nv_bfloat16*)w->fc1_w + (size_t)l * w->mlp_hidden * D, B * N, w->mlp_hidden, D,
-                        EPI_BIAS_GELU_BF16, ep, st));
-    }
-    {
-      ProfScope ps(st, PROF_DIT_GEMM_FC2);
-      GemmEpilogue ep;
-      ep.out = x_out; ep.ldc = D; ep.bias = w->fc2_b + (size_t)l * D;
-      ep.gate = m + 5 * D; ep.gate_stride = mod_stride; ep.rows_per_sample = N;
-      if (train) { ep.resid = x_mid; ep.aux = ts.fc2_out + (size_t)l * MD; }
-      DGS_TRY(gemm_bf16(u, (const __nv_bfloat16*)w->fc2_w + (size_t)l * D * w->mlp_hidden, B * N, D, w->mlp_hidden,
-                        EPI_GATE_RESID_F32, ep, st));
-    }
+    DGS_TRY(block_forward(w, l, m, mod_stride, B, N, bb, st));
   }
-  float* x_fin = train ? ts.x_all + (size_t)L * MD : ws.x;
+  float* x_fin = (train && !recompute) ? ts.x_all + (size_t)L * MD : ws.x;
+  if (recompute) DGS_CUDA_OK(cudaMemcpyAsync(ts.x_all + (size_t)L * MD, ws.x, MD * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (io->tokens_out)
     DGS_CUDA_OK(cudaMemcpyAsync(io->tokens_out, x_fin, (size_t)B * N * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
@@ -260,13 +302,27 @@ int dgs_dit_forward(const dgs_dit_weights* w, const dgs_dit_io* io, void* worksp
 }
 
 size_t dgs_dit_train_state_bytes(const dgs_dit_weights* w, int B, int V, int H, int W) {
+  return dgs_dit_train_state_bytes_ex(w, B, V, H, W, DGS_TRAIN_STORE);
+}
+
+size_t dgs_dit_train_state_bytes_ex(const dgs_dit_weights* w, int B, int V, int H, int W, int train_mode) {
   if (check_dit(w, B, V, H, W)) return 0;
-  return TrainState(nullptr, w, B, V, H, W).bytes;
+  if (train_mode != DGS_TRAIN_STORE && train_mode != DGS_TRAIN_RECOMPUTE) {
+    set_error("bad train_mode %d", train_mode);
+    return 0;
+  }
+  return TrainState(nullptr, w, B, V, H, W, train_mode).bytes;
 }
 
 int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, const dgs_dit_io* io,
                      const dgs_dit_out_grads* dout, const dgs_dit_grads* g, void* workspace, size_t workspace_bytes,
                      void* stream) {
+  return dgs_dit_backward_ex(w, wT, io, dout, g, nullptr, workspace, workspace_bytes, stream);
+}
+
+int dgs_dit_backward_ex(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, const dgs_dit_io* io,
+                        const dgs_dit_out_grads* dout, const dgs_dit_grads* g, const dgs_dit_bwd_opts* opts,
+                        void* workspace, size_t workspace_bytes, void* stream) {
   DGS_REQUIRE(io != nullptr && wT != nullptr && dout != nullptr && g != nullptr, "NULL argument");
   DGS_TRY(check_dit(w, io->B, io->V, io->H, io->W));
   DGS_REQUIRE(io->train_state, "dgs_dit_backward: io->train_state is NULL (the forward must run in training mode)");
@@ -280,10 +336,13 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
   DGS_REQUIRE(N >= 64, "dgs_dit_backward: needs at least 64 tokens per sample");
   DitWorkspace ws(workspace, w, B, V, H, W);
   DGS_REQUIRE(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
-  TrainState ts(io->train_state, w, B, V, H, W);
+  DGS_REQUIRE(io->train_mode == DGS_TRAIN_STORE || io->train_mode == DGS_TRAIN_RECOMPUTE, "bad train_mode %d", io->train_mode);
+  const bool recompute = io->train_mode == DGS_TRAIN_RECOMPUTE;
+  TrainState ts(io->train_state, w, B, V, H, W, io->train_mode);
   const int mod_stride = L * 6 * D + 4 * D;
   const size_t MD = (size_t)M * D, MU = (size_t)M * U;
   const int Np = attention_lse_stride(N);
+  void** done_ev = opts ? opts->block_done : nullptr;
 
   // gradients accumulated by atomics start from zero; GEMM-produced ones are overwritten
   DGS_CUDA_OK(cudaMemsetAsync(ts.dmod, 0, (size_t)B * mod_stride * sizeof(float), st));
@@ -344,22 +403,28 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
   for (int l = L - 1; l >= 0; l--) {
     const float* m = ws.mod + (size_t)l * 6 * D;
     float* dm = ts.dmod + (size_t)l * 6 * D;
+    const size_t sl = recompute ? 0 : (size_t)l;  // slot of the per-layer tensors
+    if (recompute) {  // refill the single slot: block l's forward from the saved residual stream (denoiser.py:348-354)
+      BlockBufs bb = train_bufs(ts, w, l, MD, MU, B, N, /*keep_aux=*/true);
+      bb.x_out = ts.dx_pre;  // the block's output is not needed again; dx_pre is free until the input stage
+      DGS_TRY(block_forward(w, l, m, mod_stride, B, N, bb, st));
+    }
     const float* x_in = ts.x_all + (size_t)l * MD;
-    const float* x_mid = ts.x_mid + (size_t)l * MD;
+    const float* x_mid = ts.x_mid + sl * MD;
     // -- MLP branch: x_out = x_mid + gate_mlp * (fc2(gelu(fc1(h2))) )
     {
       ProfScope ps(st, PROF_DIT_BWD_ELEM);
-      DGS_TRY(gate_bwd(ts.dx, ts.fc2_out + (size_t)l * MD, m + 5 * D, mod_stride, N, M, D, ts.dyb, nullptr, dm + 5 * D,
+      DGS_TRY(gate_bwd(ts.dx, ts.fc2_out + sl * MD, m + 5 * D, mod_stride, N, M, D, ts.dyb, nullptr, dm + 5 * D,
                        g->fc2_b + l * LS, st));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_WGRAD);
-      DGS_TRY(wgrad_tn(ts.dyb, D, ts.u + (size_t)l * MU, U, g->fc2_w + l * LS, D, U, M));
+      DGS_TRY(wgrad_tn(ts.dyb, D, ts.u + sl * MU, U, g->fc2_w + l * LS, D, U, M));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_DGRAD);
       DGS_TRY(dgrad(ts.dyb, (const __nv_bfloat16*)wT->fc2_wT + (size_t)l * D * U, ts.big0, M, U, D, EPI_DGELU_BF16,
-                    ts.u_pre + (size_t)l * MU));  // du_pre = (dy W2) * gelu'(u_pre)
+                    ts.u_pre + sl * MU));  // du_pre = (dy W2) * gelu'(u_pre)
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_ELEM);
@@ -367,7 +432,7 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_WGRAD);
-      DGS_TRY(wgrad_tn(ts.big0, U, ts.h2 + (size_t)l * MD, D, g->fc1_w + l * LS, U, D, M));
+      DGS_TRY(wgrad_tn(ts.big0, U, ts.h2 + sl * MD, D, g->fc1_w + l * LS, U, D, M));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_DGRAD);
@@ -378,12 +443,12 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
       DGS_TRY(ln_modulate_bwd(x_mid, ts.dh, 0, nullptr, m + 4 * D, mod_stride, B, N, 0, N, D, 1e-6f, ts.dx, 1, dm + 3 * D,
                               dm + 4 * D, nullptr, ts.ln_stats, st));
       // -- attention branch: x_mid = x_in + gate_msa * proj(attn(qkv(h1)))
-      DGS_TRY(gate_bwd(ts.dx, ts.proj_out + (size_t)l * MD, m + 2 * D, mod_stride, N, M, D, ts.dyb, nullptr, dm + 2 * D,
+      DGS_TRY(gate_bwd(ts.dx, ts.proj_out + sl * MD, m + 2 * D, mod_stride, N, M, D, ts.dyb, nullptr, dm + 2 * D,
                        g->proj_b + l * LS, st));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_WGRAD);
-      DGS_TRY(wgrad_tn(ts.dyb, D, ts.attn + (size_t)l * MD, D, g->proj_w + l * LS, D, D, M));
+      DGS_TRY(wgrad_tn(ts.dyb, D, ts.attn + sl * MD, D, g->proj_w + l * LS, D, D, M));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_DGRAD);
@@ -391,8 +456,8 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_ATTN);
-      DGS_TRY(attention_bwd(ts.qkv + (size_t)l * 3 * MD, ts.attn + (size_t)l * MD, ts.dh,
-                            ts.lse + (size_t)l * B * w->heads * Np, ts.dsum, ts.big0, B, N, w->heads, st));
+      DGS_TRY(attention_bwd(ts.qkv + sl * 3 * MD, ts.attn + sl * MD, ts.dh,
+                            ts.lse + sl * B * w->heads * Np, ts.dsum, ts.big0, B, N, w->heads, st));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_ELEM);
@@ -400,7 +465,7 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_WGRAD);
-      DGS_TRY(wgrad_tn(ts.big0, 3 * D, ts.h1 + (size_t)l * MD, D, g->qkv_w + l * LS, 3 * D, D, M));
+      DGS_TRY(wgrad_tn(ts.big0, 3 * D, ts.h1 + sl * MD, D, g->qkv_w + l * LS, 3 * D, D, M));
     }
     {
       ProfScope ps(st, PROF_DIT_BWD_DGRAD);
@@ -409,7 +474,13 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
     {
       ProfScope ps(st, PROF_DIT_BWD_ELEM);
       DGS_TRY(ln_modulate_bwd(x_in, ts.dh, 0, nullptr, m + D, mod_stride, B, N, 0, N, D, 1e-6f, ts.dx, 1, dm, dm + D, nullptr, ts.ln_stats, st));
+      // this block's adaLN linear (6w x w, a third of the block's parameters): d mod_l is complete now, so its weight /
+      // bias gradient is produced HERE -- every gradient of block l is final at this point and its all-reduce can start
+      // while blocks l-1 .. 0 are still being differentiated (block_done event); d silu(c) accumulates across blocks
+      DGS_TRY(skinny_linear_bwd(ws.c, w->adaln_w + (size_t)l * 6 * D * D, dm, mod_stride, B, 6 * D, D, 1, g->adaln_w + l * LS,
+                                g->adaln_b + l * LS, ts.dcond, st));
     }
+    if (done_ev && done_ev[l]) DGS_CUDA_OK(cudaEventRecord((cudaEvent_t)done_ev[l], st));
   }
 
   ProfScope ps_in(st, PROF_DIT_BWD_ELEM);
@@ -425,18 +496,39 @@ int dgs_dit_backward(const dgs_dit_weights* w, const dgs_dit_weights_t* wT, cons
   float* dsc = ts.dcond;                       // d silu(c), then dc
   float* dt1 = ts.dcond + (size_t)B * D;       // d temb1, then d pre1
   float* pre1 = ts.dcond + (size_t)2 * B * D;  // t0 pre-activation (recomputed)
-  {  // ONE launch over the stacked adaLN linears (L blocks + 2 heads); their gradients are separate parameters
+  {  // the two heads' adaLN linears in one launch (the blocks' ones were differentiated inside the block loop)
     SkinnySegs segs;
-    segs.seg_rows = 6 * D; segs.n_seg = L; segs.seg_stride = (long long)LS; segs.dW0 = g->adaln_w; segs.db0 = g->adaln_b;
+    segs.seg_rows = 0; segs.n_seg = 0; segs.seg_stride = 0; segs.dW0 = nullptr; segs.db0 = nullptr;
     segs.tail_rows[0] = 2 * D; segs.tail_dW[0] = g->ups_adaln_w; segs.tail_db[0] = g->ups_adaln_b;
     segs.tail_rows[1] = 2 * D; segs.tail_dW[1] = g->dec_adaln_w; segs.tail_db[1] = g->dec_adaln_b;
-    DGS_TRY(skinny_linear_bwd_segs(ws.c, w->adaln_w, ts.dmod, mod_stride, B, mod_stride, D, 1, segs, dsc, st));
+    DGS_TRY(skinny_linear_bwd_segs(ws.c, w->adaln_w + (size_t)L * 6 * D * D, ts.dmod + (size_t)L * 6 * D, mod_stride, B, 4 * D, D,
+                                   1, segs, dsc, st));
   }
   DGS_TRY(silu_bwd_inplace(dsc, ws.c, B * D, st));
   DGS_TRY(skinny_linear_bwd(ws.temb1, w->t2_w, dsc, D, B, D, D, 0, g->t2_w, g->t2_b, dt1, st));
   DGS_TRY(skinny_linear(ws.temb0, w->t0_w, w->t0_b, pre1, B, D, 256, 0, 0, st));
   DGS_TRY(silu_bwd_inplace(dt1, pre1, B * D, st));
   DGS_TRY(skinny_linear_bwd(ws.temb0, w->t0_w, dt1, D, B, D, 256, 0, g->t0_w, g->t0_b, nullptr, st));
+  if (done_ev && done_ev[L]) DGS_CUDA_OK(cudaEventRecord((cudaEvent_t)done_ev[L], st));
+  return DGS_OK;
+}
+
+int dgs_event_create(void** ev) {
+  DGS_REQUIRE(ev != nullptr, "NULL pointer");
+  cudaEvent_t e;
+  DGS_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *ev = (void*)e;
+  return DGS_OK;
+}
+
+int dgs_event_destroy(void* ev) {
+  if (ev) DGS_CUDA_OK(cudaEventDestroy((cudaEvent_t)ev));
+  return DGS_OK;
+}
+
+int dgs_stream_wait_event(void* stream, void* ev) {
+  DGS_REQUIRE(ev != nullptr, "NULL event");
+  DGS_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0));
   return DGS_OK;
 }
 
@@ -451,6 +543,15 @@ int dgs_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
   DGS_REQUIRE(param && grad && exp_avg && exp_avg_sq && step >= 1, "bad AdamW arguments");
   return adamw_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
                     grad_scale_dev, (cudaStream_t)stream);
+}
+
+int dgs_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, size_t n, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                       const float* grad_scale_dev, float ema_decay, void* stream) {
+  DGS_REQUIRE(param && grad && exp_avg && exp_avg_sq && step >= 1, "bad AdamW arguments");
+  DGS_REQUIRE(!ema || (ema_decay >= 0.f && ema_decay <= 1.f), "EMA decay must be in [0, 1]");  // ema.py:56-57
+  return adamw_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                    grad_scale_dev, (cudaStream_t)stream, ema, ema_decay);
 }
 
 int dgs_cast_transpose_f32(const float* in, long long in_batch_stride, int batch, int M, int C, void* out_bf16,

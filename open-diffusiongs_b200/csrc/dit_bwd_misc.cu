@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256) gaussians_epilogue_bwd_kernel(const float
     const float m = (src[0] + src[1] + src[2]) / 3.0f;
     const float sg = 1.0f / (1.0f + expf(-m));
     const float dt = gx * d0 + gy * d1 + gz * d2;  // xyz = o + t d
-    const float dtdm = (scene ? (far_ - near_) : 3.6f) * sg * (1.0f - sg);
+    const float dtdm = (scene == 1 ? (far_ - near_) : scene == 2 ? 1.0f : 3.6f) * sg * (1.0f - sg);
     da[0] = da[1] = da[2] = dt * dtdm * (1.0f / 3.0f);
   }
   da[3] = d.features[3 * o]; da[4] = d.features[3 * o + 1]; da[5] = d.features[3 * o + 2];
@@ -524,7 +524,8 @@ __global__ void pos_embed_bwd_kernel(const float* __restrict__ dx, float* __rest
 // AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments), fp32 master weights
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                             float bc1, float bc2_sqrt, float grad_scale, const float* __restrict__ grad_scale_dev) {
+                             float bc1, float bc2_sqrt, float grad_scale, const float* __restrict__ grad_scale_dev,
+                             float* __restrict__ ema, float ema_decay) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (grad_scale_dev) grad_scale *= __ldg(grad_scale_dev);  // e.g. the clip factor, computed on the device
@@ -536,6 +537,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   float pi = p[i] * (1.0f - lr * wd);
   pi -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
   p[i] = pi;
+  if (ema) ema[i] = ema_decay * ema[i] + (1.0f - ema_decay) * pi;  // ema.py:82-101 (multi_tensor_axpby form)
 }
 
 }  // namespace
@@ -682,11 +684,11 @@ int pos_embed_bwd(const float* dx, float* dpos, int B, int G, int N, int D, cuda
 }
 
 int adamw_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
-               int step, float grad_scale, const float* grad_scale_dev, cudaStream_t st) {
+               int step, float grad_scale, const float* grad_scale_dev, cudaStream_t st, float* ema, float ema_decay) {
   if (n == 0) return DGS_OK;
   const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
   adamw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2),
-                                                            grad_scale, grad_scale_dev);
+                                                            grad_scale, grad_scale_dev, ema, ema_decay);
   DGS_POST_LAUNCH();
   return DGS_OK;
 }

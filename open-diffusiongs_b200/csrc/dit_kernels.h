@@ -34,15 +34,11 @@ int gemm_bf16_tn(const void* A, const void* W, int M, int N, int K, const GemmEp
 int gemm_bf16_2cta(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st);
 int gemm_bf16_tn_2cta(const void* A, const void* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t st);
 
-// single-CTA 256 x 256 tile variant (gemm3_sm100.cu), needs N % 256 == 0
-int gemm_bf16_m256(const void* A, const void* W, int M, int N, int K, int epi, const GemmEpilogue& ep, cudaStream_t st);
 
 // softmax(Q K^T / sqrt(64)) V over qkv [B, N, 3, H, 64] (bf16) -> out [B, N, H*64] (bf16) (attention_sm100.cu)
 // lse2 (optional, training): [B, H, attention_lse_stride(N)] fp32, log2-domain log-sum-exp of the scaled scores
 int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st);
 inline int attention_lse_stride(int N) { return (N + 127) / 128 * 128; }
-// experiment (attention2_sm100.cu, DGS_ATT_TPR2=1): same contract, two softmax threads per query row
-int attention_fwd_tpr2(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st);
 // backward (attention_bwd_sm100.cu): dqkv [B, N, 3, H, 64] (bf16) from qkv, out (= O), lse2 and dout [B, N, H*64] (bf16);
 // dsum = scratch [B, H, attention_lse_stride(N)] fp32.  Fills the pad entries of lse2 (+inf) as a side effect.
 int attention_bwd(const void* qkv, const void* out, const void* dout, float* lse2, float* dsum, void* dqkv, int B, int N,
@@ -111,7 +107,7 @@ int tiny_linear_bwd(const float* dy, const float* W, const __nv_bfloat16* h3, __
                     int N, int K, cudaStream_t st);
 int pos_embed_bwd(const float* dx, float* dpos, int B, int G, int N, int D, cudaStream_t st);
 int adamw_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps, float wd,
-               int step, float grad_scale, const float* grad_scale_dev, cudaStream_t st);
+               int step, float grad_scale, const float* grad_scale_dev, cudaStream_t st, float* ema = nullptr, float ema_decay = 0.f);
 int cast_transpose_f32(const float* in, long long in_bstride, int batch, int M, int C, __nv_bfloat16* out_rm,
                        __nv_bfloat16* outT, cudaStream_t st);
 

@@ -351,7 +351,8 @@ __global__ void __launch_bounds__(256) gaussians_epilogue_kernel(const float* __
     const float m = (a[0] + a[1] + a[2]) / 3.0f;
     const float sg = 1.0f / (1.0f + expf(-m));
     float t;
-    if (scene) t = sg * (far_ - near_) + near_;                       // denoiser_scene.py:263,406-410
+    if (scene == 1) t = sg * (far_ - near_) + near_;                  // denoiser_scene.py:263,406-410
+    else if (scene == 2) t = sg;                                      // denoiser.py:381-388 with ray_pe_type == 'plk'
     else t = (2.0f * sg - 1.0f) * 1.8f + (-o0 * d0 + -o1 * d1 + -o2 * d2);  // denoiser.py:382-392
     xyz[0] = o0 + t * d0; xyz[1] = o1 + t * d1; xyz[2] = o2 + t * d2;
     if (out.img_aligned_xyz) {

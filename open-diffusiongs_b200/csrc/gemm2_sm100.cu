@@ -102,7 +102,7 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 // splits > 1 (split-K, fp32 TMA reduce-add epilogue only): work unit u = (tile u % num_tiles, K range u / num_tiles);
 // every unit adds its partial product into the (pre-zeroed) output.  Used by the weight-gradient GEMMs, whose K = tokens is
 // long and whose 256 x 256 output tiles are too few to fill 74 clusters (proj: 16 tiles).
-// UNI (experiment, DGS_GEMM_UNI=1): the TMA-producer and MMA-issuer warps run converged and issue under elect.sync instead of
+// UNI (default; DGS_GEMM_UNI=0 selects the old path): the TMA-producer and MMA-issuer warps run converged and issue under elect.sync instead of
 // `lane == 0` (elect_one_sync in sm100_ptx.cuh): without it ptxas wraps every TMA / tcgen05 instruction of those roles in an
 // ELECT / BRA.U.ANY serialisation loop with R2UR operand moves (99 such loops in this file's kernels).
 template <int EPI, bool MN, int TMAEPI, bool UNI = false>
@@ -268,7 +268,7 @@ static int launch_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     DGS_CUDA_OK(cudaFuncSetAttribute(g2::gemm_bf16_2cta_kernel<EPI, MN, TMAEPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     DGS_CUDA_OK(cudaFuncSetAttribute(g2::gemm_bf16_2cta_kernel<EPI, MN, TMAEPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const char* eu = getenv("DGS_GEMM_UNI");
-    uni = (eu && eu[0] == '1') ? 1 : 0;
+    uni = (eu && eu[0] == '0') ? 0 : 1;  // default since round 2 (measured: r2 first GPU call)
     configured = true;
   }
   auto kern = uni ? g2::gemm_bf16_2cta_kernel<EPI, MN, TMAEPI, true> : g2::gemm_bf16_2cta_kernel<EPI, MN, TMAEPI, false>;

@@ -262,13 +262,6 @@ int gemm_bf16(const void* A, const void* W, int M, int N, int K, int epi, const 
     use_2cta = (e && e[0] == '0') ? 0 : 1;
   }
   if (use_2cta && N % 256 == 0 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_2cta(A, W, M, N, K, epi, ep, st);
-  // 256 x 256 single-CTA tiles (gemm3_sm100.cu, 1.5x less operand traffic per FLOP): DGS_GEMM_M256=1
-  static int use_m256 = -1;
-  if (use_m256 < 0) {
-    const char* e = getenv("DGS_GEMM_M256");
-    use_m256 = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (use_m256 && epi != EPI_DGELU_BF16 && !ep.lda && !ep.ldb && N % 256 == 0 && M >= 256 && ceil_div(M, 256) * (N / 256) >= 48) return gemm_bf16_m256(A, W, M, N, K, epi, ep, st);
   // wide tiles when they still fill the machine, else 128-wide tiles for more CTAs
   static int wide_min = -1;
   if (wide_min < 0) {

@@ -687,6 +687,23 @@ __device__ __forceinline__ float ex2_mufu(float x) {
   return y;
 }
 
+// Fused image loss (LossComputer.forward's l2 term, diffusionGS/utils/losses.py:280-284): the blend
+// forward accumulates sum (render - target)^2 per sample while the pixel is still in registers, and the blend backward
+// forms dL/dpix = [upstream gradient image] + coef[sample] * (render - target) itself, so the MSE never materialises a
+// per-element loss or gradient image.  target [NV, tc, H, W] (tc = 3, or 4 = rgb + mask whose plane is skipped,
+// losses.py:274-276).
+struct MseFwd {
+  const float* target = nullptr;
+  int tc = 3;
+  double* loss = nullptr;  // [samples]
+};
+struct MseBwd {
+  const float* target = nullptr;
+  int tc = 3;
+  const float* images = nullptr;  // the forward's output [NV,3,H,W]
+  const float* coef = nullptr;    // [samples] device
+};
+
 // ---------------------------------------------------------------------------------------------
 // K6: per-tile front-to-back alpha blend (forward.cu:261-374), one CTA per (view, tile)
 // ---------------------------------------------------------------------------------------------
@@ -695,7 +712,7 @@ __device__ __forceinline__ float ex2_mufu(float x) {
 template <int MODE>
 __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, GeomState gs, ImgState im,
                                                                  const uint32_t* __restrict__ point_list,
-                                                                 float* __restrict__ out_color) {
+                                                                 float* __restrict__ out_color, MseFwd mse) {
   const int tile_g = blockIdx.x;
   const int view = tile_g / pb.tiles, tile = tile_g - view * pb.tiles;
   const int tx = tile % pb.gx, ty = tile / pb.gx;
@@ -757,13 +774,14 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, Geo
       last = ok ? contributor : last;
     }
   }
+  int unfinished = 0;
   if (MODE == 1) {
     // a pixel that ran out of phase-A entries without saturating must continue in phase B
     if (inside) {
       im.acc[pix_g] = make_float4(C0, C1, C2, T);
       im.contrib[pix_g] = contributor | (done ? 0x80000000u : 0u);
     }
-    const int unfinished = __syncthreads_or(!done);
+    unfinished = __syncthreads_or(!done);
     if (threadIdx.x == 0) {
       im.tile_open[tile_g] = unfinished ? 1u : 0u;
       if (unfinished) atomicAdd(gs.totals + 2, 1u);
@@ -779,6 +797,28 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, Geo
     oc[pid] = C0 + T * pb.bg[0];
     oc[plane + pid] = C1 + T * pb.bg[1];
     oc[2 * plane + pid] = C2 + T * pb.bg[2];
+  }
+  if (mse.target) {
+    // every pixel's FINAL colour is counted exactly once: phase A counts the tiles it finished, phase B the open ones
+    const bool count = MODE == 0 ? true : MODE == 1 ? !unfinished : (im.tile_open[tile_g] != 0u);
+    float e = 0.f;
+    if (inside && count) {
+      const size_t plane = (size_t)pb.W * pb.H, pid = (size_t)y * pb.W + x;
+      const float* t = mse.target + (size_t)view * mse.tc * plane + pid;
+      const float d0 = (C0 + T * pb.bg[0]) - t[0], d1 = (C1 + T * pb.bg[1]) - t[plane], d2 = (C2 + T * pb.bg[2]) - t[2 * plane];
+      e = d0 * d0 + d1 * d1 + d2 * d2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    __shared__ float s_loss[TILE_PIX / 32];
+    if ((threadIdx.x & 31) == 0) s_loss[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0 && count) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < TILE_PIX / 32; w++) tot += s_loss[w];
+      atomicAdd(mse.loss + view / pb.V, (double)tot);
+    }
   }
 }
 
@@ -800,7 +840,7 @@ constexpr int BWD_CHUNK = 64;  // Gaussians staged per round in the backward
 __global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(Problem pb, GeomState gs, ImgState im,
                                                                   const uint32_t* __restrict__ point_list,
                                                                   const uint32_t* __restrict__ point_list_b,
-                                                                  const float* __restrict__ dL_dpix,
+                                                                  const float* __restrict__ dL_dpix, MseBwd mse,
                                                                   float* __restrict__ dmean2D /*[N,3]*/,
                                                                   float* __restrict__ dconic /*[N,4]*/,
                                                                   float* __restrict__ dopac /*[N]*/,
@@ -830,8 +870,16 @@ __global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(Problem pb, Ge
   const uint32_t last = inside ? im.n_contrib[ibase + pid] : 0u;
   float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
   if (inside) {
-    const float* d = dL_dpix + 3 * ibase;
-    dp0 = d[pid]; dp1 = d[plane + pid]; dp2 = d[2 * plane + pid];
+    if (dL_dpix) {
+      const float* d = dL_dpix + 3 * ibase;
+      dp0 = d[pid]; dp1 = d[plane + pid]; dp2 = d[2 * plane + pid];
+    }
+    if (mse.target) {  // + coef[sample] * (render - target): the MSE gradient, never stored as an image
+      const float k = mse.coef[view / pb.V];
+      const float* c = mse.images + 3 * ibase + pid;
+      const float* t = mse.target + (size_t)view * mse.tc * plane + pid;
+      dp0 = fmaf(k, c[0] - t[0], dp0); dp1 = fmaf(k, c[plane] - t[plane], dp1); dp2 = fmaf(k, c[2 * plane] - t[2 * plane], dp2);
+    }
   }
   if (threadIdx.x == 0) s_max = 0;
   __syncthreads();
@@ -1208,7 +1256,7 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
                        const float* proj, const float* campos, float tanx, float tany, dgs_alloc_fn geom_alloc,
                        void* geom_user, dgs_alloc_fn bin_alloc, void* bin_user, dgs_alloc_fn img_alloc,
                        void* img_user, float* out_color, int* radii, long long* R_out, long long chunk_R[2],
-                       cudaStream_t st, int debug) {
+                       cudaStream_t st, int debug, MseFwd mse = MseFwd()) {
   const size_t N = (size_t)pb.NV * pb.P;
   DGS_REQUIRE(N < (size_t)INT32_MAX, "n_views * P = %zu does not fit the 32-bit scan", N);
   size_t gbytes = 0, ibytes = 0;
@@ -1306,7 +1354,7 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
     int rc = bin_pass(R, 0, 0, pb.P, im.ranges, &bsa);
     if (rc) return rc;
     ProfScope ps(st, PROF_RASTER_BLEND_FWD);
-    blend_forward_kernel<0><<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bsa.point_list, out_color);
+    blend_forward_kernel<0><<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bsa.point_list, out_color, mse);
     DGS_LAUNCH_OK(st, debug);
     return DGS_OK;
   }
@@ -1316,7 +1364,7 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
     int rc = bin_pass(RA, 1, 0, Pn, im.ranges, &bsa);
     if (rc) return rc;
     ProfScope ps(st, PROF_RASTER_BLEND_FWD);
-    blend_forward_kernel<1><<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bsa.point_list, out_color);
+    blend_forward_kernel<1><<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bsa.point_list, out_color, mse);
     DGS_LAUNCH_OK(st, debug);
   }
   uint32_t unfinished = 0;
@@ -1363,7 +1411,7 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
     }
     chunk_R[1] = RBo;
     ProfScope ps(st, PROF_RASTER_BLEND_FWD);
-    blend_forward_kernel<2><<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bsb.point_list, out_color);
+    blend_forward_kernel<2><<<(unsigned)ntiles, TILE_PIX, 0, st>>>(pb, gs, im, bsb.point_list, out_color, mse);
     DGS_LAUNCH_OK(st, debug);
   }
   return DGS_OK;
@@ -1464,7 +1512,7 @@ int dgs_raster_backward(const dgs_raster_args* a, int R, const int* radii, const
   ImgState im = ImgState::carve(const_cast<void*>(image_buffer), 1, a->W, a->H, nullptr);
   BinState bs = BinState::carve(const_cast<void*>(binning_buffer), R, nullptr);
   if (R > 0) {
-    blend_backward_kernel<<<pb.tiles, TILE_PIX, 0, st>>>(pb, gs, im, bs.point_list, nullptr, dL_dpix, dL_dmean2D,
+    blend_backward_kernel<<<pb.tiles, TILE_PIX, 0, st>>>(pb, gs, im, bs.point_list, nullptr, dL_dpix, MseBwd(), dL_dmean2D,
                                                           dL_dconic, dL_dopacity, dL_dcolor);
     DGS_LAUNCH_OK(st, a->debug);
   }
@@ -1508,14 +1556,28 @@ int dgs_render_batch_forward(const dgs_render_batch_args* a, dgs_alloc_fn geom_a
                              dgs_alloc_fn bin_alloc, void* bin_user, dgs_alloc_fn img_alloc, void* img_user,
                              float* out_images, long long* num_rendered, long long* chunk_instances,
                              void* stream) {
+  return dgs_render_batch_forward_mse(a, geom_alloc, geom_user, bin_alloc, bin_user, img_alloc, img_user, out_images,
+                                      num_rendered, chunk_instances, nullptr, stream);
+}
+
+int dgs_render_batch_forward_mse(const dgs_render_batch_args* a, dgs_alloc_fn geom_alloc, void* geom_user,
+                                 dgs_alloc_fn bin_alloc, void* bin_user, dgs_alloc_fn img_alloc, void* img_user,
+                                 float* out_images, long long* num_rendered, long long* chunk_instances,
+                                 const dgs_render_mse* mse, void* stream) {
   int rc = check_batch_args(a);
   if (rc) return rc;
   DGS_REQUIRE(geom_alloc && bin_alloc && img_alloc && out_images && num_rendered && chunk_instances,
               "NULL output/allocator");
+  MseFwd mf;
+  if (mse) {
+    DGS_REQUIRE(mse->target && mse->loss_sum && (mse->target_channels == 3 || mse->target_channels == 4),
+                "mse: target / loss_sum NULL or target_channels not 3|4");
+    mf.target = mse->target; mf.tc = mse->target_channels; mf.loss = mse->loss_sum;
+  }
   Problem pb = batch_problem(a);
   return run_forward(pb, true, a->c2w, a->fxfycxcy, nullptr, nullptr, nullptr, 0.f, 0.f, geom_alloc, geom_user,
                      bin_alloc, bin_user, img_alloc, img_user, out_images, nullptr, num_rendered, chunk_instances,
-                     (cudaStream_t)stream, a->debug);
+                     (cudaStream_t)stream, a->debug, mf);
 }
 
 int dgs_render_batch_backward(const dgs_render_batch_args* a, long long R, const long long* chunk_instances,
@@ -1523,10 +1585,27 @@ int dgs_render_batch_backward(const dgs_render_batch_args* a, long long R, const
                               const void* image_buffer, const float* dL_dimages,
                               float* d_xyz, float* d_features, float* d_scaling, float* d_rotation,
                               float* d_opacity, dgs_alloc_fn scratch_alloc, void* scratch_user, void* stream) {
+  DGS_REQUIRE(dL_dimages, "NULL state buffer");
+  return dgs_render_batch_backward_mse(a, R, chunk_instances, geom_buffer, binning_buffer, binning_buffer_b, image_buffer,
+                                       dL_dimages, nullptr, d_xyz, d_features, d_scaling, d_rotation, d_opacity,
+                                       scratch_alloc, scratch_user, stream);
+}
+
+int dgs_render_batch_backward_mse(const dgs_render_batch_args* a, long long R, const long long* chunk_instances,
+                                  const void* geom_buffer, const void* binning_buffer, const void* binning_buffer_b,
+                                  const void* image_buffer, const float* dL_dimages, const dgs_render_mse* mse,
+                                  float* d_xyz, float* d_features, float* d_scaling, float* d_rotation,
+                                  float* d_opacity, dgs_alloc_fn scratch_alloc, void* scratch_user, void* stream) {
   int rc = check_batch_args(a);
   if (rc) return rc;
-  DGS_REQUIRE(geom_buffer && binning_buffer && image_buffer && dL_dimages && scratch_alloc && chunk_instances,
+  DGS_REQUIRE(geom_buffer && binning_buffer && image_buffer && (dL_dimages || mse) && scratch_alloc && chunk_instances,
               "NULL state buffer");
+  MseBwd mb;
+  if (mse) {
+    DGS_REQUIRE(mse->target && mse->coef && mse->images && (mse->target_channels == 3 || mse->target_channels == 4),
+                "mse: target / coef / images NULL or target_channels not 3|4");
+    mb.target = mse->target; mb.tc = mse->target_channels; mb.images = mse->images; mb.coef = mse->coef;
+  }
   DGS_REQUIRE(chunk_instances[1] == 0 || binning_buffer_b, "phase-B binning buffer missing");
   DGS_REQUIRE(d_xyz && d_features && d_scaling && d_rotation && d_opacity, "NULL gradient buffer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1553,7 +1632,7 @@ int dgs_render_batch_backward(const dgs_render_batch_args* a, long long R, const
   if (R > 0) {
     ProfScope ps(st, PROF_RASTER_BLEND_BWD);
     blend_backward_kernel<<<(unsigned)((size_t)pb.NV * pb.tiles), TILE_PIX, 0, st>>>(
-        pb, gs, im, bs.point_list, list_b, dL_dimages, dmean2D, dconic, dopac, dcolor);
+        pb, gs, im, bs.point_list, list_b, dL_dimages, mb, dmean2D, dconic, dopac, dcolor);
     DGS_LAUNCH_OK(st, a->debug);
   }
   GeomGradOut out;

@@ -39,7 +39,19 @@ class DitIO(C.Structure):
     _fields_ = [("B", C.c_int), ("V", C.c_int), ("H", C.c_int), ("W", C.c_int), ("plucker_mode", C.c_int),
                 ("scene_depth", C.c_int), ("range_near", C.c_float), ("range_far", C.c_float)] + [
         (n, C.c_void_p) for n in ("images", "ray_o", "ray_d", "t", "xyz", "features", "scaling", "rotation",
-                                  "opacity", "img_aligned_xyz", "tokens_out", "train_state")]
+                                  "opacity", "img_aligned_xyz", "tokens_out", "train_state")] + [("train_mode", C.c_int)]
+
+
+TRAIN_STORE, TRAIN_RECOMPUTE = 0, 1  # dgs_dit_io.train_mode
+
+
+class DitBwdOpts(C.Structure):  # dgs_dit_bwd_opts
+    _fields_ = [("block_done", C.POINTER(C.c_void_p))]
+
+
+class RenderMse(C.Structure):  # dgs_render_mse
+    _fields_ = [("target", C.c_void_p), ("target_channels", C.c_int), ("loss_sum", C.c_void_p), ("coef", C.c_void_p),
+                ("images", C.c_void_p)]
 
 
 GRAD_FIELDS_A = ("tokenizer_w", "pos_embed", "in_ln_w", "t0_w", "t0_b", "t2_w", "t2_b")
@@ -105,6 +117,21 @@ def lib():
         L.dgs_dit_train_state_bytes.argtypes = [C.POINTER(DitWeights), C.c_int, C.c_int, C.c_int, C.c_int]
         L.dgs_dit_backward.argtypes = [C.POINTER(DitWeights), C.POINTER(DitWeightsT), C.POINTER(DitIO),
                                        C.POINTER(DitOutGrads), C.POINTER(DitGrads), vp, C.c_size_t, vp]
+        L.dgs_dit_train_state_bytes_ex.restype = C.c_size_t
+        L.dgs_dit_train_state_bytes_ex.argtypes = [C.POINTER(DitWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.dgs_dit_backward_ex.argtypes = [C.POINTER(DitWeights), C.POINTER(DitWeightsT), C.POINTER(DitIO),
+                                          C.POINTER(DitOutGrads), C.POINTER(DitGrads), C.POINTER(DitBwdOpts), vp,
+                                          C.c_size_t, vp]
+        L.dgs_event_create.argtypes = [C.POINTER(C.c_void_p)]
+        L.dgs_event_destroy.argtypes = [vp]
+        L.dgs_stream_wait_event.argtypes = [vp, vp]
+        L.dgs_adamw_ema_step.argtypes = [vp, vp, vp, vp, vp, C.c_size_t] + [C.c_float] * 5 + [C.c_int, C.c_float, vp,
+                                                                                               C.c_float, vp]
+        L.dgs_render_batch_forward_mse.argtypes = [C.POINTER(RenderBatchArgs), ALLOC_FN, vp, ALLOC_FN, vp, ALLOC_FN, vp, vp,
+                                                   C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                                   C.POINTER(RenderMse), vp]
+        L.dgs_render_batch_backward_mse.argtypes = [C.POINTER(RenderBatchArgs), C.c_longlong, C.POINTER(C.c_longlong)] + \
+            [vp] * 5 + [C.POINTER(RenderMse)] + [vp] * 5 + [ALLOC_FN, vp, vp]
         L.dgs_transpose_bf16.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
         L.dgs_adamw_step.argtypes = [vp, vp, vp, vp, C.c_size_t] + [C.c_float] * 5 + [C.c_int, C.c_float, vp, vp]
         L.dgs_cast_transpose_f32.argtypes = [vp, C.c_longlong, C.c_int, C.c_int, C.c_int, vp, vp, vp]
@@ -151,4 +178,6 @@ EXPORTED = [  # every symbol include/dgs_b200.h declares (checked by tests/test_
     "dgs_rays_from_cameras", "dgs_q_sample", "dgs_p_sample_step",
     "dgs_dit_train_state_bytes", "dgs_dit_backward", "dgs_transpose_bf16", "dgs_adamw_step", "dgs_attention_fwd_train",
     "dgs_attention_bwd", "dgs_gemm_bf16_ex", "dgs_ln_modulate_bwd", "dgs_gate_bwd", "dgs_cast_transpose_f32", "dgs_gemm_bf16_tn",
+    "dgs_dit_train_state_bytes_ex", "dgs_dit_backward_ex", "dgs_event_create", "dgs_event_destroy", "dgs_stream_wait_event",
+    "dgs_adamw_ema_step", "dgs_render_batch_forward_mse", "dgs_render_batch_backward_mse",
 ]

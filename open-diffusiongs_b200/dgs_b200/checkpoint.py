@@ -52,8 +52,8 @@ def extract_denoiser_state_dict(obj):
 def load_checkpoint(model, path_or_obj, strict=True, map_location="cpu"):
     """Load any of the three layouts into a `DGSDenoiser[Scene]`; returns the meta dict (epoch / global_step).
     Tensors are cast to the parameters' dtype (released checkpoints are fp16/bf16, the master weights here are fp32)."""
-    obj = torch.load(path_or_obj, map_location=map_location, weights_only=False) if isinstance(path_or_obj, (str, bytes)) \
-        or hasattr(path_or_obj, "__fspath__") else path_or_obj
+    obj = path_or_obj if isinstance(path_or_obj, dict) else torch.load(path_or_obj, map_location=map_location,
+                                                                        weights_only=False)  # path, PathLike or file object
     sd, meta, _ = extract_denoiser_state_dict(obj)
     own = model.state_dict()
     sd = {k: (v.to(own[k].dtype) if k in own and torch.is_tensor(v) else v) for k, v in sd.items()}
@@ -61,8 +61,9 @@ def load_checkpoint(model, path_or_obj, strict=True, map_location="cpu"):
     if strict and (missing or unexpected):
         raise RuntimeError(f"checkpoint does not match the denoiser: missing {sorted(missing)[:8]} unexpected {sorted(unexpected)[:8]}")
     if getattr(model, "_trainer", None) is not None:   # flat fp32 master arena + bf16 GEMM operands follow the new values
-        model._trainer.refresh_weights()
-    model._packed = None
+        model._trainer.refresh_weights()               # (updates the packed stacks in place and re-keys them)
+    else:
+        model._packed = None                           # inference-only model: repack lazily on the next forward
     return meta
 
 
@@ -82,6 +83,26 @@ def system_checkpoint(model, epoch=0, global_step=0, extra_state_dict=None):
 def save_system_checkpoint(model, path, epoch=0, global_step=0, extra_state_dict=None):
     torch.save(system_checkpoint(model, epoch, global_step, extra_state_dict), path)
     return path
+
+
+def ema_checkpoint_path(path):
+    """EMAModelCheckpoint._ema_format_filepath (diffusionGS/utils/ema.py:205-206): "x.ckpt" -> "x-EMA.ckpt"."""
+    path = str(path)
+    return path.replace(".ckpt", "-EMA.ckpt") if ".ckpt" in path else path + "-EMA"
+
+
+def save_ema_checkpoint(trainer, path, epoch=0, global_step=0, extra_state_dict=None):
+    """What EMAModelCheckpoint._save_checkpoint adds next to every checkpoint (ema.py:191-203): the same Lightning layout
+    with the EMA weights in place of the trained ones, written to "<name>-EMA.ckpt".  `path` is the REGULAR checkpoint's
+    path; returns the EMA file's path."""
+    sd = {SYSTEM_PREFIX + k: v.detach().cpu().clone() for k, v in trainer.ema_state_dict().items()}
+    for k, v in trainer.model.state_dict().items():  # non-parameter entries (none today) keep their live values
+        sd.setdefault(SYSTEM_PREFIX + k, v.detach().cpu().clone())
+    if extra_state_dict:
+        sd.update(extra_state_dict)
+    out = ema_checkpoint_path(path)
+    torch.save({"state_dict": sd, "epoch": int(epoch), "global_step": int(global_step)}, out)
+    return out
 
 
 def module_weights(path_or_obj, module_name="shape_model", map_location="cpu"):

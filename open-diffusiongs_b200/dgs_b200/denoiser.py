@@ -39,11 +39,16 @@ class AttrDict(dict):
     __setattr__ = dict.__setitem__
 
 
-_DEFAULTS = dict(pretrained_model_name_or_path="", use_downsample=False, num_latents=256, width=1024, in_channels=3,
+_DEFAULTS = dict(pretrained_model_name_or_path="", use_downsample=False, num_latents=256, width=1024, in_channels=9,
                  patch_size=16, n_gaussians=2, dim_heads=64, num_layers=24, ray_pe_type="relative_plk",
                  hard_pixelalign=True, clip_xyz=True, gaussians_sh_degree=0, use_gssplat=False,
                  prior_distribution="gaussian", use_flash=False, use_checkpoint=True, grad_checkpoint_every=1,
-                 range_setting_type="sigmoid", range_setting_near=0.0, range_setting_far=500.0)
+                 range_setting_type="linear_depth", range_setting_near=0.0, range_setting_far=500.0)
+# in_channels: the reference class default is 3 (denoiser.py:181) but its tokenizer is
+# Linear(in_channels * patch^2, width) fed with the 9-channel posed image (rgb + 6 Pluecker), so only in_channels == 9
+# -- what every shipped yaml sets (configs/*.yaml "in_channels: 9 #rgb+plucker") -- can run; 9 is the default here and
+# anything else is rejected.  range_setting_type is carried for config compatibility only: the reference's range_func
+# is sigmoid(t)*(far-near)+near whatever it says (denoiser_scene.py:263).
 
 
 def _cfg(cfg):
@@ -107,13 +112,18 @@ class DGSDenoiser(nn.Module):
         super().__init__()
         self.cfg = c = _cfg(cfg)
         w = c.width
+        if c.in_channels != 9:
+            raise ValueError(f"in_channels={c.in_channels}: the tokenizer consumes the 9-channel posed image (rgb + Pluecker); "
+                             "every shipped reference config sets in_channels: 9")
+        if c.ray_pe_type not in ("relative_plk", "plk"):
+            raise ValueError(f"ray_pe_type={c.ray_pe_type!r} (expected 'relative_plk' or 'plk')")
         if c.gaussians_sh_degree != 0:
             raise NotImplementedError("the DiT heads are built for gaussians_sh_degree == 0 (every shipped config)")
         self.t_embedder = _TEmbedParams(w)
         nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)
         nn.init.normal_(self.t_embedder.mlp[2].weight, std=0.02)
         self.image_tokenizer = nn.Sequential(nn.Identity(),
-                                             nn.Linear(3 * c.in_channels * c.patch_size ** 2, w, bias=False))
+                                             nn.Linear(c.in_channels * c.patch_size ** 2, w, bias=False))  # denoiser.py:216-221
         self.image_tokenizer.apply(_init_linear)
         shape = (1, c.n_gaussians, w) if self.SCENE else (c.n_gaussians, w)
         self.gaussians_pos_embedding = nn.Parameter(torch.randn(*shape))
@@ -180,6 +190,7 @@ class DGSDenoiser(nn.Module):
         c = self.cfg
         w = DitWeights(width=c.width, heads=c.width // c.dim_heads, layers=c.num_layers, patch=c.patch_size,
                        n_gaussians=c.n_gaussians, mlp_hidden=4 * c.width)
+        assert tuple(self.image_tokenizer[1].weight.shape) == (c.width, 9 * c.patch_size ** 2), "tokenizer weight shape"
         for k, v in t.items():
             setattr(w, k, v.data_ptr())
         self._packed, self._packed_key = (w, t), key
@@ -210,7 +221,7 @@ class DGSDenoiser(nn.Module):
                 img_xyz = img_xyz.clamp(-1.0, 1.0)
         return (out, img_xyz, tokens) if return_tokens else (out, img_xyz)
 
-    def _run_dit(self, images, ray_o, ray_d, t, return_tokens=False, train_state=None):
+    def _run_dit(self, images, ray_o, ray_d, t, return_tokens=False, train_state=None, train_mode=0):
         dev = self.device
         if dev.type != "cuda":
             raise _lib.DgsError("DGSDenoiser runs on a CUDA device only (no CPU / PyTorch fallback)")
@@ -236,13 +247,13 @@ class DGSDenoiser(nn.Module):
             if ws is None or ws.numel() < nbytes or ws.device != dev:
                 ws = self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             io = DitIO(B=B, V=V, H=H, W=W, plucker_mode=0 if c.ray_pe_type == "relative_plk" else 1,
-                       scene_depth=1 if self.SCENE else 0, range_near=float(c.range_setting_near),
+                       scene_depth=1 if self.SCENE else (0 if c.ray_pe_type == "relative_plk" else 2), range_near=float(c.range_setting_near),
                        range_far=float(c.range_setting_far), images=images.data_ptr(), ray_o=ray_o.data_ptr(),
                        ray_d=ray_d.data_ptr(), t=tf.data_ptr(), xyz=out.xyz.data_ptr(),
                        features=out.features.data_ptr(), scaling=out.scaling.data_ptr(),
                        rotation=out.rotation.data_ptr(), opacity=out.opacity.data_ptr(),
                        img_aligned_xyz=img_xyz.data_ptr(), tokens_out=None if tokens is None else tokens.data_ptr(),
-                       train_state=None if train_state is None else train_state.data_ptr())
+                       train_state=None if train_state is None else train_state.data_ptr(), train_mode=int(train_mode))
             check(L.dgs_dit_forward(C.byref(w), C.byref(io), ws.data_ptr(), nbytes,
                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         keep = (io, ws, nbytes, images, ray_o, ray_d, tf, w, _keep)  # what a later dgs_dit_backward needs alive

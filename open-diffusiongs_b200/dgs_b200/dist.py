@@ -87,24 +87,50 @@ class GradArena:
                      key=lambda k: -int(k.split(".")[1].split("#")[0]))
         return blk + [k for k in self.buckets if not k.startswith("transformer.")]
 
-    def allreduce_mean_(self, group=None):
-        """sum over ranks / world, bucket by bucket in reverse order; async on a side stream on GPUs."""
+    def bucket_block(self, name):
+        """transformer block index of a bucket name, None for the non-block buckets."""
+        return int(name.split(".")[1].split("#")[0]) if name.startswith("transformer.") else None
+
+    def allreduce_issue_(self, group=None, gate=None, sync_main=True):
+        """Enqueue the SUM all-reduce of every bucket in reverse order on the side stream and return at once.
+        `gate(block_index_or_None)` is called (with the side stream current) right before a bucket's collective is
+        enqueued: the overlapped training step passes a function that makes the side stream wait on the event the
+        backward records when that block's gradients are final (dgs_dit_backward_ex / dgs_stream_wait_event), so bucket l
+        travels over NVLink while blocks l-1 .. 0 are still being differentiated -- what torch DDP's autograd hooks do for
+        the reference (diffusionGS_rel.yaml:80).  sync_main: the side stream first waits for everything already enqueued on
+        the current stream (the un-overlapped form: the whole backward)."""
         world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._works, self._world = [], world
         if world == 1:
             return self
-        works = []
-        if self._stream is not None:
+        if self._stream is not None and sync_main:
             self._stream.wait_stream(torch.cuda.current_stream(self.flat.device))
         ctx = torch.cuda.stream(self._stream) if self._stream is not None else _null()
         with ctx:
             for k in self.reverse_bucket_order():
+                if gate is not None:
+                    gate(self.bucket_block(k))
                 a, b = self.buckets[k]
-                works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True))
-            for w in works:
-                w.wait()
+                self._works.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True))
+        return self
+
+    def allreduce_wait_(self, scale=True):
+        """Make the current stream wait for the collectives of allreduce_issue_; scale=True divides by the world size
+        here, scale=False leaves the SUM in the arena and returns 1/world for the consumer to fold in (the fused AdamW
+        takes it as its gradient scale, saving a pass over 1.8 GB)."""
+        works, world = getattr(self, "_works", []), getattr(self, "_world", 1)
+        for w in works:
+            w.wait()
+        self._works = []
+        if world > 1 and scale:
             self.flat.mul_(1.0 / world)
-        if self._stream is not None:
-            torch.cuda.current_stream(self.flat.device).wait_stream(self._stream)
+            return 1.0
+        return 1.0 / world if world > 1 else 1.0
+
+    def allreduce_mean_(self, group=None):
+        """sum over ranks / world, bucket by bucket in reverse order; async on a side stream on GPUs."""
+        self.allreduce_issue_(group)
+        self.allreduce_wait_(scale=True)
         return self
 
     def clip_grad_norm_(self, max_norm: float, eps: float = 1e-6) -> torch.Tensor:

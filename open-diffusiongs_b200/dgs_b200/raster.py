@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ALLOC_FN, DgsError, RasterArgs, RenderBatchArgs, check
+from ._lib import ALLOC_FN, DgsError, RasterArgs, RenderBatchArgs, RenderMse, check
 
 
 LAST_NUM_RENDERED = None  # instance count R of the most recent batched forward (bench/roofline bookkeeping)
@@ -170,14 +170,16 @@ def _batch_args(xyz, features, scaling, rotation, opacity, C2W, fxfycxcy, H, W, 
 
 
 def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, fxfycxcy, scale_modifier=None,
-                         arena_cache=None, near_log2=None):
-    """All (sample, view) pairs in one launch set -> (images [B,V,3,H,W] fp32, state).  When the batch holds more than
+                         arena_cache=None, near_log2=None, mse_target=None, mse_loss_sum=None):
+    """All (sample, view) pairs in one launch set -> (images [B,V,3,H,W] fp32, state).
+    mse_target [B,V,3|4,H,W] + mse_loss_sum (fp64 [B], zeroed by the caller): the blend kernel also adds
+    sum (render - target)^2 of every sample into mse_loss_sum (dgs_render_batch_forward_mse).  When the batch holds more than
     2^31-1 instances (e.g. a random-init denoiser at 512x512: ~6e8 per view) the views are rendered in halves,
     recursively -- the reference renders one view per call anyway (gs_core.py:990-1001); `state` then carries one
     sub-state per chunk and render_batch_backward sums the chunks' gradients."""
     try:
         return _render_batch_forward_one(xyz, features, scaling, rotation, opacity, H, W, C2W, fxfycxcy, scale_modifier,
-                                         arena_cache, near_log2)
+                                         arena_cache, near_log2, mse_target, mse_loss_sum)
     except DgsError as e:
         V = C2W.shape[1]
         if "exceeds 2^31-1" not in str(e) or V < 2:
@@ -186,8 +188,11 @@ def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, f
     outs, subs, total = [], [], 0
     for ci, (v0, v1) in enumerate(((0, V // 2), (V // 2, V))):
         sub_cache = None if arena_cache is None else arena_cache.setdefault(("views", ci), {})
+        if mse_loss_sum is not None and ci == 0:
+            mse_loss_sum.zero_()  # the failed whole-batch attempt may have counted some tiles already
         o, st = render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W[:, v0:v1].contiguous(),
-                                     fxfycxcy[:, v0:v1].contiguous(), scale_modifier, sub_cache, near_log2)
+                                     fxfycxcy[:, v0:v1].contiguous(), scale_modifier, sub_cache, near_log2,
+                                     None if mse_target is None else mse_target[:, v0:v1].contiguous(), mse_loss_sum)
         outs.append(o)
         subs.append((v0, v1, st))
         total += st["R"]
@@ -196,7 +201,7 @@ def render_batch_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, f
 
 
 def _render_batch_forward_one(xyz, features, scaling, rotation, opacity, H, W, C2W, fxfycxcy, scale_modifier=None,
-                              arena_cache=None, near_log2=None):
+                              arena_cache=None, near_log2=None, mse_target=None, mse_loss_sum=None):
     """One launch set over every (sample, view) pair.  `arena_cache` (a dict): re-use grow-only arenas across calls; the caller must not hand the same dict to another
     forward while this call's state is still needed (renderer.py keeps one dict for inference and a pool of dicts for
     differentiated forwards); stream order makes the re-use safe."""
@@ -211,37 +216,58 @@ def _render_batch_forward_one(xyz, features, scaling, rotation, opacity, H, W, C
         a = _batch_args(*tens, H, W, scale_modifier, near_log2=near_log2)
         R = C.c_longlong(0)
         chunks = (C.c_longlong * 2)(0, 0)
-        check(_lib.lib().dgs_render_batch_forward(C.byref(a), geom.cb, None, binning.cb, None, img.cb, None,
-                                                  out.data_ptr(), C.byref(R), chunks, _stream(dev)))
+        mse = None
+        if mse_target is not None:
+            mse_target = _f32c(mse_target)
+            if tuple(mse_target.shape) not in ((B, V, 3, int(H), int(W)), (B, V, 4, int(H), int(W))):
+                raise ValueError(f"mse target shape {tuple(mse_target.shape)} != [{B},{V},3|4,{H},{W}]")
+            if mse_loss_sum.dtype != torch.float64 or mse_loss_sum.numel() != B:
+                raise ValueError("mse_loss_sum must be a float64 tensor with one entry per sample")
+            mse = RenderMse(target=mse_target.data_ptr(), target_channels=mse_target.shape[2],
+                            loss_sum=mse_loss_sum.data_ptr(), coef=None, images=None)
+        check(_lib.lib().dgs_render_batch_forward_mse(C.byref(a), geom.cb, None, binning.cb, None, img.cb, None,
+                                                      out.data_ptr(), C.byref(R), chunks,
+                                                      None if mse is None else C.byref(mse), _stream(dev)))
     global LAST_NUM_RENDERED
     LAST_NUM_RENDERED = R.value
-    state = dict(tensors=tens, geom=geom.tensor, binning=binning.tensors[0],
+    state = dict(mse_target=mse_target, images=out if mse_target is not None else None, tensors=tens, geom=geom.tensor, binning=binning.tensors[0],
                  binning_b=binning.tensors[1] if len(binning.tensors) > 1 else None, img=img.tensor, R=R.value,
                  chunks=(int(chunks[0]), int(chunks[1])), H=int(H), W=int(W), scale_modifier=scale_modifier,
                  near_log2=near_log2)
     return out, state
 
 
-def render_batch_backward(state, grad_images, arena_cache=None):
-    """-> (d_xyz, d_features, d_scaling, d_rotation, d_opacity), re-using the forward's sorted lists."""
+def render_batch_backward(state, grad_images, arena_cache=None, mse_coef=None):
+    """-> (d_xyz, d_features, d_scaling, d_rotation, d_opacity), re-using the forward's sorted lists.
+    mse_coef (fp32 [B], device): dL/dpix += mse_coef[b] * (render - target) is formed inside the blend-backward kernel
+    (the forward must have been given mse_target); grad_images may then be None."""
     if "sub" in state:  # view-chunked forward: the per-Gaussian gradients are sums over views
         total = None
         for ci, (v0, v1, st) in enumerate(state["sub"]):
             sub_cache = None if arena_cache is None else arena_cache.setdefault(("views", ci), {})
-            g = render_batch_backward(st, grad_images[:, v0:v1], sub_cache)
+            g = render_batch_backward(st, None if grad_images is None else grad_images[:, v0:v1], sub_cache, mse_coef)
             total = g if total is None else tuple(a + b for a, b in zip(total, g))
         return total
     tens = state["tensors"]
     dev = tens[0].device
     g = _f32c(grad_images)
+    if g is None and mse_coef is None:
+        raise ValueError("render_batch_backward needs grad_images or mse_coef")
+    mse = None
+    if mse_coef is not None:
+        if state.get("mse_target") is None:
+            raise ValueError("mse_coef given but the forward ran without mse_target")
+        mse_coef = _f32c(mse_coef)
+        mse = RenderMse(target=state["mse_target"].data_ptr(), target_channels=state["mse_target"].shape[2], loss_sum=None,
+                        coef=mse_coef.data_ptr(), images=state["images"].data_ptr())
     with torch.cuda.device(dev):
         outs = [torch.empty_like(t) for t in tens[:5]]
         scratch = _Arena(dev, arena_cache, "bwd_scratch")
         a = _batch_args(*tens, state["H"], state["W"], state["scale_modifier"], near_log2=state["near_log2"])
         chunks = (C.c_longlong * 2)(*state["chunks"])
-        check(_lib.lib().dgs_render_batch_backward(
+        check(_lib.lib().dgs_render_batch_backward_mse(
             C.byref(a), state["R"], chunks, _ptr(state["geom"]), _ptr(state["binning"]), _ptr(state["binning_b"]),
-            _ptr(state["img"]), g.data_ptr(),
+            _ptr(state["img"]), None if g is None else g.data_ptr(), None if mse is None else C.byref(mse),
             outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), outs[4].data_ptr(),
             scratch.cb, None, _stream(dev)))
     return tuple(outs)

@@ -54,6 +54,52 @@ class BatchedGaussianRender(torch.autograd.Function):
         return (*grads, None, None, None, None, None, None, None)
 
 
+class BatchedGaussianRenderMSE(torch.autograd.Function):
+    """Render + the l2 term of LossComputer.forward (diffusionGS/utils/losses.py:261-284) as ONE node:
+    -> (images [b,v,3,H,W], l2_loss [b] = mean over (v,3,h,w) of (images - target[:, :, :3])^2).
+    The per-sample sums come out of the blend-forward kernel and the backward forms the MSE part of dL/dpix inside the
+    blend-backward kernel from (images, target, dL/dl2_loss) -- no per-element loss or gradient image."""
+
+    @staticmethod
+    def forward(ctx, xyz, features, scaling, rotation, opacity, height, width, C2W, fxfycxcy, target,
+                scaling_modifier=None, arena_cache=None):
+        ctx.set_materialize_grads(False)
+        needs_bwd = any(ctx.needs_input_grad[:5])
+        cache = None
+        if arena_cache is not None:
+            if needs_bwd:
+                pool = arena_cache.setdefault("pool", [])
+                cache = pool.pop() if pool else {}
+            else:
+                cache = arena_cache.setdefault("infer", {})
+        b, v = C2W.shape[0], C2W.shape[1]
+        with torch.no_grad():
+            loss_sum = torch.zeros(b, dtype=torch.float64, device=xyz.device)
+            images, state = _raster.render_batch_forward(xyz, features, scaling, rotation, opacity, height, width, C2W,
+                                                         fxfycxcy, scaling_modifier, arena_cache=cache,
+                                                         mse_target=target, mse_loss_sum=loss_sum)
+            n = v * 3 * int(height) * int(width)
+            l2 = (loss_sum / n).float()
+        ctx.state, ctx.n = state, n
+        ctx.pool = (arena_cache, cache) if needs_bwd and arena_cache is not None else None
+        ctx.in_dtypes = (xyz.dtype, features.dtype, scaling.dtype, rotation.dtype, opacity.dtype)
+        return images, l2
+
+    @staticmethod
+    def backward(ctx, g_images, g_l2):
+        cache = ctx.pool[1] if ctx.pool else None
+        if g_images is None and g_l2 is None:
+            raise RuntimeError("BatchedGaussianRenderMSE.backward without any upstream gradient")
+        coef = None if g_l2 is None else (g_l2.float() * (2.0 / ctx.n)).contiguous()
+        grads = _raster.render_batch_backward(ctx.state, g_images, arena_cache=cache, mse_coef=coef)
+        ctx.state = None
+        if ctx.pool:
+            ctx.pool[0]["pool"].append(cache)
+            ctx.pool = None
+        grads = tuple(g.to(dt) for g, dt in zip(grads, ctx.in_dtypes))
+        return (*grads, None, None, None, None, None, None, None)
+
+
 batched_gaussian_render = BatchedGaussianRender.apply
 deferred_gaussian_render = batched_gaussian_render  # reference name (gs_core.py:1064)
 
@@ -120,6 +166,16 @@ class Renderer(nn.Module):
         out = batched_gaussian_render(xyz, features, scaling, rotation, opacity, height, width, C2W, fxfycxcy,
                                       self.scaling_modifier, getattr(self.config, "use_gssplat", False),
                                       self._arena_cache)
+        self.last_num_rendered = _raster.LAST_NUM_RENDERED
+        return out
+
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward_mse(self, xyz, features, scaling, rotation, opacity, height, width, C2W, fxfycxcy, target):
+        """forward() + the image-space MSE of the training loss in the same launch set:
+        -> (renderings [b,v,3,H,W], l2_loss [b]) with l2_loss exactly LossComputer.forward's first output
+        (losses.py:261-284; target [b,v,3|4,H,W], a 4th mask channel is ignored as there)."""
+        out = BatchedGaussianRenderMSE.apply(xyz, features, scaling, rotation, opacity, height, width, C2W, fxfycxcy, target,
+                                             self.scaling_modifier, self._arena_cache)
         self.last_num_rendered = _raster.LAST_NUM_RENDERED
         return out
 

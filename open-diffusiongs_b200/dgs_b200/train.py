@@ -11,7 +11,11 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import DitGrads, DitOutGrads, DitWeightsT, check
+import contextlib
+
+import torch.distributed as dist
+
+from ._lib import DitBwdOpts, DitGrads, DitOutGrads, DitWeightsT, check
 from .dist import GradArena
 
 
@@ -25,11 +29,30 @@ class DitTrainer:
     * `master`: every parameter, fp32, in module.parameters() order; `p.data` are views of it;
     * `arena`:  the gradients in the same layout (dist.GradArena: `p.grad` are views; one bucket per block);
     * `exp_avg`, `exp_avg_sq`: AdamW moments, same layout -> the optimizer is ONE kernel over the whole model;
-    * bf16 / transposed-bf16 GEMM weights are re-derived from `master` after each step (refresh_weights)."""
+    * bf16 / transposed-bf16 GEMM weights are re-derived from `master` after each step (refresh_weights);
+    * `ema` (ema_decay given): NeMo-style EMA of the parameters (diffusionGS/utils/ema.py, decay 0.9999 in launch.py:227),
+      updated inside the AdamW kernel; `ema_state_dict` / `swap_ema_weights` / checkpoint.save_ema_checkpoint use it;
+    * recompute=True: the forward keeps only the residual stream entering each block and the backward re-runs each block
+      (the reference's per-block torch.utils.checkpoint, denoiser.py:348-354): 0.6 instead of 4 GB per sample;
+    * accumulate_grad_batches=k: k forward/backward pairs per optimizer step (Lightning's option of the same name); each
+      backward lands in the arena and is added to a second arena, the step uses their mean;
+    * overlap_allreduce: with torch.distributed initialised (world > 1) the per-block buckets are all-reduced on a side
+      stream WHILE the remaining blocks are still being differentiated (dgs_dit_backward_ex's block_done events).
 
-    def __init__(self, model, lr=1e-5, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.01, clip=0.5):
+    ONE training forward may be outstanding at a time (it owns the activation state and the workspace): a second
+    grad-enabled forward before the first one's backward, a second backward through the same forward, or an optimizer step
+    with a forward still pending raise instead of corrupting state."""
+
+    def __init__(self, model, lr=1e-5, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.01, clip=0.5, ema_decay=None,
+                 recompute=False, accumulate_grad_batches=1, overlap_allreduce=True):
         self.model = model
         self.lr, self.betas, self.eps, self.weight_decay, self.clip = lr, betas, eps, weight_decay, clip
+        if ema_decay is not None and not (0.0 <= ema_decay <= 1.0):
+            raise ValueError("EMA decay value must be between 0 and 1")  # ema.py:56-57
+        if accumulate_grad_batches < 1:
+            raise ValueError("accumulate_grad_batches must be >= 1")
+        self.ema_decay, self.recompute = ema_decay, bool(recompute)
+        self.accumulate, self.overlap = int(accumulate_grad_batches), bool(overlap_allreduce)
         params = [p for p in model.parameters()]
         dev = params[0].device
         if dev.type != "cuda":
@@ -46,8 +69,14 @@ class DitTrainer:
         assert self.arena.total == total
         self.exp_avg = torch.zeros_like(self.master)
         self.exp_avg_sq = torch.zeros_like(self.master)
+        self.ema = self.master.clone() if ema_decay is not None else None  # ema.py:69-72: a copy at train start
+        self._accum = torch.zeros_like(self.master) if self.accumulate > 1 else None
         self.steps = 0
         self._state = None
+        self._pending = False     # a training forward whose backward has not run yet
+        self._micro = 0           # backward passes since the last optimizer step
+        self._reduced = False     # the overlapped all-reduce of this step has been issued
+        self._events = None
         self._grads = self._grad_struct()
         self.anchor = torch.zeros(1, device=dev, requires_grad=True)  # makes autograd call our backward
         model._trainer = self
@@ -119,9 +148,13 @@ class DitTrainer:
             setattr(wT, k, v.data_ptr())
         self._wT = wT
 
+    @property
+    def train_mode(self):
+        return _lib.TRAIN_RECOMPUTE if self.recompute else _lib.TRAIN_STORE
+
     def train_state(self, B, V, H, W):
         w, _ = self.model.packed_weights()
-        n = _lib.lib().dgs_dit_train_state_bytes(C.byref(w), B, V, H, W)
+        n = _lib.lib().dgs_dit_train_state_bytes_ex(C.byref(w), B, V, H, W, self.train_mode)
         if n == 0:
             raise _lib.DgsError(_lib.lib().dgs_last_error().decode())
         if self._state is None or self._state.numel() < n:
@@ -131,24 +164,124 @@ class DitTrainer:
 
     def zero_grad(self):
         self.arena.zero_()
+        if self._accum is not None:
+            self._accum.zero_()
+        self._micro = 0
+
+    def reset(self):
+        """Drop an outstanding training forward (e.g. after an exception between forward and backward)."""
+        self._pending, self._reduced = False, False
+
+    # -- hooks called by _DitFunction --
+    def _begin_forward(self):
+        if self._pending:
+            raise RuntimeError("DitTrainer: a training forward is already pending (its backward has not run). The trainer "
+                               "holds ONE activation state; run backward first, wrap evaluation in torch.no_grad(), or call "
+                               "trainer.reset() to drop the pending forward.")
+        if self._reduced:
+            raise RuntimeError("DitTrainer: gradients of this step were already all-reduced; call optimizer_step() "
+                               "before the next forward")
+        self._pending = True
+
+    def _world(self):
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _bwd_opts(self):
+        """block_done events for the overlapped all-reduce, or None when there is nothing to overlap with."""
+        last_micro = self._micro + 1 >= self.accumulate
+        if not (self.overlap and self._world() > 1 and self.accumulate == 1 and last_micro):
+            return None
+        if self._events is None:
+            n = len(self.model.transformer) + 1
+            arr = (C.c_void_p * n)()
+            for i in range(n):
+                ev = C.c_void_p()
+                check(_lib.lib().dgs_event_create(C.byref(ev)))
+                arr[i] = ev.value
+            self._events = arr
+        return DitBwdOpts(block_done=C.cast(self._events, C.POINTER(C.c_void_p)))
+
+    def _end_backward(self, overlapped):
+        self._pending = False
+        self._micro += 1
+        if self._accum is not None:
+            self._accum.add_(self.arena.flat)
+        if overlapped:
+            L, ev, n = _lib.lib(), self._events, len(self.model.transformer)
+            side = C.c_void_p(self.arena._stream.cuda_stream)
+
+            def gate(block):  # side stream: wait until that block's (or, for the rest, every) gradient is final
+                check(L.dgs_stream_wait_event(side, ev[n if block is None else block]))
+            self.arena.allreduce_issue_(gate=gate, sync_main=False)
+            self._reduced = True
 
     def optimizer_step(self, allreduce=True):
-        """all-reduce (mean) -> clip at `clip` (Lightning gradient_clip_val) -> fused AdamW -> refresh bf16 weights."""
-        if allreduce:
-            self.arena.allreduce_mean_()
+        """all-reduce (mean) -> clip at `clip` (Lightning gradient_clip_val) -> fused AdamW [+ EMA] -> refresh bf16 weights."""
+        if self._pending:
+            raise RuntimeError("DitTrainer.optimizer_step: a training forward is still pending (no backward yet)")
+        if self._micro == 0:
+            raise RuntimeError("DitTrainer.optimizer_step: no backward since the last step")
+        grads = self.arena.flat
+        gscale = 1.0
+        if self._accum is not None:  # mean over the micro-batches (Lightning divides the loss by accumulate_grad_batches)
+            grads = self._accum
+            gscale = 1.0 / self._micro
+            if allreduce and self._world() > 1:
+                self.arena.flat.copy_(self._accum)
+                grads = self.arena.flat
+        if self._reduced:          # issued bucket by bucket during the backward; only the tail can still be in flight
+            gscale *= self.arena.allreduce_wait_(scale=False)
+        elif allreduce and self._world() > 1:
+            self.arena.allreduce_issue_()
+            gscale *= self.arena.allreduce_wait_(scale=False)
+        self._reduced = False
         norm = scale = None
         if self.clip:  # torch clip_grad_norm_ semantics; the factor stays on the device and is applied inside AdamW
-            norm = torch.linalg.vector_norm(self.arena.flat)
+            norm = torch.linalg.vector_norm(grads) * gscale
             scale = torch.clamp(self.clip / (norm + 1e-6), max=1.0).reshape(1).float()
         self.steps += 1
         dev = self.master.device
         with torch.cuda.device(dev):
-            check(_lib.lib().dgs_adamw_step(self.master.data_ptr(), self.arena.flat.data_ptr(), self.exp_avg.data_ptr(),
-                                            self.exp_avg_sq.data_ptr(), self.master.numel(), self.lr, self.betas[0],
-                                            self.betas[1], self.eps, self.weight_decay, self.steps, 1.0,
-                                            None if scale is None else scale.data_ptr(), _stream(dev)))
+            check(_lib.lib().dgs_adamw_ema_step(self.master.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(),
+                                                self.exp_avg_sq.data_ptr(), None if self.ema is None else self.ema.data_ptr(),
+                                                self.master.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                                self.weight_decay, self.steps, gscale,
+                                                None if scale is None else scale.data_ptr(),
+                                                0.0 if self.ema_decay is None else float(self.ema_decay), _stream(dev)))
+        if self._accum is not None:
+            self._accum.zero_()
+        self._micro = 0
         self.refresh_weights()
         return norm
+
+    # -- EMA (ema.py:94-101 update; 119-160 replace/restore for evaluation and the "-EMA" checkpoint) --
+    def ema_state_dict(self):
+        """state_dict-shaped views into the EMA arena (same keys / shapes as model.state_dict())."""
+        if self.ema is None:
+            raise RuntimeError("DitTrainer was built without ema_decay")
+        out, off = {}, 0
+        for name, p in self.model.named_parameters():
+            n = p.numel()
+            out[name] = self.ema[off:off + n].view_as(p)
+            off += n
+        return out
+
+    @contextlib.contextmanager
+    def swap_ema_weights(self):
+        """with trainer.swap_ema_weights(): evaluate / save with the EMA weights in place of the trained ones
+        (EMA.replace_model_weights / restore_original_weights)."""
+        if self.ema is None:
+            raise RuntimeError("DitTrainer was built without ema_decay")
+        if self._pending:
+            raise RuntimeError("swap_ema_weights with a training forward pending")
+        backup = self.master.clone()
+        self.master.copy_(self.ema)
+        self.refresh_weights()
+        try:
+            yield self.model
+        finally:
+            self.master.copy_(backup)
+            self.refresh_weights()
 
 
 class _DitFunction(torch.autograd.Function):
@@ -156,8 +289,13 @@ class _DitFunction(torch.autograd.Function):
     def forward(ctx, model, images, ray_o, ray_d, t, anchor):
         tr = model._trainer
         B, V, _, H, W = images.shape
-        state = tr.train_state(B, V, H, W)
-        out, img_xyz, _, keep = model._run_dit(images, ray_o, ray_d, t, train_state=state)
+        tr._begin_forward()
+        try:
+            state = tr.train_state(B, V, H, W)
+            out, img_xyz, _, keep = model._run_dit(images, ray_o, ray_d, t, train_state=state, train_mode=tr.train_mode)
+        except Exception:
+            tr._pending = False
+            raise
         ctx.model, ctx.keep = model, keep
         ctx.mark_non_differentiable(img_xyz)
         return out.xyz, out.features, out.scaling, out.rotation, out.opacity, img_xyz
@@ -166,6 +304,9 @@ class _DitFunction(torch.autograd.Function):
     def backward(ctx, d_xyz, d_features, d_scaling, d_rotation, d_opacity, _d_img):
         model = ctx.model
         tr = model._trainer
+        if ctx.keep is None or not tr._pending:
+            raise RuntimeError("DitTrainer: this forward was already backpropagated (or dropped by trainer.reset()); the "
+                               "activation state is consumed by the backward -- retain_graph / double backward is not supported")
         io, ws, nbytes, images, *_ = ctx.keep
         w, _k = ctx.keep[7], ctx.keep[8]
         dev = images.device
@@ -175,9 +316,13 @@ class _DitFunction(torch.autograd.Function):
         gs = [z(d_xyz, B, P, 3), z(d_features, B, P, 1, 3), z(d_scaling, B, P, 3), z(d_rotation, B, P, 4),
               z(d_opacity, B, P, 1)]
         dout = DitOutGrads(*(g.data_ptr() for g in gs))
+        opts = tr._bwd_opts()
         with torch.cuda.device(dev):
-            check(_lib.lib().dgs_dit_backward(C.byref(w), C.byref(tr._wT), C.byref(io), C.byref(dout),
-                                              C.byref(tr._grads), ws.data_ptr(), nbytes, _stream(dev)))
+            check(_lib.lib().dgs_dit_backward_ex(C.byref(w), C.byref(tr._wT), C.byref(io), C.byref(dout),
+                                                 C.byref(tr._grads), None if opts is None else C.byref(opts),
+                                                 ws.data_ptr(), nbytes, _stream(dev)))
+        ctx.keep = None
+        tr._end_backward(overlapped=opts is not None)
         # parameter gradients were written straight into the arena (p.grad views); nothing to hand to autograd
         return None, None, None, None, None, torch.zeros_like(tr.anchor)
 

@@ -6,9 +6,12 @@ diffusionGS/models/transformers/utils_transformer.py:26-36,246-290 (DiTBlock).
 The block's arithmetic lives in a third-party dependency that is NOT under /root/reference:
 timm==0.9.16 (requirement.txt:25) `timm.models.vision_transformer.Attention` and `Mlp`; their published
 forward is restated here (qkv Linear -> reshape [B,N,3,H,hd] -> softmax(q k^T / sqrt(hd)) v -> proj;
-fc1 -> GELU(tanh) -> fc2; dropout 0; qk_norm off).  PARITY UNPINNED: the reference has no tests or
-golden vectors for the denoiser, and neither timm nor the reference package imports in this image, so
-this restatement is anchored only on the reference's call sites and state_dict key names.
+fc1 -> GELU(tanh) -> fc2; dropout 0; qk_norm off).
+PINNED (round 2): tests/test_oracle_dit_vs_reference.py executes the reference's OWN denoiser.py /
+denoiser_scene.py / utils_transformer.py (loaded by path, tests/golden/ref_import.py; only the absent third-party
+packages are stubbed -- timm's Attention there is an independent restatement over F.scaled_dot_product_attention)
+and holds this file to it at 1e-6 (object + scene model, both ray_pe_type values); the same run's inputs/outputs are
+committed as tests/golden/dit_ref_*.npz (tests/golden/make_dit_golden.py) for boxes without /root/reference.
 Same module tree / state_dict keys as the reference so a reference checkpoint loads with strict=True.
 Never imported by the product path.
 """
@@ -98,9 +101,12 @@ def _init_linear(m):
 
 
 class DenoiserOracle(nn.Module):
-    def __init__(self, width=1024, heads=16, layers=24, patch=8, n_gaussians=2, scene=False, near=0.0, far=500.0):
+    def __init__(self, width=1024, heads=16, layers=24, patch=8, n_gaussians=2, scene=False, near=0.0, far=500.0,
+                 ray_pe_type=None):
         super().__init__()
         self.width, self.patch, self.G, self.scene, self.near, self.far = width, patch, n_gaussians, scene, near, far
+        # yaml defaults: object configs leave the class default 'relative_plk' (denoiser.py:186), scene configs set 'plk'
+        self.ray_pe_type = ray_pe_type or ("plk" if scene else "relative_plk")
         self.t_embedder = TimestepEmbedder(width)
         nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)
         nn.init.normal_(self.t_embedder.mlp[2].weight, std=0.02)
@@ -120,7 +126,7 @@ class DenoiserOracle(nn.Module):
     def image_to_gaussians(self, images, ray_o, ray_d, t, return_tokens=False):
         p = self.patch
         o_dot_d = torch.sum(-ray_o * ray_d, dim=2, keepdim=True)
-        if not self.scene:
+        if self.ray_pe_type == "relative_plk":  # denoiser.py:312-322 == denoiser_scene.py:319-331
             posed = torch.cat([images[:, :, :3] * 2.0 - 1.0, ray_d, ray_o + o_dot_d * ray_d], dim=2)
         else:
             posed = torch.cat([images[:, :, :3] * 2.0 - 1.0, torch.cross(ray_o, ray_d, dim=2), ray_d], dim=2)
@@ -145,10 +151,12 @@ class DenoiserOracle(nn.Module):
         n_img = img_g.shape[1]
         ia = xyz[:, -n_img:, :].reshape(b, v, h // p, w // p, p, p, 3).permute(0, 1, 6, 2, 4, 3, 5).reshape(b, v, 3, h, w)
         ia = ia.mean(dim=2, keepdim=True)
-        if self.scene:
+        if self.scene:  # denoiser_scene.py:263,406-410 (range_func, whatever ray_pe_type is)
             depth = torch.sigmoid(ia) * (self.far - self.near) + self.near
-        else:
+        elif self.ray_pe_type == "relative_plk":  # denoiser.py:381-388
             depth = (2.0 * torch.sigmoid(ia) - 1.0) * 1.8 + o_dot_d
+        else:
+            depth = torch.sigmoid(ia)
         ia = ray_o + depth * ray_d
         ia_flat = ia.reshape(b, v, 3, h // p, p, w // p, p).permute(0, 1, 3, 5, 4, 6, 2).reshape(b, -1, 3)
         xyz = torch.cat((xyz[:, :-n_img, :], ia_flat), dim=1)

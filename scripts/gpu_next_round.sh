@@ -18,3 +18,4 @@ timeout 30 scripts/bin/att_probe 4098 16 1 > gpurun_out/att_probe_v2.txt 2>&1
 timeout 30 scripts/bin/att_probe 4098 16 4 >> gpurun_out/att_probe_v2.txt 2>&1
 timeout 60 scripts/bin/att_probe 16386 16 1 >> gpurun_out/att_probe_v2.txt 2>&1
 cat gpurun_out/att_probe_v2.txt
+timeout 300 python scripts/library_baseline.py gpurun_out/r2_library_baseline.json > gpurun_out/library_baseline.log 2>&1; tail -30 gpurun_out/library_baseline.log

@@ -105,8 +105,11 @@ def test_attention_vs_fp32_softmax(B, N, H):
     ref = ref.permute(0, 2, 1, 3).reshape(B, N, H * 64)
     e = rel(out.float(), ref)
     print(f"attention B={B} N={N} H={H}: rel={e:.2e}")
-    # P is rounded to bf16 before the PV MMA and the output is bf16: expected ~2e-3 norm-wise
-    assert e < 4e-3
+    # Operator-level bound, not the north-star one: the inputs here are N(0, 1.5^2) q/k (logit std 2.25, peaky rows) and
+    # BOTH P (before the PV MMA) and the output are rounded to bf16 (2^-9 relative each, uncorrelated): ~2e-3 norm-wise.
+    # Against the fp32 result rounded to bf16 the kernel must be within the P rounding alone.
+    assert e < 3e-3
+    assert rel(out.float(), ref.to(torch.bfloat16).float()) < 2.5e-3
 
 
 def test_ln_modulate():
@@ -159,7 +162,7 @@ def test_denoiser_small_vs_oracle(scene):
     oracle = DenoiserOracle(layers=2, scene=scene).to(DEV)
     oracle.load_state_dict(model.state_dict(), strict=True)
     errs = _compare_models(model, oracle, 2, 4, 64, 64, f"small scene={scene}")
-    assert all(v < 2e-3 for v in errs.values()), errs
+    assert all(v < 1e-3 for v in errs.values()), errs  # north-star bound (measured r1: 1e-4 .. 3e-4)
 
 
 def test_denoiser_full_depth_obj256_vs_oracle():
@@ -174,8 +177,8 @@ def test_denoiser_full_depth_obj256_vs_oracle():
     errs = _compare_models(model, oracle, 1, 4, 256, 256, "obj-256 x24")
     # north_star: DiT outputs within 1e-3 rel in bf16 (vs the fp32 oracle with the same fp32 master weights).
     # The two GEMMs at the ends of the network run split-bf16 and the conditioning runs fp32, so what is left is
-    # the bf16 operand rounding inside the 24 blocks, entering through the gated residual updates.
-    assert all(v < 2e-3 for v in errs.values()), errs
+    # the bf16 operand rounding inside the 24 blocks, entering through the gated residual updates (measured r1: 2.2e-4).
+    assert all(v < 1e-3 for v in errs.values()), errs
     # the hot path's final product: the rendered views from both sets of Gaussians
     from dgs_b200 import synth
     c2w, fx = synth.orbit_cameras(4, 256, 256)

@@ -10,7 +10,7 @@ def test_view_chunking_on_instance_overflow(monkeypatch):
     calls = []
 
     def fake_forward(xyz, features, scaling, rotation, opacity, H, W, C2W, fxfycxcy, scale_modifier=None, arena_cache=None,
-                     near_log2=None):
+                     near_log2=None, mse_target=None, mse_loss_sum=None):
         B, V = C2W.shape[:2]
         calls.append(V)
         if V > 2:  # "too many instances" until at most 2 views are left
@@ -18,7 +18,7 @@ def test_view_chunking_on_instance_overflow(monkeypatch):
         img = C2W[:, :, 0, 3].reshape(B, V, 1, 1, 1).expand(B, V, 3, H, W).clone()  # image = the view's tag
         return img, dict(R=100 * V, tensors=[xyz], tag=C2W[:, :, 0, 3].clone())
 
-    def fake_backward_one(state, grad_images, arena_cache=None):
+    def fake_backward_one(state, grad_images, arena_cache=None, mse_coef=None):
         # d_xyz = sum over this chunk's views of (tag * mean grad): lets the test see which views each chunk got
         w = (state["tag"].reshape(-1) * grad_images.mean(dim=(0, 2, 3, 4))).sum()
         return tuple(torch.full((1,), float(w)) for _ in range(5))
@@ -26,10 +26,10 @@ def test_view_chunking_on_instance_overflow(monkeypatch):
     monkeypatch.setattr(raster, "_render_batch_forward_one", fake_forward)
     real_backward = raster.render_batch_backward
 
-    def backward(state, grad_images, arena_cache=None):
+    def backward(state, grad_images, arena_cache=None, mse_coef=None):
         if "sub" in state:
-            return real_backward(state, grad_images, arena_cache)
-        return fake_backward_one(state, grad_images, arena_cache)
+            return real_backward(state, grad_images, arena_cache, mse_coef)
+        return fake_backward_one(state, grad_images, arena_cache, mse_coef)
     monkeypatch.setattr(raster, "render_batch_backward", backward)
 
     B, V, H, W = 1, 7, 4, 4
