@@ -142,6 +142,12 @@ CPU_VIEWS_SAMPLED = 1
 _CPU_REF = {}
 
 
+def cpu_threads():
+    """Thread count of every CPU-baseline leg: fixed, so that two records of the same box agree (r1: 0.0159 vs 0.0495
+    steps/s with os.cpu_count() threads on a box whose other tenants varied)."""
+    return min(os.cpu_count() or 1, 64)
+
+
 def cpu_reference_step(batch_np=None, threads=None):
     """One BOUNDED sample of the step on the CPU, extrapolated to a full step:
       DiT: fp32 PyTorch oracle at N = 4098 with 1 of the 24 blocks (block time x 24 + measured non-block time),
@@ -152,8 +158,9 @@ def cpu_reference_step(batch_np=None, threads=None):
     from dgs_b200 import synth
     from oracle import raster as orc
     from oracle.dit import DenoiserOracle
-    threads = threads or os.cpu_count()
+    threads = threads or cpu_threads()
     torch.set_num_threads(threads)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     b = make_batch(1, 0) if batch_np is None else batch_np
     args = (b["image"][:1], b["ray_o"][:1], b["ray_d"][:1], b["t"][:1])
     with torch.no_grad():
@@ -190,7 +197,7 @@ def run_reference_arm(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
     if rank != 0:
         return
-    threads = os.cpu_count()
+    threads = cpu_threads()
     batch = make_batch(1, 0)
     for _ in range(args.warmup):
         cpu_reference_step(batch, threads)
@@ -207,90 +214,145 @@ def run_reference_arm(args, rank, world):
                 warmup=args.warmup, ms_per_step=t_step * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=workload_name(1), per_gpu_batch=1, parallelism="cpu", detail=detail),
-                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port", sample=sample),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port", sample=sample, extrapolated=True),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 views_per_sec=val * V, gpu_launches=0)
     print(json.dumps(line))
 
 
-def run_train(args, rank, local_rank, world):
+class TrainBench:
     """Training step of the obj-256 config (BASELINE configs[2], diffusionGS_rel.yaml: 4 input views, 10 rendered views,
-    AdamW lr 1e-5, clip 0.5; loss = MSE only -- the LPIPS weights are not available offline): one process per GPU,
-    per-GPU batch --batch, gradients all-reduced over NCCL every step.  Prints one JSON line (same keys as the default
+    AdamW lr 1e-5, clip 0.5, EMA 0.9999; loss = the MSE term, fused into the rasterizer -- the LPIPS weights are not available
+    offline): one process per GPU, per-GPU batch B, gradients all-reduced over NCCL every step, the per-block buckets
+    overlapped with the rest of the backward (dgs_dit_backward_ex block_done events)."""
+
+    def __init__(self, dev, rank, world, render_views, recompute=False, overlap=True, ema=True):
+        import torch
+        from dgs_b200.denoiser import DGSDenoiser
+        from dgs_b200.train import DitTrainer
+        self.dev, self.rank, self.world, self.VR, self.overlap = dev, rank, world, render_views, overlap
+        torch.manual_seed(0)  # identical initial weights on every rank (what DDP's broadcast establishes)
+        self.model = DGSDenoiser(dict(patch_size=PATCH)).to(dev)
+        self.trainer = DitTrainer(self.model, lr=1e-5, betas=(0.9, 0.99), eps=1e-8, clip=0.5, recompute=recompute,
+                                  overlap_allreduce=overlap, ema_decay=0.9999 if ema else None)
+        self.model.train()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.host = self.devb = None
+
+    def set_batch(self, B):
+        import numpy as np
+        import torch
+        from dgs_b200 import synth
+        VR = self.VR
+        host = make_batch(B, seed=self.rank)
+        c2w_r, fx_r = synth.orbit_cameras(VR, W, H, radius=3.0, el_deg=20.0, az_step=36.0)
+        rng = np.random.default_rng(100 + self.rank)
+        host["c2w_r"] = torch.from_numpy(np.broadcast_to(c2w_r, (B, VR, 4, 4)).copy())
+        host["fx_r"] = torch.from_numpy(np.broadcast_to(fx_r, (B, VR, 4)).copy())
+        host["target"] = torch.from_numpy(rng.uniform(0, 1, (B, VR, 3, H, W)).astype(np.float32))
+        self.B = B
+        self.host = {k: v.pin_memory() for k, v in host.items()}
+        self.devb = {k: v.to(self.dev, non_blocking=True) for k, v in self.host.items()}
+
+    def step(self, b, allreduce=True):
+        from dgs_b200 import losses
+        out, _ = self.model.image_to_gaussians(b["image"], b["ray_o"], b["ray_d"], b["t"])
+        res, _ = losses.fused_render_and_loss(self.model, out, b["c2w_r"], b["fx_r"], H, W, b["target"],
+                                              lambdas=dict(lambda_diffusion=1.0))
+        self.trainer.overlap = self.overlap and allreduce  # without an all-reduce there is nothing to issue in the backward
+        res["loss"].backward()
+        self.trainer.optimizer_step(allreduce=allreduce)
+        return res["loss"].detach()
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def timed(self, steps, warmup, allreduce=True):
+        """-> (max-over-ranks seconds for `steps` steps, this rank's per-step ms, last loss)"""
+        import torch
+        import torch.distributed as dist
+        for _ in range(warmup):
+            self.step(self.devb, allreduce)
+        self.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b_ in ev:
+            self.flush.zero_()
+            a.record()
+            loss = self.step(self.devb, allreduce)
+            b_.record()
+        self.barrier()
+        step_ms = [a.elapsed_time(b_) for a, b_ in ev]
+        total_s = torch.tensor([sum(step_ms) / 1e3], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(total_s, op=dist.ReduceOp.MAX)
+        return float(total_s), step_ms, loss
+
+
+def train_section(dev, rank, world, batches, steps, warmup, render_views):
+    """The north-star's data-parallel split measured inside the default bench line (N > 1): per-GPU batch b training
+    steps with the overlapped NCCL gradient all-reduce, and the same steps without any all-reduce right after, so that
+    the EXPOSED all-reduce time per step is a measured difference.  -> list of dicts (rank 0), one per batch size."""
+    import torch
+    tb = TrainBench(dev, rank, world, render_views)
+    out = []
+    for B in batches:
+        tb.set_batch(B)
+        t_ar, step_ms, loss = tb.timed(steps, warmup, allreduce=True)
+        t_no, _, _ = tb.timed(steps, 1, allreduce=False) if world > 1 else (t_ar, None, None)
+        out.append(dict(per_gpu_batch=B, global_batch=B * world, samples_per_s=world * B * steps / t_ar,
+                        ms_per_step=t_ar / steps * 1e3, ms_per_step_no_allreduce=t_no / steps * 1e3,
+                        allreduce_exposed_ms=(t_ar - t_no) / steps * 1e3, steps=steps, warmup=warmup,
+                        render_views=render_views, loss=float(loss), step_ms_rank0=[round(v, 2) for v in step_ms],
+                        mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                        collective="ncclAllReduce(sum) of 460,391,424 fp32 gradients per step, one bucket per DiT block in "
+                                   "reverse order on a side stream, gated by the backward's block_done events"))
+    del tb
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_train(args, rank, local_rank, world):
+    """`--workload train`: the training step alone (see TrainBench).  Prints one JSON line (same keys as the default
     workload; `value` = samples/s over all ranks)."""
-    import numpy as np
     import torch
     import torch.distributed as dist
-    from dgs_b200 import _lib, synth
-    from dgs_b200.denoiser import DGSDenoiser
-    from dgs_b200.train import DitTrainer
+    from dgs_b200 import _lib
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("DGS_NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/dgs_nccl_%h_%p.log")  # keep even the version banner off stdout
         dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(0)  # identical initial weights on every rank (what DDP's broadcast establishes)
-    model = DGSDenoiser(dict(patch_size=PATCH)).to(dev)
-    trainer = DitTrainer(model, lr=1e-5, betas=(0.9, 0.99), eps=1e-8, clip=0.5)
-    model.train()
+    tb = TrainBench(dev, rank, world, args.render_views, recompute=args.recompute, overlap=not args.no_overlap)
     B, VR = args.batch, args.render_views
-    host = make_batch(B, seed=rank)
-    c2w_r, fx_r = synth.orbit_cameras(VR, W, H, radius=3.0, el_deg=20.0, az_step=36.0)
-    rng = np.random.default_rng(100 + rank)
-    host["c2w_r"] = torch.from_numpy(np.broadcast_to(c2w_r, (B, VR, 4, 4)).copy())
-    host["fx_r"] = torch.from_numpy(np.broadcast_to(fx_r, (B, VR, 4)).copy())
-    host["target"] = torch.from_numpy(rng.uniform(0, 1, (B, VR, 3, H, W)).astype(np.float32))
-    host = {k: v.pin_memory() for k, v in host.items()}
-    devb = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    tb.set_batch(B)
     L = _lib.lib()
-
-    def step(b):
-        out, _ = model.image_to_gaussians(b["image"], b["ray_o"], b["ray_d"], b["t"])
-        renders = model.render_gaussians(out, b["c2w_r"], b["fx_r"], H, W)
-        loss = ((renders - b["target"]) ** 2).mean()
-        trainer.zero_grad()
-        loss.backward()
-        trainer.optimizer_step(allreduce=True)
-        return loss.detach()
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(args.warmup):
-        step(devb)
-    barrier()
     sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        tb.step(tb.devb)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = L.dgs_kernel_launch_count()
-    barrier()
     t0 = time.time()
-    for a, b_ in ev:
-        flush.zero_()
-        a.record()
-        loss = step(devb)
-        b_.record()
-    barrier()
+    total_s, step_ms, loss = tb.timed(args.steps, 0)
     t1 = time.time()
     launches = L.dgs_kernel_launch_count() - launches0
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    step_ms = [a.elapsed_time(b_) for a, b_ in ev]
-    total_s = torch.tensor([sum(step_ms) / 1e3], device=dev, dtype=torch.float64)
+    exposed = None
     if world > 1:
-        dist.all_reduce(total_s, op=dist.ReduceOp.MAX)
-    value = world * B * args.steps / float(total_s)
+        t_no, _, _ = tb.timed(args.steps, 1, allreduce=False)
+        exposed = (total_s - t_no) / args.steps * 1e3
+    value = world * B * args.steps / total_s
+    host, step, barrier = tb.host, tb.step, tb.barrier
     # per-family device time
     L.dgs_profile_enable(1)
     _lib.profile_read()
     for _ in range(args.steps):
-        step(devb)
+        step(tb.devb)
     torch.cuda.synchronize(dev)
     fam = _lib.profile_read()
     L.dgs_profile_enable(0)
@@ -307,15 +369,16 @@ def run_train(args, rank, local_rank, world):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        flush.zero_()
+        tb.flush.zero_()
         lh = e2e_step()
     torch.cuda.synchronize(dev)
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    line = None
     if rank == 0:
         peaks = load_peaks()
-        f_train = 3 * dit_forward_flops() * B  # fwd + 2 x bwd, activations stored (no recompute)
+        f_train = 3 * dit_forward_flops() * B  # algorithmic: fwd + 2 x bwd (a recomputed forward is not credited)
         dit_ms = sum(v for k, v in fam_ms.items() if k.startswith("dit."))
         bwd_att = fam_ms.get("dit.bwd_attention")
         roof = None
@@ -325,23 +388,27 @@ def run_train(args, rank, local_rank, world):
                         unit="TFLOP/s", frac=ach / peaks["bf16_tflops_sustained"], traffic=None,
                         peak_source=peaks["source"], launch_ms=bwd_att / LAYERS,
                         note="algorithmic FLOPs = 2.5 x forward attention (dV, dP, dQ, dK + S); the kernel pair recomputes S and dP once more")
-        line = dict(metric="train-samples/sec @256^2 (DiT fwd+bwd + %d-view render fwd+bwd + grad all-reduce + AdamW)" % VR,
+        line = dict(metric="train-samples/sec @256^2 (DiT fwd+bwd + %d-view render fwd+bwd + grad all-reduce + AdamW+EMA)" % VR,
                     value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=float(total_s) / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    ms_per_step=total_s / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16", data="synthetic",
-                    config=dict(workload="obj-256 train step: 4 input views, %d rendered views, MSE loss, AdamW" % VR,
-                                per_gpu_batch=B, parallelism=f"dp{world} (NCCL all-reduce of 460 M fp32 gradients)",
+                    config=dict(workload="obj-256 train step: 4 input views, %d rendered views, fused MSE loss, AdamW + EMA" % VR,
+                                per_gpu_batch=B, activations="recompute" if args.recompute else "stored",
+                                parallelism=f"dp{world} (NCCL all-reduce of 460 M fp32 gradients, "
+                                            f"{'overlapped per block' if not args.no_overlap else 'after the backward'})",
                                 l2="256 MB buffer written between timed steps"),
                     e2e=dict(value=world * B * args.steps / float(e2e_s), unit="samples/s",
                              h2d_bytes_per_step=sum(host[k].numel() * host[k].element_size() for k in e2e_keys),
                              d2h_bytes_per_step=lh.numel() * lh.element_size()),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=None, clocks=clocks,
+                    allreduce_exposed_ms=exposed,
                     breakdown_ms=dict(dit=dit_ms, families={k: round(v, 4) for k, v in fam_ms.items()}),
                     dit_train_tflops=f_train / (dit_ms * 1e-3) / 1e12 if dit_ms else None, loss=float(loss),
                     step_ms=[round(v, 3) for v in step_ms], mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 def workload_name(batch):
@@ -364,11 +431,17 @@ def main():
                     help="denoise = BASELINE configs[1] (the contract's default line); train = configs[2]-shaped training "
                          "step (DiT fwd+bwd, V_render-view render fwd+bwd, gradient all-reduce, AdamW)")
     ap.add_argument("--render-views", type=int, default=10)
+    ap.add_argument("--recompute", action="store_true", help="train workload: activation recompute (denoiser.py:348-354)")
+    ap.add_argument("--no-overlap", action="store_true", help="train workload: all-reduce after the whole backward")
+    ap.add_argument("--train-batches", default="4,8", help="per-GPU batch sizes of the training section (N > 1)")
+    ap.add_argument("--no-train-section", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:  # the CPU-baseline legs (oracle: torch intra-op + the C oracle's OpenMP team) use a FIXED thread count
+        os.environ.setdefault("OMP_NUM_THREADS", str(cpu_threads()))
 
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
@@ -386,8 +459,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("DGS_NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/dgs_nccl_%h_%p.log")  # keep even the version banner off stdout  # keep stdout = the one JSON line
+        # NCCL's own environment (NCCL_DEBUG, NCCL_DEBUG_FILE) is left exactly as the launcher set it, so that its log shows
+        # the communicator with `world` ranks; the JSON line is the LAST line this process prints.
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
@@ -410,12 +483,16 @@ def main():
 
     for _ in range(args.warmup):
         img = step(devb)
+    # N > 1: the clocks / power of a box that just went from idle to N busy GPUs settle over the first ~100 ms (r1 SCALE:
+    # the first timed region was slower than the later wall-timed e2e loop); extra UNTIMED steps, same on every rank
+    for _ in range(30 if world > 1 else 0):
+        flush.zero_()
+        img = step(devb)
     barrier()
 
     # ---- timed region 1: inputs resident in HBM, per-step CUDA events, L2 flushed between steps ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(local_rank)  # every rank samples its own GPU (per-rank clocks / power in the N > 1 line)
+    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = L.dgs_kernel_launch_count()
     barrier()
@@ -428,14 +505,23 @@ def main():
     barrier()
     t_wall1 = time.time()
     launches = L.dgs_kernel_launch_count() - launches0
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1)
     step_ms = [a.elapsed_time(b_) for a, b_ in ev]
     total_s = torch.tensor([sum(step_ms) / 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total_s, op=dist.ReduceOp.MAX)
     total_s = float(total_s)
     value = world * args.batch * args.steps / total_s
+    per_rank = None
+    if world > 1:  # where the N-GPU time goes: every rank's own step statistics and clocks during the timed region
+        mine = dict(rank=rank, gpu=local_rank, step_ms_min=round(min(step_ms), 3), step_ms_median=round(statistics.median(step_ms), 3),
+                    step_ms_max=round(max(step_ms), 3), step_ms_sum=round(sum(step_ms), 3), wall_s=round(t_wall1 - t_wall0, 4),
+                    sm_mhz=clocks and clocks["sm_mhz"], reasons=clocks and clocks["reasons"])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
 
+    last_R = getattr(model.gs_renderer, "last_num_rendered", None)
     # ---- timed region 2: per-kernel-family device time, same steps with the library's event hooks on ----
     L.dgs_profile_enable(1)
     _lib.profile_read()
@@ -478,9 +564,18 @@ def main():
     h2d = sum(host[k].numel() * host[k].element_size() for k in e2e_keys)
     d2h = out_host.numel() * out_host.element_size()
 
+    # ---- N > 1: the training step with the NCCL gradient all-reduce (the path's one collective), same launch ----
+    train = None
+    if world > 1 and not args.no_train_section:
+        del model, devb
+        torch.cuda.empty_cache()
+        model = None
+        train = train_section(dev, rank, world, [int(b) for b in args.train_batches.split(",")], steps=6, warmup=3,
+                              render_views=args.render_views)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel family ----
@@ -502,7 +597,7 @@ def main():
                         launch_ms=per_launch_ms, algorithmic_flops_per_launch=flops[dom])
         else:
             # rasterizer family: algorithmic bytes B_fwd = 159 P + 84 R + 20 N_pix per view
-            R = getattr(model.gs_renderer, "last_num_rendered", None)
+            R = last_R
             nbytes = None if R is None else (159 * P_GAUSS * V + 84 * R + 20 * H * W * V) * args.batch
             tot_ms = sum(v for k, v in fam_ms.items() if k.startswith("raster."))
             ach = None if nbytes is None else nbytes / (tot_ms * 1e-3) / 1e9
@@ -514,11 +609,13 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        t_cpu, detail = cpu_reference_step(None, os.cpu_count())
-        cpu = dict(value=1.0 / t_cpu, unit=UNIT, cores=os.cpu_count(), kind="port",
-                   sample=(f"one bounded sample: fp32 PyTorch oracle DiT with {CPU_DIT_LAYERS_SAMPLED}/{LAYERS} blocks timed "
-                           f"(x{LAYERS} + non-block time) + C/OpenMP oracle rasterizer on 1/{V} views (x{V}); "
-                           f"dit {detail['dit_s']:.1f}s + raster {V}x{detail['raster_view_s']:.1f}s"),
+        threads = cpu_threads()
+        t_cpu, detail = min((cpu_reference_step(None, threads) for _ in range(2)), key=lambda r: r[0])
+        cpu = dict(value=1.0 / t_cpu, unit=UNIT, cores=threads, kind="port", extrapolated=True,
+                   sample=(f"best of 2 bounded samples, EXTRAPOLATED to a full step: fp32 PyTorch oracle DiT with "
+                           f"{CPU_DIT_LAYERS_SAMPLED}/{LAYERS} blocks timed (x{LAYERS} + non-block time) + C/OpenMP oracle "
+                           f"rasterizer on 1/{V} views (x{V}); dit {detail['dit_s']:.1f}s + raster {V}x{detail['raster_view_s']:.1f}s; "
+                           f"{threads} threads (pinned: min(os.cpu_count(), 64))"),
                    detail=detail)
 
     ms_per_step = total_s / args.steps * 1e3
@@ -538,9 +635,11 @@ def main():
         dit_tflops=dit_forward_flops() * args.batch / (dit_ms * 1e-3) / 1e12 if dit_ms else None,
         step_ms_min=min(step_ms), step_ms_max=max(step_ms), step_ms=[round(v, 3) for v in step_ms],
     )
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if per_rank is not None:
+        line["per_rank"] = per_rank
+    if train is not None:
+        line["train"] = train
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

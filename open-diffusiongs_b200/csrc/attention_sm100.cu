@@ -374,6 +374,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
 int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st) {
   DGS_REQUIRE(B > 0 && N > 0 && H > 0, "attention: bad shape B=%d N=%d H=%d", B, N, H);
+  {
+    static int k128 = -1, poly128 = 0;  // generation switch: DGS_ATT_K128=0 selects this file's 64-key kernel
+    if (k128 < 0) {
+      const char* e = getenv("DGS_ATT_K128");
+      k128 = (e && e[0] == '0') ? 0 : 1;
+      const char* pe = getenv("DGS_ATT_POLY");
+      poly128 = pe ? atoi(pe) : 0;
+    }
+    if (k128) return attention_fwd_k128(qkv, out, lse2, B, N, H, poly128, st);
+  }
   const int D = H * ATT_HD;
   const int Np = attention_lse_stride(N);
   CUtensorMap tm_q, tm_kv;

@@ -213,6 +213,10 @@ class DGSDenoiser(nn.Module):
             from .train import dit_train_forward
             out, img_xyz = dit_train_forward(self, images, ray_o, ray_d, t)
             return (out, img_xyz, None) if return_tokens else (out, img_xyz)
+        tr = getattr(self, "_trainer", None)
+        if tr is not None and tr._pending:
+            raise RuntimeError("DGSDenoiser: a training forward is pending; an inference call would overwrite the workspace "
+                               "its backward reads (run backward first, or trainer.reset())")
         with torch.no_grad():
             out, img_xyz, tokens, _ = self._run_dit(images, ray_o, ray_d, t, return_tokens=return_tokens)
             if self.cfg.clip_xyz and training and not self.SCENE:  # denoiser.py:395-396 (never taken by the reference's callers)

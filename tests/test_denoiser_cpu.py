@@ -71,3 +71,25 @@ def test_oracle_fp32_vs_fp64():
     b, _ = o.double().image_to_gaussians(img.double(), ro.double(), rd.double(), t)
     for k in a:
         assert float((a[k].double() - b[k]).norm() / b[k].norm()) < 1e-5, k
+
+
+def test_reference_yaml_config_builds_and_loads_a_576_column_tokenizer():
+    """every shipped reference yaml sets in_channels: 9 and the tokenizer is
+    Linear(in_channels * patch^2, width) (denoiser.py:216-221) -> image_tokenizer.1.weight is [1024, 576] in released
+    and Lightning checkpoints.  Build from the yaml's values and strictly load such a state_dict."""
+    import pytest
+    import torch
+    from dgs_b200 import denoiser as dn
+    yaml_obj = dict(width=1024, in_channels=9, patch_size=8, n_gaussians=2, dim_heads=64, num_layers=1,
+                    prior_distribution="gaussian", use_flash=True, use_checkpoint=True)       # diffusionGS_rel.yaml:26-36
+    yaml_scene = dict(yaml_obj, range_setting_near=0, range_setting_far=500, ray_pe_type="plk")  # diffusionGS_scene.yaml:28-40
+    for cls, cfg in ((dn.DGSDenoiser, yaml_obj), (dn.DGSDenoiserScene, yaml_scene)):
+        m = cls(cfg)
+        assert tuple(m.image_tokenizer[1].weight.shape) == (1024, 576)
+        sd = {k: torch.zeros_like(v) for k, v in m.state_dict().items()}
+        assert sd["image_tokenizer.1.weight"].shape == (1024, 9 * 64)
+        m.load_state_dict(sd, strict=True)
+    with pytest.raises(ValueError, match="in_channels"):
+        dn.DGSDenoiser(dict(yaml_obj, in_channels=3))
+    with pytest.raises(ValueError, match="ray_pe_type"):
+        dn.DGSDenoiser(dict(yaml_obj, ray_pe_type="abs"))

@@ -73,3 +73,30 @@ def test_arena_layout_single_process():
     assert all(float(p.grad.min()) == 1.0 for p in m.parameters())
     n = a.clip_grad_norm_(0.5)
     assert abs(float(n) - a.total ** 0.5) < 1e-3 * a.total ** 0.5
+
+
+def _overlap_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dd.init_from_env("gloo")
+    try:
+        from dgs_b200.denoiser import DGSDenoiser
+        torch.manual_seed(0)
+        model = DGSDenoiser(dict(patch_size=8, num_layers=3))
+        arena = dd.GradArena(model)
+        arena.flat.fill_(float(rank + 1))
+        gated = []
+        arena.allreduce_issue_(gate=gated.append, sync_main=False)   # the overlapped form: one gate per bucket, in issue order
+        inv = arena.allreduce_wait_(scale=False)                     # SUM stays in the arena, 1/world goes to the consumer
+        ret[rank] = dict(gated=gated, inv=inv, lo=float(arena.flat.min()), hi=float(arena.flat.max()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_gated_issue_and_deferred_scale():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_overlap_worker, args=(world, 29613, ret), nprocs=world, join=True)
+    for r in (ret[0], ret[1]):
+        assert r["gated"] == [2, 1, 0, None, None]   # blocks in reverse order, then the two non-block buckets
+        assert r["inv"] == 0.5 and r["lo"] == r["hi"] == 3.0
