@@ -87,7 +87,9 @@ constexpr int DQ_SMEM = 2 * AB_T128 /*Q, dO*/ + 2 * DQ_STAGES * AB_T64 /*K, V*/ 
 constexpr uint32_t DQ_TM_S = 0 /* 2 buffers x 64 */, DQ_TM_DP = 128, DQ_TM_DQ = 192, DQ_TMEM_COLS = 256;
 
 // UNI (default; DGS_ATT_UNI=0 selects the old path): MMA issue by the converged warp under elect.sync (see attention_sm100.cu / sm100_ptx.cuh)
-template <bool UNI>
+constexpr int ATTB_POLY_DEFAULT = 1;  // index into {0, 2, 4} of 8 pairs; measured r2 (B = 1 / 4): 295 / 1064 -> 284 / 1033 us with 2 of 8, 289 / 1047 with 4 of 8
+
+template <bool UNI, int POLY>
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_constant__ CUtensorMap tm_kv64,
                    const __grid_constant__ CUtensorMap tm_do128, const float* __restrict__ lse2,
@@ -229,8 +231,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q128, const __grid_con
         for (int i = 0; i < 16; i += 2) {  // packed fp32 pairs (FFMA2): x = s * c - lse
           float x0, x1;
           unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1])), sl2_2, nlse_2), x0, x1);
-          p[sub * 16 + i] = ex2_approx(x0);
-          p[sub * 16 + i + 1] = ex2_approx(x1);
+          // POLY of the 8 pairs of each 16-column load: packed polynomial exp2 on the FMA pipe (ex2_poly3_x2)
+          if ((i >> 1) < POLY) ex2_poly3_x2(x0, x1, p[sub * 16 + i], p[sub * 16 + i + 1]);
+          else { p[sub * 16 + i] = ex2_approx(x0); p[sub * 16 + i + 1] = ex2_approx(x1); }
         }
       }
       if (kv_valid < 64) {  // warp-uniform, last key block only: zero-filled tail keys contribute nothing
@@ -297,7 +300,7 @@ constexpr int DKV_SMEM = 2 * AB_T128 /*K, V*/ + 2 * DKV_STAGES * AB_T64 /*Q, dO*
                          2 * 128 * 4 /*lse2 | Dsum of a query block, x2*/ + 1024 + 256;
 constexpr uint32_t DKV_TM_ST = 0, DKV_TM_DPT = 64, DKV_TM_DV = 128, DKV_TM_DK = 192, DKV_TMEM_COLS = 256;
 
-template <bool UNI>
+template <bool UNI, int POLY>
 __global__ void __launch_bounds__(AB_THREADS, 2)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_constant__ CUtensorMap tm_q64,
                     const __grid_constant__ CUtensorMap tm_do64, const float* __restrict__ lse2,
@@ -453,10 +456,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv128, const __grid_c
           float x0, x1, x2, x3;
           unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(rs[c]), __uint_as_float(rs[c + 1])), sl2_2, l4.x), x0, x1);
           unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(rs[c + 2]), __uint_as_float(rs[c + 3])), sl2_2, l4.y), x2, x3);
-          p[sub * 16 + c] = ex2_approx(x0);
-          p[sub * 16 + c + 1] = ex2_approx(x1);
-          p[sub * 16 + c + 2] = ex2_approx(x2);
-          p[sub * 16 + c + 3] = ex2_approx(x3);
+          if ((c >> 1) < POLY) ex2_poly3_x2(x0, x1, p[sub * 16 + c], p[sub * 16 + c + 1]);
+          else { p[sub * 16 + c] = ex2_approx(x0); p[sub * 16 + c + 1] = ex2_approx(x1); }
+          if ((c >> 1) + 1 < POLY) ex2_poly3_x2(x2, x3, p[sub * 16 + c + 2], p[sub * 16 + c + 3]);
+          else { p[sub * 16 + c + 2] = ex2_approx(x2); p[sub * 16 + c + 3] = ex2_approx(x3); }
         }
       }
       if (!key_valid) {  // zero-filled tail key rows (last key block only)
@@ -550,25 +553,34 @@ int attention_bwd(const void* qkv, const void* out, const void* dout, float* lse
     rc = make_tmap_bf16(&tm_do64, dout, 3, dims, str, b64);
     if (rc) return rc;
   }
+  using KernT = decltype(&attn_bwd_dq_kernel<true, 0>);
+  static KernT dq_tab[2][3] = {{attn_bwd_dq_kernel<false, 0>, attn_bwd_dq_kernel<false, 2>, attn_bwd_dq_kernel<false, 4>},
+                               {attn_bwd_dq_kernel<true, 0>, attn_bwd_dq_kernel<true, 2>, attn_bwd_dq_kernel<true, 4>}};
+  static KernT dkv_tab[2][3] = {{attn_bwd_dkv_kernel<false, 0>, attn_bwd_dkv_kernel<false, 2>, attn_bwd_dkv_kernel<false, 4>},
+                                {attn_bwd_dkv_kernel<true, 0>, attn_bwd_dkv_kernel<true, 2>, attn_bwd_dkv_kernel<true, 4>}};
   static bool configured = false;
-  static int uni = 0;
+  static int uni = 0, poly = 0;
   if (!configured) {
-    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
-    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
-    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
-    DGS_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    for (int u = 0; u < 2; u++)
+      for (int q = 0; q < 3; q++) {
+        DGS_CUDA_OK(cudaFuncSetAttribute(dq_tab[u][q], cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+        DGS_CUDA_OK(cudaFuncSetAttribute(dkv_tab[u][q], cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+      }
     const char* eu = getenv("DGS_ATT_UNI");
     uni = (eu && eu[0] == '0') ? 0 : 1;  // default since round 2 (measured: r2 first GPU call)
+    const char* ep = getenv("DGS_ATTB_POLY");  // 0 / 1 / 2 = none / 2 of 8 / 4 of 8 pairs on the packed polynomial exp2
+    poly = ep ? atoi(ep) : ATTB_POLY_DEFAULT;
+    poly = poly < 0 ? 0 : poly > 2 ? 2 : poly;
     configured = true;
   }
   DGS_CUDA_OK(launch_pdl(attn_bwd_prep_kernel, dim3(Np, B), dim3(H * 16 < 32 ? 32 : H * 16), 0, st,
                          (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse2, dsum, N, Np, H));
   DGS_POST_LAUNCH();
   dim3 grid(ceil_div(N, 128), H, B);
-  DGS_CUDA_OK(launch_pdl(uni ? attn_bwd_dq_kernel<true> : attn_bwd_dq_kernel<false>, grid, dim3(AB_THREADS), DQ_SMEM, st, tm_qkv128,
+  DGS_CUDA_OK(launch_pdl(dq_tab[uni][poly], grid, dim3(AB_THREADS), DQ_SMEM, st, tm_qkv128,
                          tm_qkv64, tm_do128, (const float*)lse2, (const float*)dsum, (__nv_bfloat16*)dqkv, N, Np, H));
   DGS_POST_LAUNCH();
-  DGS_CUDA_OK(launch_pdl(uni ? attn_bwd_dkv_kernel<true> : attn_bwd_dkv_kernel<false>, grid, dim3(AB_THREADS), DKV_SMEM, st,
+  DGS_CUDA_OK(launch_pdl(dkv_tab[uni][poly], grid, dim3(AB_THREADS), DKV_SMEM, st,
                          tm_qkv128, tm_qkv64, tm_do64, (const float*)lse2, (const float*)dsum, (__nv_bfloat16*)dqkv, N, Np, H));
   DGS_POST_LAUNCH();
   return DGS_OK;

@@ -60,7 +60,7 @@ constexpr float ATT_RESCALE_THRESHOLD = 8.0f;
 // half-precision MUFU forms do not help -- ex2.approx.ftz.bf16x2 compiles to two MUFU.EX2.BF16 (same 135 us, error
 // 2.1e-3 -> 4.5e-3), and an fp16 P against the bf16 V is rejected by the hardware (kind::f16 needs A and B of one
 // format: illegal instruction).
-constexpr int ATT_POLY_DEFAULT = 0;
+constexpr int ATT_POLY_DEFAULT = 4;  // measured r2: 121.3 -> 111.1 us at N = 4098 (profiles/r2_attention_experiments.md)
 
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -226,7 +226,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #ifdef DGS_ATT_PROBE
     const long long probe_begin = clock64();
 #endif
-
     for (int j = 0; j < n_blocks; j++) {
       const int buf = j & 1;
       {
@@ -293,20 +292,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const float moff = m_run * sl2;
       uint32_t pk[32];  // 64 probabilities, two bf16 per word: key 2i in the low half (K order of the MMA's A operand)
       const uint64_t sl2_2 = pack_f32x2(sl2, sl2), moff_2 = pack_f32x2(-moff, -moff);  // x = s * sl2 - moff as FFMA2
+      // POLY_OF_8 of every 8 element PAIRS go through the packed polynomial (FMA pipe), the rest through MUFU ex2
 #pragma unroll
       for (int i = 0; i < 16; i++) {
-        float x0, x1;
+        float x0, x1, p0, p1;
         unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1])), sl2_2, moff_2), x0, x1);
-        const float p0 = (((2 * i) & 7) < POLY_OF_8) ? ex2_poly3(x0) : ex2_approx(x0);
-        const float p1 = (((2 * i + 1) & 7) < POLY_OF_8) ? ex2_poly3(x1) : ex2_approx(x1);
+        if ((i & 7) < POLY_OF_8) ex2_poly3_x2(x0, x1, p0, p1);  // (spreading the polynomial pairs over the 8 measured slower: 117 vs 111 us)
+        else { p0 = ex2_approx(x0); p1 = ex2_approx(x1); }
         pk[i] = pack2_bf16(p0, p1);
       }
 #pragma unroll
       for (int i = 0; i < 16; i++) {
-        float x0, x1;
+        float x0, x1, p0, p1;
         unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1])), sl2_2, moff_2), x0, x1);
-        const float p0 = (((2 * i) & 7) < POLY_OF_8) ? ex2_poly3(x0) : ex2_approx(x0);
-        const float p1 = (((2 * i + 1) & 7) < POLY_OF_8) ? ex2_poly3(x1) : ex2_approx(x1);
+        if ((i & 7) < POLY_OF_8) ex2_poly3_x2(x0, x1, p0, p1);  // (spreading the polynomial pairs over the 8 measured slower: 117 vs 111 us)
+        else { p0 = ex2_approx(x0); p1 = ex2_approx(x1); }
         pk[16 + i] = pack2_bf16(p0, p1);
       }
       {
@@ -374,16 +374,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
 int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st) {
   DGS_REQUIRE(B > 0 && N > 0 && H > 0, "attention: bad shape B=%d N=%d H=%d", B, N, H);
-  {
-    static int k128 = -1, poly128 = 0;  // generation switch: DGS_ATT_K128=0 selects this file's 64-key kernel
-    if (k128 < 0) {
-      const char* e = getenv("DGS_ATT_K128");
-      k128 = (e && e[0] == '0') ? 0 : 1;
-      const char* pe = getenv("DGS_ATT_POLY");
-      poly128 = pe ? atoi(pe) : 0;
-    }
-    if (k128) return attention_fwd_k128(qkv, out, lse2, B, N, H, poly128, st);
-  }
   const int D = H * ATT_HD;
   const int Np = attention_lse_stride(N);
   CUtensorMap tm_q, tm_kv;
@@ -395,21 +385,24 @@ int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, 
   rc = make_tmap_bf16(&tm_kv, qkv, 3, dims, str, box_kv);
   if (rc) return rc;
   static int poly = -1, uni = 0;
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, __nv_bfloat16*, float*, int, int, int);
+  static Kern table[2][5] = {{attention_fwd_kernel<0, false>, attention_fwd_kernel<1, false>, attention_fwd_kernel<2, false>,
+                              attention_fwd_kernel<3, false>, attention_fwd_kernel<4, false>},
+                             {attention_fwd_kernel<0, true>, attention_fwd_kernel<1, true>, attention_fwd_kernel<2, true>,
+                              attention_fwd_kernel<3, true>, attention_fwd_kernel<4, true>}};
   if (poly < 0) {
-    const char* e = getenv("DGS_ATT_POLY");
+    const char* e = getenv("DGS_ATT_POLY");   // pairs of every 8 element pairs on the packed polynomial (0..4 = 0 .. 50 %)
     poly = e ? atoi(e) : ATT_POLY_DEFAULT;
-    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    poly = poly < 0 ? 0 : poly > 4 ? 4 : poly;
+    for (int u = 0; u < 2; u++)
+      for (int q = 0; q < 5; q++)
+        DGS_CUDA_OK(cudaFuncSetAttribute(table[u][q], cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     const char* eu = getenv("DGS_ATT_UNI");
     uni = (eu && eu[0] == '0') ? 0 : 1;  // default since round 2 (measured: r2 first GPU call)
   }
   dim3 grid(ceil_div(N, ATT_BM), H, B);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  auto kern = (uni && poly <= 0) ? attention_fwd_kernel<0, true> : poly == 1 ? attention_fwd_kernel<1> : poly == 2 ? attention_fwd_kernel<2>
-                  : poly >= 3 ? attention_fwd_kernel<3> : attention_fwd_kernel<0>;
+  Kern kern = table[uni][poly];
   DGS_CUDA_OK(launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tm_q, tm_kv, o, lse2, Np, N, H));
   DGS_POST_LAUNCH();
   return DGS_OK;

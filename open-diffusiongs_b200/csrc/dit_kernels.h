@@ -38,8 +38,6 @@ int gemm_bf16_tn_2cta(const void* A, const void* W, int M, int N, int K, const G
 // softmax(Q K^T / sqrt(64)) V over qkv [B, N, 3, H, 64] (bf16) -> out [B, N, H*64] (bf16) (attention_sm100.cu)
 // lse2 (optional, training): [B, H, attention_lse_stride(N)] fp32, log2-domain log-sum-exp of the scaled scores
 int attention_fwd(const void* qkv, void* out, float* lse2, int B, int N, int H, cudaStream_t st);
-// second-generation forward (attention_k128_sm100.cu): 128-key blocks, S MMA N = 128, row sums in registers
-int attention_fwd_k128(const void* qkv, void* out, float* lse2, int B, int N, int H, int poly, cudaStream_t st);
 inline int attention_lse_stride(int N) { return (N + 127) / 128 * 128; }
 // backward (attention_bwd_sm100.cu): dqkv [B, N, 3, H, 64] (bf16) from qkv, out (= O), lse2 and dout [B, N, H*64] (bf16);
 // dsum = scratch [B, H, attention_lse_stride(N)] fp32.  Fills the pad entries of lse2 (+inf) as a side effect.

@@ -39,11 +39,6 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 
 template <int POLY_OF_8>
 __global__ void __launch_bounds__(THREADS, 2)
@@ -168,21 +163,32 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
       const int chunks = (kv_valid + 31) >> 5;           // 32-key chunks that hold at least one valid key
       mbar_wait(s_full, (uint32_t)j & 1);
       tc_fence_after();
-      // ---- pass 1: row max over the block (S stays in tensor memory) ----
+      // ---- pass 1: row max over the block (S stays in tensor memory); two 32-column loads in flight per wait ----
       float mx0 = -INFINITY, mx1 = -INFINITY;
-      for (int c = 0; c < chunks; c++) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_s + (uint32_t)(c * 32), r);
+      for (int c = 0; c < chunks; c += 2) {
+        uint32_t ra[32], rb[32];
+        const bool two = c + 1 < chunks;  // warp-uniform
+        tmem_ld_32x32(t_s + (uint32_t)(c * 32), ra);
+        if (two) tmem_ld_32x32(t_s + (uint32_t)(c * 32 + 32), rb);
         tmem_ld_wait();
         if (last) {
 #pragma unroll
-          for (int i = 0; i < 32; i++)
-            if (c * 32 + i >= kv_valid) r[i] = 0xff800000u;  // -inf: zero-filled / stale tail columns
+          for (int i = 0; i < 32; i++) {
+            if (c * 32 + i >= kv_valid) ra[i] = 0xff800000u;  // -inf: zero-filled / stale tail columns
+            if (c * 32 + 32 + i >= kv_valid) rb[i] = 0xff800000u;
+          }
         }
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(ra[i]), __uint_as_float(ra[i + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(ra[i + 2]), __uint_as_float(ra[i + 3])));
+        }
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(rb[i]), __uint_as_float(rb[i + 1])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(rb[i + 2]), __uint_as_float(rb[i + 3])));
+          }
         }
       }
       const float m_blk = fmaxf(mx0, mx1);
@@ -214,18 +220,14 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         unpack_f32x2(l2, la, lb);
         l2 = pack_f32x2(la * alpha, lb * alpha);
       }
-      // ---- pass 2: p = 2^(s * sl2 - m), row sum, bf16 pack, chunk by chunk ----
+      // ---- pass 2: p = 2^(s * sl2 - m), row sum, bf16 pack; the load of chunk c+1 is in flight while chunk c is
+      //      exponentiated (two register buffers) ----
       const float moff = m_run * sl2;
       const uint64_t sl2_2 = pack_f32x2(sl2, sl2), moff_2 = pack_f32x2(-moff, -moff);
-      for (int c = 0; c < chunks; c++) {
-        uint32_t r[32], pk[16];
-        tmem_ld_32x32(t_s + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
-        if (c == chunks - 1) {
-          // every score of S_j is in registers (or already consumed): S_{j+1} may overwrite the buffer
-          tc_fence_before();
-          mbar_arrive(s_free);
-        }
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(t_s, ra);
+      auto do_chunk = [&](int c, uint32_t (&r)[32]) {
+        uint32_t pk[16];
         if (last) {
 #pragma unroll
           for (int i = 0; i < 32; i++)
@@ -233,14 +235,26 @@ attention_fwd_k128_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid
         }
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-          float x0, x1;
+          float x0, x1, p0, p1;
           unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sl2_2, moff_2), x0, x1);
-          const float p0 = (((2 * i) & 7) < POLY_OF_8) ? ex2_poly3(x0) : ex2_approx(x0);
-          const float p1 = (((2 * i + 1) & 7) < POLY_OF_8) ? ex2_poly3(x1) : ex2_approx(x1);
+          if ((i & 7) < POLY_OF_8) ex2_poly3_x2(x0, x1, p0, p1);
+          else { p0 = ex2_approx(x0); p1 = ex2_approx(x1); }
           l2 = add_f32x2(l2, pack_f32x2(p0, p1));
           pk[i] = pack2_bf16(p0, p1);
         }
         tmem_st_32x16(t_p + (uint32_t)(c * 16), pk);  // 32 keys = 16 packed columns
+      };
+      for (int c = 0; c < chunks; c += 2) {
+        tmem_ld_wait();                                              // chunk c is in ra
+        if (c + 1 < chunks) tmem_ld_32x32(t_s + (uint32_t)(c * 32 + 32), rb);
+        else { tc_fence_before(); mbar_arrive(s_free); }             // every score of S_j has left tensor memory
+        do_chunk(c, ra);
+        if (c + 1 < chunks) {
+          tmem_ld_wait();                                            // chunk c+1 is in rb
+          if (c + 2 < chunks) tmem_ld_32x32(t_s + (uint32_t)(c * 32 + 64), ra);
+          else { tc_fence_before(); mbar_arrive(s_free); }
+          do_chunk(c + 1, rb);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -308,11 +322,14 @@ int attention_fwd_k128(const void* qkv, void* out, float* lse2, int B, int N, in
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_k128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_k128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_k128_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_k128_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DGS_CUDA_OK(cudaFuncSetAttribute(attention_fwd_k128_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   dim3 grid(ceil_div(N, BM), H, B);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  auto kern = poly == 1 ? attention_fwd_k128_kernel<1> : poly >= 2 ? attention_fwd_k128_kernel<2> : attention_fwd_k128_kernel<0>;
+  auto kern = poly == 1 ? attention_fwd_k128_kernel<1> : poly == 2 ? attention_fwd_k128_kernel<2> : poly == 3 ? attention_fwd_k128_kernel<3>
+              : poly >= 4 ? attention_fwd_k128_kernel<4> : attention_fwd_k128_kernel<0>;
   DGS_CUDA_OK(launch_pdl(kern, grid, dim3(THREADS), SMEM_BYTES, st, tm_q, tm_kv, o, lse2, Np, N, H));
   DGS_POST_LAUNCH();
   return DGS_OK;
