@@ -481,6 +481,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)  # every rank samples its own GPU (per-rank clocks / power in the N > 1 line);
+    sampler.start()                     # started BEFORE the warm-up: spawning nvidia-smi right before the timed region cost the first timed step 5 ms (r2, N = 2)
     for _ in range(args.warmup):
         img = step(devb)
     # N > 1: the clocks / power of a box that just went from idle to N busy GPUs settle over the first ~100 ms (r1 SCALE:
@@ -491,8 +493,7 @@ def main():
     barrier()
 
     # ---- timed region 1: inputs resident in HBM, per-step CUDA events, L2 flushed between steps ----
-    sampler = ClockSampler(local_rank)  # every rank samples its own GPU (per-rank clocks / power in the N > 1 line)
-    sampler.start()
+
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = L.dgs_kernel_launch_count()
     barrier()

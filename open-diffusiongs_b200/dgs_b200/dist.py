@@ -29,6 +29,24 @@ def init_from_env(backend=None, device=None):
     return dist.get_rank(), dist.get_world_size()
 
 
+def gradient_group(max_ctas=None):
+    """Optional communicator for the gradient all-reduce alone, with NCCL's CTA count capped (DGS_NCCL_MAX_CTAS > 0).  The
+    collective runs UNDER the backward (overlapped per block), so its kernels compete with the persistent tcgen05 GEMMs for
+    SMs (weight-gradient GEMMs +1.5 ms per step at 2 GPUs).  Measured at 2 x B200, batch 4 per GPU (r2, gpurun call 14):
+    cap 2 / 4 / 8 / 16 / none = 107.7 / 106.2 / 102.4 / 102.6 / 101.3 ms per step -- a slower exchange overlaps MORE kernels
+    and costs more than it frees, so the default is NO cap (returns None = the default group)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or dist.get_backend() != "nccl":
+        return None
+    if max_ctas is None:
+        max_ctas = int(os.environ.get("DGS_NCCL_MAX_CTAS", "0"))
+    if max_ctas <= 0:
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = max_ctas
+    opts.config.min_ctas = 1
+    return dist.new_group(backend="nccl", pg_options=opts)
+
+
 def max_over_ranks(value: float, device="cpu") -> float:
     """Device-time aggregation rule of bench.py: a multi-GPU time is the MAX over ranks."""
     t = torch.tensor([value], dtype=torch.float64, device=device)

@@ -16,7 +16,7 @@ import contextlib
 import torch.distributed as dist
 
 from ._lib import DitBwdOpts, DitGrads, DitOutGrads, DitWeightsT, check
-from .dist import GradArena
+from .dist import GradArena, gradient_group
 
 
 def _stream(dev):
@@ -77,6 +77,7 @@ class DitTrainer:
         self._micro = 0           # backward passes since the last optimizer step
         self._reduced = False     # the overlapped all-reduce of this step has been issued
         self._events = None
+        self._group = gradient_group()  # CTA-capped communicator for the gradient exchange (None: default group / 1 rank)
         self._grads = self._grad_struct()
         self.anchor = torch.zeros(1, device=dev, requires_grad=True)  # makes autograd call our backward
         model._trainer = self
@@ -212,7 +213,7 @@ class DitTrainer:
 
             def gate(block):  # side stream: wait until that block's (or, for the rest, every) gradient is final
                 check(L.dgs_stream_wait_event(side, ev[n if block is None else block]))
-            self.arena.allreduce_issue_(gate=gate, sync_main=False)
+            self.arena.allreduce_issue_(group=self._group, gate=gate, sync_main=False)
             self._reduced = True
 
     def optimizer_step(self, allreduce=True):
@@ -232,7 +233,7 @@ class DitTrainer:
         if self._reduced:          # issued bucket by bucket during the backward; only the tail can still be in flight
             gscale *= self.arena.allreduce_wait_(scale=False)
         elif allreduce and self._world() > 1:
-            self.arena.allreduce_issue_()
+            self.arena.allreduce_issue_(group=self._group)
             gscale *= self.arena.allreduce_wait_(scale=False)
         self._reduced = False
         norm = scale = None
