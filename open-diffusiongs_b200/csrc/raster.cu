@@ -657,6 +657,143 @@ __global__ void __launch_bounds__(256) emit_open_keys_kernel(Problem pb, GeomSta
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small-scene binning (round 2): when a batch has few view-Gaussians the global machinery above (depth ranking sort, scan,
+// key emission, tile sort: ~12 launches) costs more than the work.  Instead: the projection counts instances per tile,
+// ONE block turns the counts into tile ranges, a fill kernel drops (depth bits, id) into each tile's bucket in arrival
+// order, and every tile sorts its own bucket in shared memory by (depth bits, Gaussian index) -- the reference's order
+// (stable radix sort of tile | depth keys emitted in index order, rasterizer_impl.cu:70-111, 300-308).  point_list and
+// ranges come out exactly as from the global path; the blend kernels do not know the difference.
+// ---------------------------------------------------------------------------------------------
+constexpr int SMALL_TILE_CAP = 4096;      // longest tile list the shared-memory sort takes (32 KB of keys)
+constexpr int SMALL_MAX_N = 1 << 18;      // view-Gaussians
+constexpr int SMALL_MAX_TILES = 1 << 15;  // views * tiles (one block scans them)
+
+// counts[t] -> ranges[t] = [start, end), cursor[t] = start; totals[0] = R, totals[3] = longest list, totals[4..5] = R (64 bit)
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int ntiles, const uint32_t* __restrict__ counts, uint2* __restrict__ ranges,
+                                                         uint2* __restrict__ cursor, uint32_t* __restrict__ totals) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry, s_max;
+  if (threadIdx.x == 0) { s_carry = 0; s_max = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < ntiles; base += 1024) {
+    const int t = base + threadIdx.x;
+    const uint32_t c = t < ntiles ? counts[t] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    uint32_t mx = c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) atomicMax(&s_max, mx);
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t start = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - c;
+    if (t < ntiles) {
+      ranges[t] = make_uint2(start, start + c);
+      cursor[t] = make_uint2(start, 0u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += s_warp[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    totals[0] = s_carry; totals[1] = 0; totals[2] = 0; totals[3] = s_max; totals[4] = s_carry; totals[5] = 0;
+  }
+}
+
+// COUNT: every (view, Gaussian) adds 1 to each tile of its rect.  FILL: it drops one (depth bits, id) record into each of
+// those tiles at the tile's cursor.  Rects below 32 tiles are walked by their own thread; larger ones (a few big splats
+// would otherwise serialise a thread for hundreds of atomics) lane-parallel by the whole warp, one after the other.
+template <bool FILL>
+__global__ void __launch_bounds__(256) tile_count_fill_kernel(Problem pb, GeomState gs, uint32_t* __restrict__ counts,
+                                                              uint2* __restrict__ cursor, uint32_t* __restrict__ depth_out,
+                                                              uint32_t* __restrict__ id_out) {
+  const int view = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  uint32_t cnt = 0, depth = 0;
+  if (i < pb.P) {
+    const size_t n = (size_t)view * pb.P + i;
+    cnt = gs.tiles[n];
+    if (cnt) {
+      const float4 g = gs.g0[n];
+      tile_rect(g.x, g.y, __float_as_int(g.w), pb.gx, pb.gy, x0, y0, x1, y1);
+      depth = __float_as_uint(g.z);
+    }
+  }
+  const size_t tbase = (size_t)view * pb.tiles;
+  auto visit = [&](int tile, uint32_t d, uint32_t id) {
+    if (FILL) {
+      const uint32_t pos = atomicAdd(&cursor[tbase + tile].x, 1u);
+      depth_out[pos] = d;
+      id_out[pos] = id;
+    } else {
+      atomicAdd(counts + tbase + tile, 1u);
+    }
+  };
+  if (cnt && cnt < DUP_COOP_THRESHOLD) {
+    for (int y = y0; y < y1; y++)
+      for (int x = x0; x < x1; x++) visit(y * pb.gx + x, depth, (uint32_t)i);
+  }
+  unsigned big = __ballot_sync(0xffffffffu, cnt >= DUP_COOP_THRESHOLD);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+    const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
+    const uint32_t bd = __shfl_sync(0xffffffffu, depth, src);
+    const uint32_t bid = (uint32_t)__shfl_sync(0xffffffffu, i, src);
+    const int w = bx1 - bx0, area = w * (by1 - by0);
+    for (int t = lane; t < area; t += 32) visit((by0 + t / w) * pb.gx + bx0 + t % w, bd, bid);
+  }
+}
+
+// one CTA per (view, tile): bitonic sort of the bucket's 64-bit (depth bits << 32 | id) keys in shared memory
+__global__ void __launch_bounds__(256) tile_sort_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ depth_in,
+                                                        const uint32_t* __restrict__ id_in, uint32_t* __restrict__ point_list) {
+  extern __shared__ unsigned long long s_key[];
+  const uint2 r = ranges[blockIdx.x];
+  const int n = (int)(r.y - r.x);
+  if (n == 0) return;
+  if (n == 1) {
+    if (threadIdx.x == 0) point_list[r.x] = id_in[r.x];
+    return;
+  }
+  int m = 2;
+  while (m < n) m <<= 1;
+  for (int k = threadIdx.x; k < m; k += blockDim.x)
+    s_key[k] = k < n ? (((unsigned long long)depth_in[r.x + k] << 32) | id_in[r.x + k]) : ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= m; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int k = threadIdx.x; k < (m >> 1); k += blockDim.x) {
+        const int lo = ((k / stride) * stride << 1) + (k % stride), hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long a = s_key[lo], b = s_key[hi];
+        if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int k = threadIdx.x; k < n; k += blockDim.x) point_list[r.x + k] = (uint32_t)s_key[k];
+}
+
 // K5: tile ranges from the sorted keys (rasterizer_impl.cu:116-138)
 __global__ void tile_ranges_kernel(long long R, const uint32_t* __restrict__ keys, uint2* __restrict__ ranges) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -686,6 +823,24 @@ __device__ __forceinline__ float ex2_mufu(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// Exact footprint of a Gaussian at the alpha >= 1/255 level (round 2): alpha = o exp(power) with
+// power = -0.5 (A dx^2 + C dy^2) - B dx dy;  for a fixed dy the largest power over dx is -0.5 dy^2 det / A, so the pair can
+// only pass the alpha test when dy^2 <= 2 ln(255 o) A / det (and dx^2 <= 2 ln(255 o) C / det).  The blend kernels use these
+// half-extents to skip, per WARP (two pixel rows of the tile), staged list entries that cannot contribute to any of its
+// pixels: a skipped entry is one the reference's own `alpha < 1/255` test rejects for every pixel of the warp, so images,
+// n_contrib, final_T and gradients are unchanged (it still counts as a visited entry).  The sparse regimes spend 85-94 %
+// of their pair evaluations on such rejections.  Margins (0.1 % + 0.01 px) keep the bound conservative against
+// fp32 rounding; a conic that is not positive definite gets +inf (never skipped), an opacity <= 1/255 gets -1 (always).
+__device__ __forceinline__ float2 alpha_extent(float4 q /* A, B, C, opacity */) {
+  const float det = q.x * q.z - q.y * q.y;
+  if (!(q.x > 0.f && q.z > 0.f && det > 0.f)) return make_float2(INFINITY, INFINITY);
+  const float lv = 2.0f * __logf(255.0f * q.w);
+  if (!(lv > 0.f)) return make_float2(-1.f, -1.f);
+  const float s = lv / det;
+  return make_float2(sqrtf(s * q.z) * 1.001f + 0.01f, sqrtf(s * q.x) * 1.001f + 0.01f);  // (x half-extent, y half-extent)
+}
+constexpr float SKIP_WORTH = 13.0f;  // a y half-extent below this can miss at least one warp of a 16-row tile
 
 // Fused image loss (LossComputer.forward's l2 term, diffusionGS/utils/losses.py:280-284): the blend
 // forward accumulates sum (render - target)^2 per sample while the pixel is still in registers, and the blend backward
@@ -724,9 +879,12 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, Geo
   const size_t gbase = (size_t)view * pb.P;
   const size_t pix_g = (size_t)view * pb.W * pb.H + (size_t)y * pb.W + x;
 
-  __shared__ float2 s_xy[TILE_PIX];
+  __shared__ float4 s_xy[TILE_PIX];  // x, y, x half-extent, y half-extent (alpha_extent)
   __shared__ float4 s_co[TILE_PIX];
   __shared__ float4 s_rgb[TILE_PIX];
+  __shared__ uint8_t s_list[TILE_PIX / 32][TILE_PIX];  // per-warp compacted entry indices of a sparse chunk
+  const float wy0 = (float)(ty * TILE + (threadIdx.x >> 5) * 2);  // this warp's first pixel row
+  const float tx0 = (float)(tx * TILE);
 
   bool done = !inside;
   float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
@@ -739,40 +897,76 @@ __global__ void __launch_bounds__(TILE_PIX) blend_forward_kernel(Problem pb, Geo
     done = (cb >> 31) != 0;
     last = im.n_contrib[pix_g];
   }
+  // visits before this kernel's list: 0, or (phase B) the phase-A list length, which every unfinished pixel has visited fully
+  const uint32_t contrib0 = (MODE == 2) ? (im.ranges[tile_g].y - im.ranges[tile_g].x) : 0u;
   int todo = (int)(range.y - range.x);
   for (uint32_t start = range.x; start < range.y; start += TILE_PIX, todo -= TILE_PIX) {
     if (__syncthreads_count(done) == TILE_PIX) break;
     const uint32_t e = start + threadIdx.x;
+    int small = 0;
     if (e < range.y) {
       const size_t g = gbase + point_list[e];
       const float4 a0 = gs.g0[g];
-      s_xy[threadIdx.x] = make_float2(a0.x, a0.y);
-      s_co[threadIdx.x] = conic_log2(gs.g1[g]);
+      const float4 q = gs.g1[g];
+      const float2 ext = alpha_extent(q);
+      s_xy[threadIdx.x] = make_float4(a0.x, a0.y, ext.x, ext.y);
+      s_co[threadIdx.x] = conic_log2(q);
       s_rgb[threadIdx.x] = gs.g2[g];
+      small = ext.y < SKIP_WORTH;
     }
-    __syncthreads();
+    const int use_skip = __syncthreads_or(small);  // dense chunks (every footprint covers the tile) keep the plain loop
     const int nb = min(TILE_PIX, todo);
-    // Branch-free body (the reference's three `continue`s become predicates): every lane evaluates every staged entry
+    // Sparse chunks: every warp first compacts the staged entries whose footprint can reach its two pixel rows (and the
+    // tile's 16 columns) into its own index list -- 8 tests per lane, ballot-compacted, order preserved -- and then runs the
+    // SAME branch-free body over that list only.  A dropped entry is one the alpha test rejects for every pixel of the warp.
+    int nw = nb;
+    if (use_skip) {
+      const int w_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
+      int cnt = 0;
+#pragma unroll
+      for (int r = 0; r < TILE_PIX / 32; r++) {
+        const int j = r * 32 + lane_;
+        bool hit = false;
+        if (j < nb) {
+          const float4 xy = s_xy[j];
+          const float dyc = xy.y - wy0, dxc = xy.x - tx0;
+          hit = !(dyc > 1.0f + xy.w || dyc < -xy.w || dxc > 15.0f + xy.z || dxc < -xy.z);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) s_list[w_][cnt + __popc(m & ((1u << lane_) - 1u))] = (uint8_t)j;
+        cnt += __popc(m);
+      }
+      nw = cnt;
+      __syncwarp();
+    }
+    // Branch-free body (the reference's three `continue`s become predicates): every lane evaluates every listed entry
     // until its whole warp is done; ~28 instructions per (pixel, entry) pair instead of 24 (rejected) / 54 (blended).
-    for (int j = 0; j < nb; j++) {
-      if ((j & 3) == 0 && __all_sync(0xffffffffu, done)) break;
-      const float2 xy = s_xy[j];
+    // `contributor` (entries visited before the pixel was done, forward.cu:333) is positional: entry j of this chunk is
+    // visit number cbase + j + 1 whether or not the warp evaluated the entries before it.
+    const uint32_t cbase = contrib0 + (start - range.x);
+    const uint8_t* lst = s_list[threadIdx.x >> 5];
+    for (int k = 0; k < nw; k++) {
+      if ((k & 3) == 0 && __all_sync(0xffffffffu, done)) break;
+      const int j = use_skip ? (int)lst[k] : k;
+      const float4 xy = s_xy[j];
       const float4 co = s_co[j];
       const float4 col = s_rgb[j];
       const float dx = xy.x - pxf, dy = xy.y - pyf;
       const float power2 = pair_power2(co, dx, dy);
       const float alpha = fminf(0.99f, co.w * ex2_mufu(power2));
-      contributor += done ? 0u : 1u;
+      const uint32_t visit = cbase + (uint32_t)j + 1u;
       bool ok = !done && power2 <= 0.0f && alpha >= ALPHA_MIN;
       const float test_T = T * (1 - alpha);
       const bool sat = ok && test_T < T_EPS;
+      contributor = sat ? visit : contributor;
       done |= sat;
       ok = ok && !sat;
       const float w = ok ? alpha * T : 0.f;
       C0 = fmaf(col.x, w, C0); C1 = fmaf(col.y, w, C1); C2 = fmaf(col.z, w, C2);
       T = ok ? test_T : T;
-      last = ok ? contributor : last;
+      last = ok ? visit : last;
     }
+    if (!done) contributor = cbase + (uint32_t)nb;  // every entry of the chunk was visited (an early break needs all done)
   }
   int unfinished = 0;
   if (MODE == 1) {
@@ -858,12 +1052,15 @@ __global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(Problem pb, Ge
   const size_t pid = (size_t)y * pb.W + x;
   const size_t plane = (size_t)pb.W * pb.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float wy0 = (float)(ty * TILE + warp * 2);  // this warp's first pixel row
+  const float tx0 = (float)(tx * TILE);
 
   __shared__ uint32_t s_id[BWD_CHUNK];
-  __shared__ float2 s_xy[BWD_CHUNK];
+  __shared__ float4 s_xy[BWD_CHUNK];  // x, y, x half-extent, y half-extent (alpha_extent)
   __shared__ float4 s_co[BWD_CHUNK];
   __shared__ float4 s_rgb[BWD_CHUNK];
   __shared__ float s_acc[BWD_CHUNK][9];  // CTA-level partial sums, 9 components per staged Gaussian
+  __shared__ uint8_t s_list[TILE_PIX / 32][BWD_CHUNK];  // per-warp compacted slot indices
   __shared__ uint32_t s_max;
 
   const float T_final = inside ? im.final_T[ibase + pid] : 0.f;
@@ -911,18 +1108,40 @@ __global__ void __launch_bounds__(TILE_PIX) blend_backward_kernel(Problem pb, Ge
       const size_t g = gbase + id;
       s_id[threadIdx.x] = id;
       const float4 a0 = gs.g0[g];
-      s_xy[threadIdx.x] = make_float2(a0.x, a0.y);
-      s_co[threadIdx.x] = gs.g1[g];
+      const float4 q = gs.g1[g];
+      const float2 ext = alpha_extent(q);
+      s_xy[threadIdx.x] = make_float4(a0.x, a0.y, ext.x, ext.y);
+      s_co[threadIdx.x] = q;
       s_rgb[threadIdx.x] = gs.g2[g];
     }
     for (int t = threadIdx.x; t < nb * 9; t += TILE_PIX) (&s_acc[0][0])[t] = 0.f;
     __syncthreads();
-    for (int j = 0; j < nb; j++) {
+    // per-warp compaction of the staged slots whose footprint can reach this warp's pixels (see alpha_extent and the
+    // forward kernel); 2 tests per lane, order preserved
+    int nw = 0;
+    {
+#pragma unroll
+      for (int r = 0; r < BWD_CHUNK / 32; r++) {
+        const int j = r * 32 + lane;
+        bool hit = false;
+        if (j < nb) {
+          const float4 xy = s_xy[j];
+          const float dyc = xy.y - wy0, dxc = xy.x - tx0;
+          hit = !(dyc > 1.0f + xy.w || dyc < -xy.w || dxc > 15.0f + xy.z || dxc < -xy.z);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) s_list[warp][nw + __popc(m & ((1u << lane) - 1u))] = (uint8_t)j;
+        nw += __popc(m);
+      }
+      __syncwarp();
+    }
+    for (int k = 0; k < nw; k++) {
+      const int j = (int)s_list[warp][k];
       const uint32_t pos = (uint32_t)(top - j);  // 0-based position in the tile list
       float g_c0 = 0.f, g_c1 = 0.f, g_c2 = 0.f, g_mx = 0.f, g_my = 0.f, g_ca = 0.f, g_cb = 0.f, g_cc = 0.f, g_op = 0.f;
       bool active = false;
+      const float4 xy = s_xy[j];
       if (pos < last) {
-        const float2 xy = s_xy[j];
         const float dx = xy.x - pxf, dy = xy.y - pyf;
         const float4 co = s_co[j];
         const float power2 = pair_power2(conic_log2(co), dx, dy);  // same bits as the forward's decision
@@ -1268,6 +1487,15 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
   GeomState gs = GeomState::carve(gbuf, pb.NV, pb.P, nullptr);
   ImgState im = ImgState::carve(ibuf, pb.NV, pb.W, pb.H, nullptr);
 
+  // small scenes: try the per-tile path first (decided after the one host sync, when the longest tile list is known)
+  const size_t ntiles_all = (size_t)pb.NV * pb.tiles;
+  static int small_on = -1;
+  if (small_on < 0) {
+    const char* e = getenv("DGS_RASTER_SMALL");
+    small_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool small_try = small_on && N <= (size_t)SMALL_MAX_N && ntiles_all <= (size_t)SMALL_MAX_TILES;
+  if (small_try) DGS_CUDA_OK(cudaMemsetAsync(im.tile_open, 0, ntiles_all * sizeof(uint32_t), st));
   if (build_cams) {
     build_cameras_kernel<<<ceil_div(pb.NV, 64), 64, 0, st>>>(pb.NV, c2w, fxfycxcy, pb.W, pb.H, gs.cams);
   } else {
@@ -1279,6 +1507,53 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
     ProfScope ps(st, PROF_RASTER_PROJECT);
     project_kernel<<<pgrid, 256, 0, st>>>(pb, gs, radii);
     DGS_LAUNCH_OK(st, debug);
+  }
+  if (small_try) {
+    uint32_t tot[6] = {0, 0, 0, 0, 0, 0};
+    {
+      ProfScope ps(st, PROF_RASTER_SCAN);
+      tile_count_fill_kernel<false><<<pgrid, 256, 0, st>>>(pb, gs, im.tile_open, nullptr, nullptr, nullptr);
+      DGS_LAUNCH_OK(st, debug);
+      tile_scan_kernel<<<1, 1024, 0, st>>>((int)ntiles_all, im.tile_open, im.ranges, im.ranges_b, gs.totals);
+      DGS_LAUNCH_OK(st, debug);
+      DGS_CUDA_OK(cudaMemcpyAsync(tot, gs.totals, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      DGS_CUDA_OK(cudaStreamSynchronize(st));  // the one host sync of the batch
+    }
+    if (tot[3] <= (uint32_t)SMALL_TILE_CAP) {
+      const long long R = (long long)tot[0];
+      *R_out = R;
+      chunk_R[0] = R;
+      chunk_R[1] = 0;
+      size_t bbytes = 0;
+      BinState::carve(nullptr, R, &bbytes);
+      void* bbuf = bin_alloc(bbytes, bin_user);
+      if (!bbuf) { set_error("binning allocator returned NULL"); return DGS_ERR_ALLOC; }
+      BinState bs = BinState::carve(bbuf, R, nullptr);
+      if (R > 0) {
+        {
+          ProfScope ps(st, PROF_RASTER_EMIT);
+          tile_count_fill_kernel<true><<<pgrid, 256, 0, st>>>(pb, gs, nullptr, im.ranges_b, bs.keys_in, bs.vals_in);
+          DGS_LAUNCH_OK(st, debug);
+        }
+        {
+          ProfScope ps(st, PROF_RASTER_SORT);
+          int cap = 2;
+          while (cap < (int)tot[3]) cap <<= 1;
+          static bool configured = false;
+          if (!configured) {
+            DGS_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_TILE_CAP * 8));
+            configured = true;
+          }
+          tile_sort_kernel<<<(unsigned)ntiles_all, 256, (size_t)cap * 8, st>>>(im.ranges, bs.keys_in, bs.vals_in, bs.point_list);
+          DGS_LAUNCH_OK(st, debug);
+        }
+      }
+      ProfScope ps(st, PROF_RASTER_BLEND_FWD);
+      blend_forward_kernel<0><<<(unsigned)ntiles_all, TILE_PIX, 0, st>>>(pb, gs, im, bs.point_list, out_color, mse);
+      DGS_LAUNCH_OK(st, debug);
+      return DGS_OK;
+    }
+    // a tile list longer than the shared-memory sort takes: continue on the global path (the projection's outputs stand)
   }
   {
     ProfScope ps(st, PROF_RASTER_SCAN);  // per-view depth ranking + instance offsets in rank order

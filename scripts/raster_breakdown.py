@@ -13,7 +13,7 @@ for p in (ROOT, os.path.join(ROOT, "open-diffusiongs_b200")):
 from dgs_b200 import _lib, raster, synth  # noqa: E402
 
 DEV = "cuda:0"
-CASES = [(10000, 256, 1, "trained"), (10000, 256, 1, "fine"), (50000, 256, 8, "fine"), (500000, 256, 8, "fine"),
+CASES = [(262146, 256, 4, "init"), (1000000, 512, 8, "fine"), (10000, 256, 1, "trained"), (10000, 256, 1, "fine"), (50000, 256, 8, "fine"), (500000, 256, 8, "fine"),
          (500000, 1024, 8, "fine"), (2000000, 512, 8, "fine"), (50000, 256, 8, "trained"), (500000, 512, 8, "trained")]
 
 

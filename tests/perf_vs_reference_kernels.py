@@ -49,13 +49,15 @@ def case(ref, P, res, V, dist, iters):
     c2w_t, fx_t = T(c2w[None]), T(fx[None])
     out = {}
 
+    cache = {}  # grow-only arenas re-used call after call, as dgs_b200.renderer.Renderer does (r1 timed the allocator too)
+
     def ours_fwd():
-        return raster.render_batch_forward(*raw, res, res, c2w_t, fx_t)
+        return raster.render_batch_forward(*raw, res, res, c2w_t, fx_t, arena_cache=cache)
     img, state = ours_fwd()
     R = state["R"]
     gimg = torch.randn_like(img)
     t_f = timeit(lambda: ours_fwd(), iters)
-    t_fb = timeit(lambda: raster.render_batch_backward(ours_fwd()[1], gimg), iters)
+    t_fb = timeit(lambda: raster.render_batch_backward(ours_fwd()[1], gimg, arena_cache=cache), iters)
     npix = res * res
     b_fwd = 159 * P * V + 84 * R + 20 * npix * V
     b_bwd = 263 * P * V + 76 * R + 20 * npix * V

@@ -173,7 +173,7 @@ def test_gradient_accumulation_is_the_mean_of_micro_batches():
     m1, t1, _ = _model_and_inputs(clip=0.0, lr=1e-3, accumulate_grad_batches=2)
     _backward_once(m1, t1, inp, seed=1)
     _backward_once(m1, t1, inp, seed=2)
-    assert rel(t1._accum, g1 + g2) < 1e-6
+    assert rel(t1._accum, g1 + g2) < 1e-5  # split-K weight gradients add their partial sums in arrival order
     # one AdamW step from zero moments: update = -lr * sign-ish(mean grad); compare against a single step on the mean
     t1.optimizer_step(allreduce=False)
     t0.arena.flat.copy_((g1 + g2) / 2)
