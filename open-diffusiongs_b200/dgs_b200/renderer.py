@@ -148,6 +148,106 @@ class GaussianModel:
         return self._features_dc
 
 
+    # ---- post-processing after the sampler loop: gs_core.py:386-475 filters, 577-713 PLY export ----
+    def to(self, device):
+        for k in ("_xyz", "_features_dc", "_features_rest", "_scaling", "_rotation", "_opacity"):
+            v = getattr(self, k)
+            if v is not None:
+                setattr(self, k, v.to(device))
+        return self
+
+    def filter(self, valid_mask):  # gs_core.py:394-403
+        for k in ("_xyz", "_features_dc", "_features_rest", "_scaling", "_rotation", "_opacity"):
+            v = getattr(self, k)
+            if v is not None and (k != "_features_rest" or self.sh_degree > 0):
+                setattr(self, k, v[valid_mask])
+        return self
+
+    def crop(self, crop_bbx=(-1, 1, -1, 1, -1, 1)):  # gs_core.py:406-419
+        x0, x1, y0, y1, z0, z1 = crop_bbx
+        p = self._xyz
+        bad = (p[:, 0] < x0) | (p[:, 0] > x1) | (p[:, 1] < y0) | (p[:, 1] > y1) | (p[:, 2] < z0) | (p[:, 2] > z1)
+        return self.filter(~bad)
+
+    def prune(self, opacity_thres=0.05):  # gs_core.py:421-425
+        return self.filter(self.get_opacity.squeeze(1) > opacity_thres)
+
+    def prune_by_nearfar(self, cam_origins, nearfar_percent=(0.01, 0.99)):  # gs_core.py:427-461
+        assert len(nearfar_percent) == 2 and 0 <= nearfar_percent[0] < nearfar_percent[1] <= 1
+        dev = self._xyz.device
+        dists = torch.cdist(self._xyz[None], cam_origins[None].to(dev))[0]               # [points, cams]
+        pct = torch.quantile(dists, torch.tensor(nearfar_percent).to(dev), dim=0)        # [2, cams]
+        reject = ((dists < pct[0:1, :]) | (dists > pct[1:2, :])).any(dim=1)
+        return self.filter(~reject)
+
+    def apply_all_filters(self, opacity_thres=0.05, crop_bbx=(-1, 1, -1, 1, -1, 1), cam_origins=None,
+                          nearfar_percent=(0.005, 1.0)):  # gs_core.py:463-475
+        self.prune(opacity_thres)
+        if crop_bbx is not None:
+            self.crop(crop_bbx)
+        if cam_origins is not None:
+            self.prune_by_nearfar(cam_origins, nearfar_percent)
+        return self
+
+    def construct_dtypes(self, use_fp16=False, enable_gs_viewer=True):  # gs_core.py:578-633
+        if use_fp16:
+            raise NotImplementedError("fp16 PLY: the reference builds 'f2' properties, which plyfile (and the PLY format) cannot write")
+        names = ["x", "y", "z"]
+        l = [(n, "f4") for n in names] + [(n, "u1") for n in ("red", "green", "blue")]
+        l += [(f"f_dc_{i}", "f4") for i in range(self._features_dc.shape[1] * self._features_dc.shape[2])]
+        if enable_gs_viewer:
+            assert self.sh_degree <= 3, "GS viewer only supports SH up to degree 3"
+            l += [(f"f_rest_{i}", "f4") for i in range(((3 + 1) ** 2 - 1) * 3)]
+        elif self.sh_degree > 0:
+            l += [(f"f_rest_{i}", "f4") for i in range(self._features_rest.shape[1] * self._features_rest.shape[2])]
+        l.append(("opacity", "f4"))
+        l += [(f"scale_{i}", "f4") for i in range(self._scaling.shape[1])]
+        l += [(f"rot_{i}", "f4") for i in range(self._rotation.shape[1])]
+        return l
+
+    def save_ply(self, path, use_fp16=False, enable_gs_viewer=True, color_code=False, filter_mask=None):
+        """gs_core.py:637-713: xyz, 8-bit RGB (from the SH DC term), f_dc, f_rest (padded to degree 3 for the viewers),
+        raw opacity / log-scale / rotation, one binary little-endian `vertex` element -- the file plyfile's
+        PlyData([PlyElement.describe(elements, "vertex")]).write(path) produces; written with numpy (plyfile is not
+        installed here)."""
+        import os
+
+        import numpy as np
+        if color_code:
+            raise NotImplementedError("color_code=True needs matplotlib's viridis colour map (visualisation, out of scope)")
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        xyz = self._xyz.detach().cpu().numpy()
+        f_dc = self._features_dc.detach().transpose(1, 2).flatten(start_dim=1).contiguous().cpu().numpy()
+        rgb = ((f_dc * 0.28209479177387814 + 0.5) * 255.0).clip(0.0, 255.0).astype(np.uint8)  # SH2RGB, gs_core.py:252
+        opac = self._opacity.detach().cpu().numpy()
+        scale = (torch.log(self.get_scaling) if self.scaling_modifier is not None else self._scaling).detach().cpu().numpy()
+        rot = self._rotation.detach().cpu().numpy()
+        f_rest = None
+        if self.sh_degree > 0:
+            f_rest = self._features_rest.detach().transpose(1, 2).flatten(start_dim=1).contiguous().cpu().numpy()
+        if enable_gs_viewer:
+            full = 3 * ((3 + 1) ** 2 - 1)
+            pad = np.zeros((xyz.shape[0], full), np.float32)
+            if f_rest is not None:
+                pad[:, :f_rest.shape[1]] = f_rest
+            f_rest = pad
+        dtype = self.construct_dtypes(use_fp16, enable_gs_viewer)
+        cols = [xyz, rgb, f_dc] + ([f_rest] if f_rest is not None else []) + [opac, scale, rot]
+        attributes = np.concatenate([c.astype(np.float32) for c in cols], axis=1)
+        if filter_mask is not None:
+            attributes = attributes[np.asarray(filter_mask)]
+        elements = np.empty(attributes.shape[0], dtype=dtype)
+        for i, (name, _) in enumerate(dtype):
+            elements[name] = attributes[:, i]
+        ply_type = {"f4": "float", "u1": "uchar"}
+        header = ["ply", "format binary_little_endian 1.0", f"element vertex {elements.shape[0]}"]
+        header += [f"property {ply_type[t]} {n}" for n, t in dtype] + ["end_header"]
+        with open(path, "wb") as f:
+            f.write(("\n".join(header) + "\n").encode("ascii"))
+            f.write(elements.astype(elements.dtype.newbyteorder("<")).tobytes())
+        return path
+
+
 class Renderer(nn.Module):
     def __init__(self, config):
         super().__init__()

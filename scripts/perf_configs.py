@@ -37,6 +37,12 @@ CONFIGS = {  # name: (scene, H = W, V_render in training, training batch used he
 }
 
 
+# --yaml: the per-GPU batch sizes of the shipped training yamls (data.batch_size: diffusionGS_rel.yaml:14 = 4,
+# diffusionGS_rel_512.yaml:14 = 4, diffusionGS_scene.yaml:16 = 24, diffusionGS_scene_512.yaml:16 = 12), run with activation
+# recompute (the reference checkpoints every block) as (micro-batch, micro-batches per optimizer step)
+YAML_BATCH = {"obj-256": (4, 1), "obj-512": (2, 2), "scene-256": (8, 3), "scene-512": (4, 3)}
+
+
 def f_fwd(n):
     return LAYERS * (24 * n * D * D + 4 * n * n * D + 12 * D * D) + 2 * (n - 2) * D * (576 + 896)
 
@@ -116,6 +122,46 @@ def main():
                    mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
         print(json.dumps(row), flush=True)
         rows.append(row)
+        if "--yaml" in sys.argv:
+            # ---- training step at the yaml batch size: recompute + micro-batches with gradient accumulation ----
+            from dgs_b200 import losses
+            from dgs_b200.train import DitTrainer
+            mb, k = YAML_BATCH[name]
+            torch.manual_seed(0)
+            cfg = dict(patch_size=PATCH, ray_pe_type="plk" if scene else "relative_plk")
+            m2 = (DGSDenoiserScene if scene else DGSDenoiser)(cfg).to(DEV)
+            tr = DitTrainer(m2, lr=1e-5, betas=(0.9, 0.99), eps=1e-8, clip=0.5, recompute=True, accumulate_grad_batches=k,
+                            ema_decay=0.9999)
+            m2.train()
+            bts = [make_inputs(mb, res, v_render, seed=10 + i) for i in range(k)]
+
+            def ystep():
+                tot = 0.0
+                for bt in bts:
+                    out, _ = m2.image_to_gaussians(bt["images"], bt["ray_o"], bt["ray_d"], bt["t"])
+                    res_, _ = losses.fused_render_and_loss(m2, out, bt["c2w"], bt["fx"], res, res, bt["target"])
+                    res_["loss"].backward()
+                    tot = tot + res_["loss"].detach()
+                tr.optimizer_step(allreduce=False)
+                return tot / k
+            torch.cuda.reset_peak_memory_stats()
+            loss = ystep()
+            assert torch.isfinite(loss)
+            ms, fam = timed(ystep, flush, steps=2, warmup=1)
+            dit_ms = sum(v for kk, v in fam.items() if kk.startswith("dit."))
+            row = dict(config=name, mode="train-yaml-batch", batch=mb * k, micro_batch=mb, micro_batches=k, activations="recompute",
+                       res=res, tokens=n_tok, render_views=v_render, ms_per_step=ms, samples_per_s=mb * k * 1e3 / ms, dit_ms=dit_ms,
+                       raster_ms=sum(v for kk, v in fam.items() if kk.startswith("raster.")),
+                       dit_train_tflops_algorithmic=3 * mb * k * f_fwd(n_tok) / dit_ms / 1e9 if dit_ms else None, loss=float(loss),
+                       families=fam, mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
+            print(json.dumps(row), flush=True)
+            rows.append(row)
+            m2._trainer = None
+            del tr, m2, bts
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            continue
         if not train:
             continue
         # ---- training step ----
