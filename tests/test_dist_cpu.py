@@ -85,6 +85,7 @@ def _overlap_worker(rank, world, port, ret):
         arena = dd.GradArena(model)
         arena.flat.fill_(float(rank + 1))
         gated = []
+        os.environ["DGS_AR_BLOCKS_PER_CALL"] = "1"
         arena.allreduce_issue_(gate=gated.append, sync_main=False)   # the overlapped form: one gate per bucket, in issue order
         inv = arena.allreduce_wait_(scale=False)                     # SUM stays in the arena, 1/world goes to the consumer
         ret[rank] = dict(gated=gated, inv=inv, lo=float(arena.flat.min()), hi=float(arena.flat.max()))
@@ -100,3 +101,38 @@ def test_gloo_world2_gated_issue_and_deferred_scale():
     for r in (ret[0], ret[1]):
         assert r["gated"] == [2, 1, 0, None, None]   # blocks in reverse order, then the two non-block buckets
         assert r["inv"] == 0.5 and r["lo"] == r["hi"] == 3.0
+
+
+def _bf16_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      DGS_GRAD_TRANSPORT="bf16", DGS_AR_BLOCKS_PER_CALL="2")
+    dd.init_from_env("gloo")
+    try:
+        from dgs_b200.denoiser import DGSDenoiser
+        torch.manual_seed(0)
+        model = DGSDenoiser(dict(patch_size=8, num_layers=3))
+        arena = dd.GradArena(model)
+        g = torch.Generator().manual_seed(7 + rank)
+        mine = torch.randn(arena.total, generator=g)
+        arena.flat.copy_(mine)
+        plan = arena.reduce_plan()
+        arena.allreduce_mean_()
+        other = torch.randn(arena.total, generator=torch.Generator().manual_seed(7 + (1 - rank)))
+        expect = (mine.bfloat16() + other.bfloat16()).float() / 2      # each rank's values rounded to bf16, summed in bf16
+        err = float((arena.flat - (mine + other) / 2).norm() / ((mine + other) / 2).norm())
+        ret[rank] = dict(plan=[(b, e - s) for b, s, e in plan], err=err,
+                         close=bool(torch.allclose(arena.flat, expect, rtol=2e-2, atol=1e-3)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_bf16_transport_and_grouped_buckets():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_bf16_worker, args=(world, 29617, ret), nprocs=world, join=True)
+    for r in (ret[0], ret[1]):
+        # 3 blocks, 2 per call: {2, 1} gated on block 1, {0} gated on block 0, then the two non-block buckets
+        assert [p[0] for p in r["plan"]] == [1, 0, None, None]
+        assert r["plan"][0][1] == 2 * 18_889_728 and r["plan"][1][1] == 18_889_728
+        assert r["close"] and 1e-4 < r["err"] < 1e-2      # bf16 rounding is visible but small
