@@ -130,7 +130,8 @@ typedef struct {
   float scale_modifier; /* 1.0 when the reference passes scaling_modifier=None */
   float bg[3];          /* (1,1,1) in render_opencv_cam, gs_core.py:880 */
   int debug;
-  int near_log2;        /* 0: one binning pass over all instances.  k > 0: two-phase binning -- phase A bins and blends
+  int near_log2;        /* 0: one binning pass over all instances.  k < 0: adaptive (1/8, or 1/16 when those near lists still
+                           average >= 2048 entries per tile).  k > 0: two-phase binning -- phase A bins and blends
                            only the nearest P >> k Gaussians of every view; if every pixel saturates there (dense scenes)
                            the remaining instances are never emitted or sorted, otherwise phase B continues from the
                            saved per-pixel state.  Same images, final_T, n_contrib and gradients either way. */

@@ -87,8 +87,8 @@ struct GeomState {
     s.offsets = c.take<uint32_t>(N);
     s.open_counts = c.take<uint32_t>(N);
     s.open_offsets = c.take<uint32_t>(N);
-    s.view_meta = c.take<uint32_t>((size_t)NV * 4);
-    s.totals = c.take<uint32_t>(6);
+    s.view_meta = c.take<uint32_t>((size_t)NV * 8);  // two candidate near fractions (adaptive two-phase binning)
+    s.totals = c.take<uint32_t>(8);
     s.cams = c.take<Camera>(NV);
     size_t scan_b = 0, sort_b = 0;
     cub::DeviceScan::InclusiveSum(nullptr, scan_b, s.tiles_sorted, s.offsets, (int)N);
@@ -510,7 +510,7 @@ constexpr int DUP_COOP_THRESHOLD = 32;
 // Two-phase binning bookkeeping: per view, where its near (ranks < Pn) and far instances start in the global scan and
 // in the two compact per-phase buffers; totals[0] = R, totals[1] = R_near.  One block, NV is small.
 __global__ void chunk_meta_kernel(int NV, int P, int Pn, const uint32_t* __restrict__ offsets,
-                                  uint32_t* __restrict__ view_meta, uint32_t* __restrict__ totals) {
+                                  uint32_t* __restrict__ view_meta, uint32_t* __restrict__ totals, int near_slot) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   uint32_t baseA = 0, baseB = 0;
   for (int v = 0; v < NV; v++) {
@@ -524,7 +524,7 @@ __global__ void chunk_meta_kernel(int NV, int P, int Pn, const uint32_t* __restr
     baseB += end - startB;
   }
   totals[0] = baseA + baseB;
-  totals[1] = baseA;
+  totals[near_slot] = baseA;
   totals[2] = 0;
 }
 
@@ -1566,13 +1566,21 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
     DGS_CUDA_OK(cub::DeviceScan::InclusiveSum(gs.scan_temp, gs.scan_bytes, gs.tiles_sorted, gs.offsets, (int)N, st));
   }
   // two-phase binning candidates need the near/far split of the instance counts; it rides on the same single sync
-  const int Pn = (pb.near_log2 > 0) ? (pb.P >> pb.near_log2) : 0;
+  // near_log2 < 0 = adaptive: the splits at 1/8 and 1/16 are both prepared (two 1-thread kernels) and the host picks after
+  // the sync: 1/16 when its near lists are still long enough to saturate the pixels (>= 2048 entries per tile on average:
+  // the dense random-init step, +1.4 % on the bench), 1/8 otherwise (r1: 1/16 costs 35 % at 2 M Gaussians @1024^2)
+  const bool adaptive = pb.near_log2 < 0;
+  const int k_a = adaptive ? 3 : pb.near_log2;
+  int Pn = (k_a > 0) ? (pb.P >> k_a) : 0;
+  const int Pn_b = adaptive ? (pb.P >> 4) : 0;
   const bool may_split = Pn >= 1024;
-  uint32_t tot[6] = {0, 0, 0, 0, 0, 0};
+  const bool two_cands = adaptive && Pn_b >= 1024;
+  uint32_t tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (may_split) {
-    chunk_meta_kernel<<<1, 32, 0, st>>>(pb.NV, pb.P, Pn, gs.offsets, gs.view_meta, gs.totals);
+    chunk_meta_kernel<<<1, 32, 0, st>>>(pb.NV, pb.P, Pn, gs.offsets, gs.view_meta, gs.totals, 1);
+    if (two_cands) chunk_meta_kernel<<<1, 32, 0, st>>>(pb.NV, pb.P, Pn_b, gs.offsets, gs.view_meta + (size_t)pb.NV * 4, gs.totals, 6);
     DGS_LAUNCH_OK(st, debug);
-    DGS_CUDA_OK(cudaMemcpyAsync(tot, gs.totals, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    DGS_CUDA_OK(cudaMemcpyAsync(tot, gs.totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   } else {
     DGS_CUDA_OK(cudaMemcpyAsync(tot, gs.offsets + N - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     DGS_CUDA_OK(cudaMemcpyAsync(tot + 4, gs.totals + 4, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -1585,6 +1593,11 @@ static int run_forward(Problem pb, bool build_cams, const float* c2w, const floa
   }
   const long long R = (long long)tot[0];
   *R_out = R;
+  if (two_cands && (unsigned long long)tot[6] >= 2048ull * (unsigned long long)pb.NV * pb.tiles) {
+    Pn = Pn_b;          // the 1/16 split: its per-view instance offsets are the second view_meta set
+    tot[1] = tot[6];
+    gs.view_meta += (size_t)pb.NV * 4;
+  }
   // phase A must be a real saving: at most half of the instances
   const bool split = may_split && R >= (1ll << 21) && 2ll * tot[1] <= R && tot[1] > 0;
   const long long RA = split ? (long long)tot[1] : R;
@@ -1823,7 +1836,7 @@ static Problem batch_problem(const dgs_render_batch_args* a) {
   Problem pb = make_problem(a->B * a->V, a->V, a->P, a->D, a->M, a->W, a->H, 1, a->scale_modifier);
   pb.means = a->xyz; pb.shs = a->features; pb.opac = a->opacity; pb.scales = a->scaling; pb.rots = a->rotation;
   pb.bg[0] = a->bg[0]; pb.bg[1] = a->bg[1]; pb.bg[2] = a->bg[2];
-  pb.near_log2 = a->near_log2 > 0 ? a->near_log2 : 0;
+  pb.near_log2 = a->near_log2;  // > 0 fixed fraction 1/2^k, 0 single pass, < 0 adaptive (1/8 or 1/16)
   return pb;
 }
 

@@ -151,7 +151,7 @@ def mark_visible(means3D, viewmatrix, projmatrix):
 import os as _os
 
 # two-phase binning: phase A = the nearest 1/2^k of every view's Gaussians (0 = single pass); DGS_RASTER_NEAR_LOG2 overrides
-DEFAULT_NEAR_LOG2 = int(_os.environ.get("DGS_RASTER_NEAR_LOG2", "3"))
+DEFAULT_NEAR_LOG2 = int(_os.environ.get("DGS_RASTER_NEAR_LOG2", "-1"))  # -1 = adaptive: 1/8, or 1/16 for dense scenes
 
 
 def _batch_args(xyz, features, scaling, rotation, opacity, C2W, fxfycxcy, H, W, scale_modifier, debug=False,

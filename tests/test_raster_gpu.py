@@ -384,3 +384,16 @@ def test_two_phase_binning_is_exact(dist, P, expect_phase_b):
     d2 = raster.render_batch_backward(st2, g)
     for a_, b_ in zip(d1, d2):
         assert rel_l2(b_.cpu().numpy(), a_.cpu().numpy()) < 2e-5
+    # adaptive near fraction (near_log2 = -1, the default): 1/16 for the dense scene, 1/8 for the sparse one -- same images
+    img3, st3 = raster.render_batch_forward(*t, H, W, T(c2w), T(fx), near_log2=-1)
+    print(f"[{dist}] adaptive chunks={st3['chunks']}")
+    assert torch.equal(img1, img3)
+    e3 = raster.export_state(B * V, P, W, H, 0, st3["geom"], st3["binning"], st3["img"])
+    assert torch.equal(e1["final_T"], e3["final_T"]) and torch.equal(e1["n_contrib"], e3["n_contrib"])
+    d3 = raster.render_batch_backward(st3, g)
+    for a_, b_ in zip(d1, d3):
+        assert rel_l2(b_.cpu().numpy(), a_.cpu().numpy()) < 2e-5
+    if dist == "init":
+        assert st3["chunks"][0] < st2["chunks"][0]      # the dense scene took the smaller near fraction
+    else:
+        assert st3["chunks"] == st2["chunks"]           # the sparse one stayed at 1/8
