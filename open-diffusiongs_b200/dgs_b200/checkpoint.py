@@ -62,6 +62,8 @@ def load_checkpoint(model, path_or_obj, strict=True, map_location="cpu"):
         raise RuntimeError(f"checkpoint does not match the denoiser: missing {sorted(missing)[:8]} unexpected {sorted(unexpected)[:8]}")
     if getattr(model, "_trainer", None) is not None:   # flat fp32 master arena + bf16 GEMM operands follow the new values
         model._trainer.refresh_weights()               # (updates the packed stacks in place and re-keys them)
+        if model._trainer.ema is not None:             # the EMA restarts from the loaded weights, as EMA.on_train_start's
+            model._trainer.ema.copy_(model._trainer.master)   # copy does in the reference (ema.py:69-72)
     else:
         model._packed = None                           # inference-only model: repack lazily on the next forward
     return meta
