@@ -10,6 +10,10 @@ One "step" = the hot path over one synthetic batch = BASELINE configs[1], the ob
   + the 4-view 256x256 splat render of those Gaussians  (DGSDenoiser.forward, denoiser.py:284-287),
 random-init weights by the reference's init rules, synthetic image/noise, orbit cameras.
 
+N > 1 (round 2): after the denoise region the SAME launch runs 6 training steps at per-GPU batch 4 and 8 with the overlapped NCCL
+gradient all-reduce and again without any, and adds `train: [{samples_per_s, ms_per_step, allreduce_exposed_ms, ...}]` plus
+`per_rank` (every rank's step statistics and clocks) to the line.  NCCL's environment is left as the launcher set it.
+
 Prints ONE JSON line (rank 0).  Keys: the driver contract + `roofline` (dominant kernel, live CUDA-event
 timing through the library's per-family event hooks) + `cpu_baseline` (oracle on the host cores, bounded
 sample) + `e2e` (same metric through the public API with pinned-host inputs, H2D/D2H inside the timed region).
